@@ -1,0 +1,937 @@
+// fcv_engine.cu -- C ABI of the B200 convolution engine (include/folve_b200.h):
+// filter spectra resident in HBM, per-stream device state, the three kernel
+// launches per block, pinned staging and the batched entry points.
+//
+// Replaces the Convproc object behind folve's SoundProcessor
+// (/root/reference/sound-processor.cc:34-145) and the impulse-loading calls of
+// the zita-config loader (/root/reference/zita-config.cc:163,203,252,274,
+// /root/reference/zita-fconfig.cc:78-93).  No CPU fallback: without a usable
+// sm_100 device every entry point fails with FCV_E_CUDA.
+#include "../../include/folve_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fcv_fft.cuh"
+#include "fcv_mac.cuh"
+
+using namespace fcv;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(FCV_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+
+// Forward transform of the current block of every (stream, input channel):
+// fused int/float conversion + de-interleave + zero padding + real FFT, written
+// into ring slot `pt` of the stream's input-spectra ring.
+template <int LOG2N>
+__global__ void __launch_bounds__(fft_threads(LOG2N))
+fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
+                  int ninp, int P, int pt, int in_fmt, int reset_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    constexpr int N = 1 << LOG2N;
+    const int i = blockIdx.x, b = blockIdx.y;
+    const StreamDev s = st[b];
+    const int frames = fv ? fv[b] : N;
+    float2 *row = s.xring + (size_t)(i * P + pt) * N;
+    // per-block maximum mode: the inverse kernel of this block starts from zero
+    if (reset_max && i == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    fwd_body<LOG2N>(sm, tb, s.din, in_fmt, ninp, i, frames, 1.0f, row);
+}
+
+// Forward transform of raw float partitions (filter preparation, K6):
+// src[row][N] -> dst[row][M].
+template <int LOG2N>
+__global__ void __launch_bounds__(fft_threads(LOG2N))
+fwd_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, FftTables tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    constexpr int N = 1 << LOG2N;
+    const size_t r = blockIdx.x;
+    fwd_body<LOG2N>(sm, tb, src + r * N, PCM_F32, 1, 0, N, 1.0f, dst + r * N);
+}
+
+// Inverse transform of every (stream, output channel) with fused DC/Nyquist
+// products, overlap-add, tail save, re-interleave, float/int conversion and
+// running signed maximum.
+template <int LOG2N>
+__global__ void __launch_bounds__(fft_threads(LOG2N))
+inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
+                  const float2 *__restrict__ Y, const MacStep *__restrict__ steps,
+                  const int *__restrict__ group_off, const float2 *__restrict__ H, int group_no,
+                  int nout, int P, int pt, int out_fmt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    __shared__ float red[32];
+    constexpr int N = 1 << LOG2N, Q = N / 2, M = N;
+    constexpr int NT = fft_threads(LOG2N);
+    const int tid = threadIdx.x;
+    const int o = blockIdx.x, b = blockIdx.y;
+    const StreamDev s = st[b];
+    const int frames = fv ? fv[b] : N;
+
+    const float2 *yrow = Y + ((size_t)b * nout + o) * M;
+    for (int e = tid; e < M; e += NT) sm[smem_pad(e)] = __ldcs(&yrow[e]);
+
+    // DC and Nyquist are real bins sharing entry 0: redo their products as two
+    // real multiply-accumulates (the MAC kernel treated the entry as complex).
+    float dc = 0.f, ny = 0.f;
+    if (tid < 32) {
+        const int g = o / group_no, oi = o - g * group_no;
+        for (int t = group_off[g] + tid; t < group_off[g + 1]; t += 32) {
+            const int row = steps[t].row[oi];
+            if (row >= 0) {
+                int slot = pt - steps[t].part;
+                if (slot < 0) slot += P;
+                const float2 x = s.xring[(size_t)(steps[t].inp * P + slot) * M];
+                const float2 h = H[(size_t)row * M];
+                dc = fmaf(x.x, h.x, dc);
+                ny = fmaf(x.y, h.y, ny);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            dc += __shfl_xor_sync(0xffffffffu, dc, d);
+            ny += __shfl_xor_sync(0xffffffffu, ny, d);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) sm[0] = make_float2(dc, ny);
+    __syncthreads();
+
+    inv_body<LOG2N>(sm, tb);
+
+    float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
+    float lmax = 0.0f;
+    for (int n = tid; n < Q; n += NT) {
+        const float2 a = sm[smem_pad(n)];
+        const float2 t = cmulconj(sm[smem_pad(Q + n)], __ldg(&tb.twA[n]));
+        const float2 tl = tail[n];
+        const float y0 = a.x + t.x + tl.x;
+        const float y1 = a.y + t.y + tl.y;
+        tail[n] = make_float2(a.x - t.x, a.y - t.y);
+        const int f0 = 2 * n;
+        pcm_store(s.dout, out_fmt, (size_t)f0 * nout + o, y0);
+        pcm_store(s.dout, out_fmt, (size_t)(f0 + 1) * nout + o, y1);
+        if (f0 < frames) lmax = fmaxf(lmax, y0);
+        if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+    if ((tid & 31) == 0) red[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; w++) lmax = fmaxf(lmax, red[w]);
+        // running maximum is >= 0, positive floats order like their bit patterns
+        if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per-device context: twiddle tables per partition size
+// ---------------------------------------------------------------------------
+struct DeviceCtx {
+    std::mutex mu;
+    bool checked = false;
+    bool ok = false;
+    std::string why;
+    bool have[16] = {};
+    FftTables tab[16];
+    bool attr_set[16] = {};
+};
+static std::mutex g_ctx_mu;
+static std::map<int, DeviceCtx *> g_ctx;
+
+static DeviceCtx *get_ctx(int device) {
+    std::lock_guard<std::mutex> l(g_ctx_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) return it->second;
+    DeviceCtx *c = new DeviceCtx();
+    g_ctx[device] = c;
+    return c;
+}
+
+static int check_device(int device) {
+    DeviceCtx *c = get_ctx(device);
+    std::lock_guard<std::mutex> l(c->mu);
+    if (!c->checked) {
+        c->checked = true;
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            c->why = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        } else if (device < 0 || device >= n) {
+            c->why = "no such CUDA device";
+        } else {
+            cudaDeviceProp p;
+            e = cudaGetDeviceProperties(&p, device);
+            if (e != cudaSuccess) c->why = cudaGetErrorString(e);
+            else if (p.major != 10) {
+                char b[128];
+                snprintf(b, sizeof(b), "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                         p.major, p.minor);
+                c->why = b;
+            } else c->ok = true;
+        }
+    }
+    if (!c->ok) return fail(FCV_E_CUDA, "device %d unusable: %s", device, c->why.c_str());
+    return 0;
+}
+
+template <int LOG2N>
+static int set_attrs() {
+    const int bytes = (int)fft_smem_bytes(LOG2N);
+    CU_TRY(cudaFuncSetAttribute(fwd_stream_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU_TRY(cudaFuncSetAttribute(fwd_raw_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU_TRY(cudaFuncSetAttribute(inv_stream_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return 0;
+}
+
+#define DISPATCH_LOG2N(l2, CALL)                    \
+    switch (l2) {                                   \
+        case 6: { constexpr int L = 6; CALL; } break;   \
+        case 7: { constexpr int L = 7; CALL; } break;   \
+        case 8: { constexpr int L = 8; CALL; } break;   \
+        case 9: { constexpr int L = 9; CALL; } break;   \
+        case 10: { constexpr int L = 10; CALL; } break; \
+        case 11: { constexpr int L = 11; CALL; } break; \
+        case 12: { constexpr int L = 12; CALL; } break; \
+        case 13: { constexpr int L = 13; CALL; } break; \
+        default: return fail(FCV_E_PARAM, "unsupported partition size 2^%d", l2); \
+    }
+
+// Builds (once per device and size) the twiddle tables in double precision.
+static int get_tables(int device, int log2n, FftTables *out) {
+    DeviceCtx *c = get_ctx(device);
+    std::lock_guard<std::mutex> l(c->mu);
+    if (!c->have[log2n]) {
+        const int q = log2n - 1, Q = 1 << q, M = 2 * Q;
+        const double PI = 3.14159265358979323846264338327950288;
+        std::vector<float2> h;
+        size_t offA = 0, offU, offP[3] = {0, 0, 0};
+        h.resize(Q);
+        for (int n = 0; n < Q; n++) {
+            const double a = -2.0 * PI * n / M;
+            h[n] = make_float2((float)cos(a), (float)sin(a));
+        }
+        offU = h.size();
+        h.resize(offU + M);
+        for (int e = 0; e < M; e++) {
+            const int half = e >> q, k = 2 * plan_revinv(q, e & (Q - 1)) + half;
+            const double a = -PI * k / M;
+            h[offU + e] = make_float2((float)cos(a), (float)sin(a));
+        }
+        const int np = plan_npass(q);
+        for (int t = 0; t < np; t++) {
+            const int R = 1 << plan_lr(q, t), S = 1 << plan_ls(q, t), Qt = 1 << plan_lqt(q, t);
+            offP[t] = h.size();
+            if (S > 1) {
+                h.resize(offP[t] + (size_t)(R - 1) * S);
+                for (int k1 = 1; k1 < R; k1++)
+                    for (int u = 0; u < S; u++) {
+                        const double a = -2.0 * PI * (double)u * (double)k1 / (double)Qt;
+                        h[offP[t] + (size_t)(k1 - 1) * S + u] = make_float2((float)cos(a), (float)sin(a));
+                    }
+            }
+        }
+        float2 *d = nullptr;
+        CU_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
+        CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        FftTables tb;
+        tb.twA = d + offA;
+        tb.twU = d + offU;
+        for (int t = 0; t < 3; t++) tb.twP[t] = d + offP[t];
+        c->tab[log2n] = tb;
+        int rc = 0;
+        DISPATCH_LOG2N(log2n, rc = set_attrs<L>());
+        if (rc) return rc;
+        c->have[log2n] = true;
+    }
+    *out = c->tab[log2n];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// filter
+// ---------------------------------------------------------------------------
+struct Pair {
+    bool exists = false;      // a MAC node was created for this pair
+    int link = -1;            // index of the pair whose spectra are used instead
+    std::vector<float> h;     // time domain, npar * fragm, already scaled by 0.5/fragm
+    std::vector<int> row;     // per partition: filter row or -1 (after commit)
+};
+
+struct fcv_filter {
+    std::atomic<int> refs{1};
+    int ninp = 0, nout = 0;
+    unsigned size = 0;
+    int fragm = 0, log2n = 0;
+    int npar = 0;  // partitions zita allocates room for
+    bool committed = false;
+    std::vector<Pair> pairs;  // [inp * nout + out]
+    // after commit
+    int device = -1;
+    int ring = 1;       // depth of the input-spectra ring
+    int nrows = 0;      // non-zero (pair, partition) spectra
+    int active_pairs = 0;
+    int group_no = 1;   // outputs per MAC group
+    int ngroups = 1;
+    int nsteps = 0;
+    float2 *dH = nullptr;
+    MacStep *dsteps = nullptr;
+    int *dgroup_off = nullptr;
+    FftTables tb{};
+    std::vector<MacStep> hsteps;
+    std::vector<int> hgroup_off;
+};
+
+extern "C" int fcv_abi_version(void) { return FCV_ABI_VERSION; }
+extern "C" const char *fcv_last_error(void) { return g_err.c_str(); }
+extern "C" unsigned long long fcv_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int fcv_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(FCV_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+extern "C" fcv_filter *fcv_filter_begin(int ninp, int nout, unsigned size, unsigned fragm) {
+    if (ninp < 1 || ninp > FCV_MAXINP || nout < 1 || nout > FCV_MAXOUT) {
+        fail(FCV_E_PARAM, "inputs/outputs out of range (%d, %d)", ninp, nout);
+        return nullptr;
+    }
+    if (fragm < FCV_MINPART || fragm > FCV_MAXQUANT || (fragm & (fragm - 1))) {
+        fail(FCV_E_PARAM, "fragm %u is not a power of two in [%d, %d]", fragm, FCV_MINPART, FCV_MAXQUANT);
+        return nullptr;
+    }
+    if (size > FCV_MAXSIZE) {
+        fail(FCV_E_PARAM, "size %u exceeds %u", size, (unsigned)FCV_MAXSIZE);
+        return nullptr;
+    }
+    fcv_filter *f = new (std::nothrow) fcv_filter();
+    if (!f) { fail(FCV_E_ALLOC, "out of memory"); return nullptr; }
+    f->ninp = ninp;
+    f->nout = nout;
+    f->size = size;
+    f->fragm = (int)fragm;
+    f->log2n = 0;
+    while ((1u << f->log2n) < fragm) f->log2n++;
+    f->npar = (int)((size + fragm - 1) / fragm);
+    f->pairs.resize((size_t)ninp * nout);
+    return f;
+}
+
+extern "C" int fcv_filter_add(fcv_filter *f, int inp, int out, int step, const float *data, int ind0, int ind1) {
+    if (!f) return fail(FCV_E_PARAM, "null filter");
+    if (f->committed) return fail(FCV_E_STATE, "filter already committed");
+    if (inp < 0 || inp >= f->ninp || out < 0 || out >= f->nout) return fail(FCV_E_PARAM, "bad input/output index");
+    // Convlevel::impdata_write range test: nothing to do if the data lies outside
+    // [0, npar * fragm) -- no MAC node is created in that case either.
+    const long n = (long)ind1 - (long)ind0;
+    const long total = (long)f->npar * f->fragm;
+    const long i0 = -(long)ind0;
+    if (i0 >= n || i0 + total <= 0) return 0;
+    Pair &p = f->pairs[(size_t)inp * f->nout + out];
+    p.exists = true;
+    if (p.link >= 0) return 0;  // linked pairs ignore new data
+    if (!data) return 0;
+    try {
+        if (p.h.empty()) p.h.assign((size_t)total, 0.0f);
+    } catch (...) {
+        return fail(FCV_E_ALLOC, "out of memory");
+    }
+    const float norm = 0.5f / (float)f->fragm;
+    const long j0 = i0 < 0 ? 0 : i0;
+    const long j1 = (i0 + total > n) ? n : i0 + total;
+    for (long j = j0; j < j1; j++) p.h[(size_t)(j - i0)] += norm * data[j * step];
+    return 0;
+}
+
+extern "C" int fcv_filter_link(fcv_filter *f, int inp1, int out1, int inp2, int out2) {
+    if (!f) return fail(FCV_E_PARAM, "null filter");
+    if (inp1 < 0 || inp1 >= f->ninp || out1 < 0 || out1 >= f->nout || inp2 < 0 || inp2 >= f->ninp ||
+        out2 < 0 || out2 >= f->nout || (inp1 == inp2 && out1 == out2))
+        return fail(FCV_E_PARAM, "bad link");
+    if (f->committed) return fail(FCV_E_STATE, "filter already committed");
+    const int src = inp1 * f->nout + out1, dst = inp2 * f->nout + out2;
+    if (!f->pairs[src].exists) return 0;  // Convlevel::impdata_link: no source node, no-op
+    Pair &d = f->pairs[dst];
+    d.exists = true;
+    d.h.clear();
+    d.h.shrink_to_fit();
+    d.link = src;
+    return 0;
+}
+
+static void filter_free_device(fcv_filter *f) {
+    if (f->device >= 0) cudaSetDevice(f->device);
+    if (f->dH) cudaFree(f->dH);
+    if (f->dsteps) cudaFree(f->dsteps);
+    if (f->dgroup_off) cudaFree(f->dgroup_off);
+    f->dH = nullptr;
+    f->dsteps = nullptr;
+    f->dgroup_off = nullptr;
+}
+
+extern "C" int fcv_filter_commit(fcv_filter *f, int device) {
+    if (!f) return fail(FCV_E_PARAM, "null filter");
+    if (f->committed) return fail(FCV_E_STATE, "filter already committed");
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    rc = get_tables(device, f->log2n, &f->tb);
+    if (rc) return rc;
+    f->device = device;
+    const int N = f->fragm;
+
+    // Rows: every non-zero partition of every pair that owns data.
+    std::vector<float> rows;
+    int nrows = 0, last_part = -1;
+    for (auto &p : f->pairs) {
+        p.row.assign((size_t)f->npar, -1);
+        if (!p.exists || p.link >= 0 || p.h.empty()) continue;
+        for (int j = 0; j < f->npar; j++) {
+            const float *src = p.h.data() + (size_t)j * N;
+            bool nz = false;
+            for (int k = 0; k < N; k++)
+                if (src[k] != 0.0f) { nz = true; break; }
+            if (!nz) continue;
+            p.row[j] = nrows++;
+            rows.insert(rows.end(), src, src + N);
+        }
+    }
+    // Resolve links (one level, as zita does: a link to a link sees no data).
+    for (auto &p : f->pairs) {
+        if (p.exists && p.link >= 0) {
+            const Pair &s = f->pairs[(size_t)p.link];
+            if (s.link < 0 && !s.row.empty()) p.row = s.row;
+        }
+    }
+    f->active_pairs = 0;
+    for (auto &p : f->pairs) {
+        bool any = false;
+        for (int j = 0; j < f->npar; j++)
+            if (p.row[j] >= 0) { any = true; if (j > last_part) last_part = j; }
+        if (any) f->active_pairs++;
+    }
+    f->nrows = nrows;
+    f->ring = last_part + 1 > 0 ? last_part + 1 : 1;
+
+    // MAC step table: outputs in groups of group_no.
+    f->group_no = f->nout >= 8 ? 8 : (f->nout > 4 ? 8 : (f->nout > 2 ? 4 : f->nout));
+    f->ngroups = (f->nout + f->group_no - 1) / f->group_no;
+    f->hsteps.clear();
+    f->hgroup_off.assign(1, 0);
+    for (int g = 0; g < f->ngroups; g++) {
+        for (int i = 0; i < f->ninp; i++)
+            for (int j = 0; j < f->ring; j++) {
+                MacStep sp;
+                sp.inp = i;
+                sp.part = j;
+                bool any = false;
+                for (int o = 0; o < MAC_NO_MAX; o++) {
+                    const int oo = g * f->group_no + o;
+                    sp.row[o] = (o < f->group_no && oo < f->nout) ? f->pairs[(size_t)i * f->nout + oo].row[j] : -1;
+                    any |= sp.row[o] >= 0;
+                }
+                if (any) f->hsteps.push_back(sp);
+            }
+        f->hgroup_off.push_back((int)f->hsteps.size());
+    }
+    f->nsteps = (int)f->hsteps.size();
+
+    const size_t M = (size_t)N;
+    CU_TRY(cudaMalloc(&f->dH, (size_t)(nrows > 0 ? nrows : 1) * M * sizeof(float2)));
+    CU_TRY(cudaMalloc(&f->dsteps, (size_t)(f->nsteps > 0 ? f->nsteps : 1) * sizeof(MacStep)));
+    CU_TRY(cudaMalloc(&f->dgroup_off, f->hgroup_off.size() * sizeof(int)));
+    if (f->nsteps)
+        CU_TRY(cudaMemcpy(f->dsteps, f->hsteps.data(), (size_t)f->nsteps * sizeof(MacStep), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(f->dgroup_off, f->hgroup_off.data(), f->hgroup_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (nrows) {
+        float *dsrc = nullptr;
+        CU_TRY(cudaMalloc(&dsrc, rows.size() * sizeof(float)));
+        CU_TRY(cudaMemcpy(dsrc, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const FftTables tb = f->tb;
+        DISPATCH_LOG2N(f->log2n, (fwd_raw_kernel<L><<<nrows, fft_threads(L), fft_smem_bytes(L)>>>(dsrc, f->dH, tb)));
+        g_launches++;
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(dsrc);
+        if (e != cudaSuccess) return fail(FCV_E_CUDA, "filter transform failed: %s", cudaGetErrorString(e));
+    }
+    // time-domain copies are no longer needed
+    for (auto &p : f->pairs) { p.h.clear(); p.h.shrink_to_fit(); }
+    f->committed = true;
+    return 0;
+}
+
+extern "C" void fcv_filter_ref(fcv_filter *f) { if (f) f->refs++; }
+extern "C" void fcv_filter_unref(fcv_filter *f) {
+    if (!f) return;
+    if (--f->refs == 0) {
+        filter_free_device(f);
+        delete f;
+    }
+}
+extern "C" int fcv_filter_ninp(const fcv_filter *f) { return f ? f->ninp : 0; }
+extern "C" int fcv_filter_nout(const fcv_filter *f) { return f ? f->nout : 0; }
+extern "C" int fcv_filter_fragm(const fcv_filter *f) { return f ? f->fragm : 0; }
+extern "C" int fcv_filter_partitions(const fcv_filter *f) { return f ? f->npar : 0; }
+extern "C" int fcv_filter_ring_depth(const fcv_filter *f) { return f ? f->ring : 0; }
+extern "C" int fcv_filter_active_rows(const fcv_filter *f) { return f ? f->nrows : 0; }
+extern "C" int fcv_filter_active_pairs(const fcv_filter *f) { return f ? f->active_pairs : 0; }
+extern "C" int fcv_filter_device(const fcv_filter *f) { return f ? f->device : -1; }
+
+// packed-permuted device row -> natural order (N+1 interleaved complex)
+static void unpermute_row(int log2n, const float2 *row, float *dst) {
+    const int q = log2n - 1, Q = 1 << q, M = 2 * Q;
+    dst[0] = row[0].x; dst[1] = 0.f;
+    dst[2 * M] = row[0].y; dst[2 * M + 1] = 0.f;
+    for (int k = 1; k < M; k++) {
+        const int e = ((k & 1) << q) + plan_rev(q, k >> 1);
+        dst[2 * k] = row[e].x;
+        dst[2 * k + 1] = row[e].y;
+    }
+}
+
+extern "C" int fcv_filter_get_spectrum(fcv_filter *f, int inp, int out, int j, float *dst) {
+    if (!f || !f->committed) return fail(FCV_E_STATE, "filter not committed");
+    if (inp < 0 || inp >= f->ninp || out < 0 || out >= f->nout || j < 0 || j >= f->npar)
+        return fail(FCV_E_PARAM, "bad index");
+    const int row = f->pairs[(size_t)inp * f->nout + out].row[j];
+    if (row < 0) return 0;
+    CU_TRY(cudaSetDevice(f->device));
+    std::vector<float2> h((size_t)f->fragm);
+    CU_TRY(cudaMemcpy(h.data(), f->dH + (size_t)row * f->fragm, h.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    unpermute_row(f->log2n, h.data(), dst);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------
+// batch
+// ---------------------------------------------------------------------------
+static size_t pcm_bytes(int fmt) { return fmt == FCV_PCM_S16 ? 2 : 4; }
+
+struct fcv_batch {
+    fcv_filter *f = nullptr;
+    int B = 0;
+    int in_fmt = FCV_PCM_F32, out_fmt = FCV_PCM_F32;
+    size_t in_block = 0, out_block = 0;  // bytes per stream per block
+    size_t out_pad = 0;                  // extra bytes after device_out (single-stream max mirror)
+    unsigned long long step = 0;         // blocks processed so far (ring slot = step % ring)
+    bool per_block_max = false;          // single-stream mode: maxv is the maximum of the last block only
+    // device
+    unsigned char *dmem = nullptr;       // one slab
+    float2 *xring = nullptr;
+    float *tail = nullptr;
+    unsigned char *din = nullptr, *dout = nullptr;
+    float2 *Y = nullptr;
+    float *maxv = nullptr;
+    StreamDev *dst = nullptr;
+    int *dfv = nullptr;
+    size_t state_bytes_per_stream = 0;
+    // host
+    unsigned char *hin = nullptr, *hout = nullptr;
+    int *hfv = nullptr;
+    // streams
+    static const int NQ = 4;
+    cudaStream_t q[NQ] = {};
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;  // 4 events per step: t0 | fwd | mac | inv
+    size_t ev_used = 0;
+    int prof_steps = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void batch_free(fcv_batch *b) {
+    if (!b) return;
+    if (b->f && b->f->device >= 0) cudaSetDevice(b->f->device);
+    for (auto e : b->ev) cudaEventDestroy(e);
+    for (int i = 0; i < fcv_batch::NQ; i++)
+        if (b->q[i]) { cudaStreamSynchronize(b->q[i]); cudaStreamDestroy(b->q[i]); }
+    if (b->dmem) cudaFree(b->dmem);
+    if (b->hin) cudaFreeHost(b->hin);
+    if (b->hout) cudaFreeHost(b->hout);
+    if (b->hfv) cudaFreeHost(b->hfv);
+    if (b->f) fcv_filter_unref(b->f);
+    delete b;
+}
+
+static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_fmt, bool shared_host_buffer) {
+    if (!f || !f->committed) { fail(FCV_E_STATE, "filter not committed"); return nullptr; }
+    if (nstreams < 1) { fail(FCV_E_PARAM, "nstreams < 1"); return nullptr; }
+    if (in_fmt < 0 || in_fmt > FCV_PCM_S24 || out_fmt < 0 || out_fmt > FCV_PCM_S24) {
+        fail(FCV_E_PARAM, "bad PCM format");
+        return nullptr;
+    }
+    if (cudaSetDevice(f->device) != cudaSuccess) { fail(FCV_E_CUDA, "cudaSetDevice failed"); return nullptr; }
+    fcv_batch *b = new (std::nothrow) fcv_batch();
+    if (!b) { fail(FCV_E_ALLOC, "out of memory"); return nullptr; }
+    b->f = f;
+    fcv_filter_ref(f);
+    b->B = nstreams;
+    b->in_fmt = in_fmt;
+    b->out_fmt = out_fmt;
+    const size_t N = (size_t)f->fragm, B = (size_t)nstreams;
+    b->in_block = N * f->ninp * pcm_bytes(in_fmt);
+    b->out_block = N * f->nout * pcm_bytes(out_fmt);
+    b->out_pad = 256;
+    b->per_block_max = shared_host_buffer;
+
+    const size_t xring_b = align_up(B * f->ninp * f->ring * N * sizeof(float2), 256);
+    const size_t tail_b = align_up(B * f->nout * N * sizeof(float), 256);
+    const size_t din_b = align_up(B * b->in_block, 256);
+    const size_t dout_b = align_up(B * b->out_block + b->out_pad, 256);
+    const size_t y_b = align_up(B * f->nout * N * sizeof(float2), 256);
+    const size_t max_b = align_up(B * sizeof(float), 256);
+    const size_t st_b = align_up(B * sizeof(StreamDev), 256);
+    const size_t fv_b = align_up(B * sizeof(int), 256);
+    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + st_b + fv_b;
+    cudaError_t e = cudaMalloc(&b->dmem, total);
+    if (e != cudaSuccess) {
+        fail(FCV_E_ALLOC, "cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
+        batch_free(b);
+        return nullptr;
+    }
+    unsigned char *p = b->dmem;
+    b->xring = (float2 *)p; p += xring_b;
+    b->tail = (float *)p; p += tail_b;
+    b->din = p; p += din_b;
+    b->dout = p; p += dout_b;
+    b->Y = (float2 *)p; p += y_b;
+    // single-stream mode keeps the running maximum right behind the output block
+    // so that one device->host copy brings back both
+    b->maxv = shared_host_buffer ? (float *)(b->dout + B * b->out_block) : (float *)p;
+    p += max_b;
+    b->dst = (StreamDev *)p; p += st_b;
+    b->dfv = (int *)p; p += fv_b;
+    b->state_bytes_per_stream = (size_t)f->ninp * f->ring * N * sizeof(float2);
+
+    bool ok = cudaMemset(b->dmem, 0, total) == cudaSuccess;
+    std::vector<StreamDev> hs(B);
+    for (size_t s = 0; s < B; s++) {
+        hs[s].xring = b->xring + s * f->ninp * f->ring * N;
+        hs[s].tail = b->tail + s * f->nout * N;
+        hs[s].din = b->din + s * b->in_block;
+        hs[s].dout = b->dout + s * b->out_block;
+        hs[s].maxv = b->maxv + s;
+    }
+    ok = ok && cudaMemcpy(b->dst, hs.data(), B * sizeof(StreamDev), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (shared_host_buffer) {
+        // SoundProcessor::buffer_: fragm * max(ninp, nout) floats (+ the max mirror)
+        const size_t bytes = N * (size_t)(f->ninp > f->nout ? f->ninp : f->nout) * sizeof(float) + b->out_pad;
+        ok = ok && cudaHostAlloc((void **)&b->hin, bytes, cudaHostAllocDefault) == cudaSuccess;
+        if (ok) memset(b->hin, 0, bytes);
+    } else {
+        ok = ok && cudaHostAlloc((void **)&b->hin, B * b->in_block, cudaHostAllocDefault) == cudaSuccess;
+        ok = ok && cudaHostAlloc((void **)&b->hout, B * b->out_block, cudaHostAllocDefault) == cudaSuccess;
+        if (ok) { memset(b->hin, 0, B * b->in_block); memset(b->hout, 0, B * b->out_block); }
+    }
+    ok = ok && cudaHostAlloc((void **)&b->hfv, B * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+    const int nq = shared_host_buffer ? 1 : fcv_batch::NQ;
+    for (int i = 0; ok && i < nq; i++) ok = cudaStreamCreateWithFlags(&b->q[i], cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        fail(FCV_E_ALLOC, "batch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        batch_free(b);
+        return nullptr;
+    }
+    return b;
+}
+
+template <int NO, int S>
+static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_t q) {
+    const fcv_filter *f = b->f;
+    const int M4 = f->fragm / 2;
+    const int TPB = M4 >= 128 ? 128 : M4;  // M4 is a power of two >= 32
+    dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->ngroups);
+    const float4 *H = reinterpret_cast<const float4 *>(f->dH);
+    float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * f->fragm);
+    if (TPB == 128)
+        mac_kernel<NO, S, 128><<<grid, 128, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, f->ring, pt, f->nout);
+    else if (TPB == 64)
+        mac_kernel<NO, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, f->ring, pt, f->nout);
+    else
+        mac_kernel<NO, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, f->ring, pt, f->nout);
+}
+
+// The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
+static int run_kernels(fcv_batch *b, int off, int cnt, bool use_fv, cudaStream_t q, cudaEvent_t *ev) {
+    fcv_filter *f = b->f;
+    const int pt = (int)(b->step % (unsigned long long)f->ring);
+    const int *fv = use_fv ? b->dfv + off : nullptr;
+    const FftTables tb = f->tb;
+    if (ev) cudaEventRecord(ev[0], q);
+    DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(f->ninp, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
+                                  b->dst + off, fv, tb, f->ninp, f->ring, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
+    if (ev) cudaEventRecord(ev[1], q);
+    const int S = cnt >= 4 ? 4 : (cnt >= 2 ? 2 : 1);
+    switch (f->group_no) {
+        case 1: if (S == 4) launch_mac<1, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<1, 2>(b, off, cnt, pt, q); else launch_mac<1, 1>(b, off, cnt, pt, q); break;
+        case 2: if (S == 4) launch_mac<2, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<2, 2>(b, off, cnt, pt, q); else launch_mac<2, 1>(b, off, cnt, pt, q); break;
+        case 4: if (S >= 2) launch_mac<4, 2>(b, off, cnt, pt, q); else launch_mac<4, 1>(b, off, cnt, pt, q); break;
+        default: if (S >= 2) launch_mac<8, 2>(b, off, cnt, pt, q); else launch_mac<8, 1>(b, off, cnt, pt, q); break;
+    }
+    if (ev) cudaEventRecord(ev[2], q);
+    const float2 *Y = b->Y + (size_t)off * f->nout * f->fragm;
+    DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
+                                  b->dst + off, fv, tb, Y, f->dsteps, f->dgroup_off, f->dH, f->group_no, f->nout,
+                                  f->ring, pt, b->out_fmt)));
+    if (ev) cudaEventRecord(ev[3], q);
+    g_launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FCV_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static cudaEvent_t *prof_events(fcv_batch *b) {
+    if (!b->profiling) return nullptr;
+    if (b->ev_used + 4 > b->ev.size()) {
+        for (int i = 0; i < 4; i++) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            b->ev.push_back(e);
+        }
+    }
+    cudaEvent_t *p = &b->ev[b->ev_used];
+    b->ev_used += 4;
+    b->prof_steps++;
+    return p;
+}
+
+extern "C" fcv_batch *fcv_batch_create(fcv_filter *f, int nstreams, int in_format, int out_format) {
+    return batch_create(f, nstreams, in_format, out_format, false);
+}
+extern "C" void fcv_batch_destroy(fcv_batch *b) { batch_free(b); }
+extern "C" int fcv_batch_nstreams(const fcv_batch *b) { return b ? b->B : 0; }
+extern "C" void *fcv_batch_host_in(fcv_batch *b) { return b ? b->hin : nullptr; }
+extern "C" void *fcv_batch_host_out(fcv_batch *b) { return b ? b->hout : nullptr; }
+extern "C" size_t fcv_batch_host_in_bytes(const fcv_batch *b) { return b ? (size_t)b->B * b->in_block : 0; }
+extern "C" size_t fcv_batch_host_out_bytes(const fcv_batch *b) { return b ? (size_t)b->B * b->out_block : 0; }
+extern "C" void *fcv_batch_device_in(fcv_batch *b) { return b ? b->din : nullptr; }
+extern "C" void *fcv_batch_device_out(fcv_batch *b) { return b ? b->dout : nullptr; }
+extern "C" void *fcv_batch_cuda_stream(fcv_batch *b) { return b ? (void *)b->q[0] : nullptr; }
+
+static int stage_fv(fcv_batch *b, const int *frames_valid, cudaStream_t q) {
+    for (int s = 0; s < b->B; s++) {
+        const int v = frames_valid[s];
+        if (v < 0 || v > b->f->fragm) return fail(FCV_E_PARAM, "frames_valid[%d] = %d out of range", s, v);
+        b->hfv[s] = v;
+    }
+    CU_TRY(cudaMemcpyAsync(b->dfv, b->hfv, (size_t)b->B * sizeof(int), cudaMemcpyHostToDevice, q));
+    return 0;
+}
+
+extern "C" int fcv_batch_process_device(fcv_batch *b, const int *frames_valid) {
+    if (!b) return fail(FCV_E_PARAM, "null batch");
+    CU_TRY(cudaSetDevice(b->f->device));
+    if (frames_valid) {
+        // the staging array is reused: the previous block must be done with it
+        CU_TRY(cudaStreamSynchronize(b->q[0]));
+        int rc = stage_fv(b, frames_valid, b->q[0]);
+        if (rc) return rc;
+    }
+    int rc = run_kernels(b, 0, b->B, frames_valid != nullptr, b->q[0], prof_events(b));
+    if (rc) return rc;
+    b->step++;
+    return 0;
+}
+
+extern "C" int fcv_batch_sync(fcv_batch *b) {
+    if (!b) return fail(FCV_E_PARAM, "null batch");
+    CU_TRY(cudaSetDevice(b->f->device));
+    for (int i = 0; i < fcv_batch::NQ; i++)
+        if (b->q[i]) CU_TRY(cudaStreamSynchronize(b->q[i]));
+    return 0;
+}
+
+extern "C" int fcv_batch_process(fcv_batch *b, const int *frames_valid) {
+    if (!b) return fail(FCV_E_PARAM, "null batch");
+    if (!b->hout) return fail(FCV_E_STATE, "batch has no host staging");
+    CU_TRY(cudaSetDevice(b->f->device));
+    if (frames_valid) {
+        int rc = stage_fv(b, frames_valid, b->q[0]);
+        if (rc) return rc;
+        CU_TRY(cudaStreamSynchronize(b->q[0]));
+    }
+    // Independent streams: cut the batch into chunks and pipeline
+    // host->device copy, kernels and device->host copy over NQ CUDA streams.
+    int nchunk = 1;
+    if (!b->profiling) {
+        nchunk = b->B / 128;
+        if (nchunk > 8) nchunk = 8;
+        if (nchunk < 1) nchunk = 1;
+    }
+    const int per = (b->B + nchunk - 1) / nchunk;
+    for (int c = 0, off = 0; off < b->B; c++, off += per) {
+        const int cnt = (b->B - off) < per ? (b->B - off) : per;
+        cudaStream_t q = b->q[nchunk == 1 ? 0 : c % fcv_batch::NQ];
+        CU_TRY(cudaMemcpyAsync(b->din + (size_t)off * b->in_block, b->hin + (size_t)off * b->in_block,
+                               (size_t)cnt * b->in_block, cudaMemcpyHostToDevice, q));
+        int rc = run_kernels(b, off, cnt, frames_valid != nullptr, q, nchunk == 1 ? prof_events(b) : nullptr);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(b->hout + (size_t)off * b->out_block, b->dout + (size_t)off * b->out_block,
+                               (size_t)cnt * b->out_block, cudaMemcpyDeviceToHost, q));
+    }
+    b->step++;
+    return fcv_batch_sync(b);
+}
+
+extern "C" int fcv_batch_reset_slot(fcv_batch *b, int slot) {
+    if (!b || slot < 0 || slot >= b->B) return fail(FCV_E_PARAM, "bad slot");
+    CU_TRY(cudaSetDevice(b->f->device));
+    const fcv_filter *f = b->f;
+    const size_t N = (size_t)f->fragm;
+    CU_TRY(cudaMemsetAsync(b->xring + (size_t)slot * f->ninp * f->ring * N, 0, b->state_bytes_per_stream, b->q[0]));
+    CU_TRY(cudaMemsetAsync(b->tail + (size_t)slot * f->nout * N, 0, (size_t)f->nout * N * sizeof(float), b->q[0]));
+    CU_TRY(cudaMemsetAsync(b->maxv + slot, 0, sizeof(float), b->q[0]));
+    return 0;
+}
+
+extern "C" int fcv_batch_get_max(fcv_batch *b, float *max_out) {
+    if (!b || !max_out) return fail(FCV_E_PARAM, "null argument");
+    CU_TRY(cudaSetDevice(b->f->device));
+    int rc = fcv_batch_sync(b);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(max_out, b->maxv, (size_t)b->B * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int fcv_batch_set_profiling(fcv_batch *b, int on) {
+    if (!b) return fail(FCV_E_PARAM, "null batch");
+    b->profiling = on != 0;
+    b->ev_used = 0;
+    b->prof_steps = 0;
+    return 0;
+}
+
+extern "C" int fcv_batch_profile(fcv_batch *b, float ms[3], int *steps) {
+    if (!b || !ms) return fail(FCV_E_PARAM, "null argument");
+    int rc = fcv_batch_sync(b);
+    if (rc) return rc;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    for (size_t i = 0; i + 3 < b->ev_used; i += 4) {
+        for (int k = 0; k < 3; k++) {
+            float t = 0.f;
+            CU_TRY(cudaEventElapsedTime(&t, b->ev[i + k], b->ev[i + k + 1]));
+            ms[k] += t;
+        }
+    }
+    if (steps) *steps = b->prof_steps;
+    b->ev_used = 0;
+    b->prof_steps = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// single stream == batch of one with a shared in/out host block
+// ---------------------------------------------------------------------------
+struct fcv_stream {
+    fcv_batch *b = nullptr;
+};
+
+extern "C" fcv_stream *fcv_stream_create(fcv_filter *f) {
+    fcv_batch *b = batch_create(f, 1, FCV_PCM_F32, FCV_PCM_F32, true);
+    if (!b) return nullptr;
+    fcv_stream *s = new (std::nothrow) fcv_stream();
+    if (!s) { batch_free(b); fail(FCV_E_ALLOC, "out of memory"); return nullptr; }
+    s->b = b;
+    return s;
+}
+
+extern "C" void fcv_stream_destroy(fcv_stream *s) {
+    if (!s) return;
+    batch_free(s->b);
+    delete s;
+}
+
+extern "C" int fcv_stream_reset(fcv_stream *s) {
+    if (!s) return fail(FCV_E_PARAM, "null stream");
+    int rc = fcv_batch_reset_slot(s->b, 0);
+    if (rc) return rc;
+    return fcv_batch_sync(s->b);
+}
+
+extern "C" float *fcv_stream_buffer(fcv_stream *s) { return s ? (float *)s->b->hin : nullptr; }
+extern "C" fcv_filter *fcv_stream_filter(fcv_stream *s) { return s ? s->b->f : nullptr; }
+
+extern "C" int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_inout) {
+    if (!s) return fail(FCV_E_PARAM, "null stream");
+    fcv_batch *b = s->b;
+    const fcv_filter *f = b->f;
+    if (frames_valid < 0 || frames_valid > f->fragm) return fail(FCV_E_PARAM, "frames_valid out of range");
+    CU_TRY(cudaSetDevice(f->device));
+    cudaStream_t q = b->q[0];
+    b->hfv[0] = frames_valid;
+    CU_TRY(cudaMemcpyAsync(b->dfv, b->hfv, sizeof(int), cudaMemcpyHostToDevice, q));
+    if (frames_valid > 0)
+        CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)frames_valid * f->ninp * sizeof(float), cudaMemcpyHostToDevice, q));
+    int rc = run_kernels(b, 0, 1, true, q, nullptr);
+    if (rc) return rc;
+    b->step++;
+    // one copy brings back the whole output block and the running maximum behind it
+    CU_TRY(cudaMemcpyAsync(b->hin, b->dout, b->out_block + sizeof(float), cudaMemcpyDeviceToHost, q));
+    CU_TRY(cudaStreamSynchronize(q));
+    if (max_inout) {
+        float m;
+        memcpy(&m, b->hin + b->out_block, sizeof(float));
+        if (m > *max_inout) *max_inout = m;
+    }
+    return 0;
+}
+
+extern "C" int fcv_stream_get_input_spectrum(fcv_stream *s, int inp, int age, float *dst) {
+    if (!s || !dst) return fail(FCV_E_PARAM, "null argument");
+    fcv_batch *b = s->b;
+    const fcv_filter *f = b->f;
+    if (inp < 0 || inp >= f->ninp || age < 0 || age >= f->ring || (unsigned long long)age >= b->step)
+        return fail(FCV_E_PARAM, "bad index");
+    CU_TRY(cudaSetDevice(f->device));
+    const int slot = (int)((b->step - 1 - age) % (unsigned long long)f->ring);
+    std::vector<float2> h((size_t)f->fragm);
+    CU_TRY(cudaMemcpy(h.data(), b->xring + (size_t)(inp * f->ring + slot) * f->fragm, h.size() * sizeof(float2),
+                      cudaMemcpyDeviceToHost));
+    unpermute_row(f->log2n, h.data(), dst);
+    return 0;
+}

@@ -1,0 +1,339 @@
+// fcv_fft.cuh -- shared-memory real FFT / inverse real FFT of one zero-padded
+// partition, hand written for sm_100a.
+//
+// Role in the reference path: these two kernels are what zita-convolver's
+// Convlevel::process() hands to FFTW (fftwf_execute_dft_r2c on the zero padded
+// input block, fftwf_execute_dft_c2r on the accumulated spectrum), called from
+// SoundProcessor::Process() at /root/reference/sound-processor.cc:113, with the
+// de-interleave (sound-processor.cc:106-111), overlap-add, re-interleave and
+// running maximum (sound-processor.cc:115-125) fused in.
+//
+// Method (ours, not FFTW's):
+//   * A real transform of length 2N is done as a complex transform of length
+//     M = N on z[n] = x[2n] + i x[2n+1].
+//   * The block is zero padded (x[N..2N) == 0), so z[n] == 0 for n >= M/2 and
+//     the first radix-2 DIF stage degenerates: even bins = FFT_Q(z), odd bins
+//     = FFT_Q(z * w_M^n), Q = M/2.  The two length-Q transforms live side by
+//     side in shared memory ("half 0" and "half 1").
+//   * Each length-Q transform is an in-place decimation-in-frequency FFT with
+//     radix-16/8/4 register butterflies and NO reordering pass: the spectrum
+//     stays in digit-reversed order ("packed-permuted layout").  The complex
+//     multiply-accumulate is element-wise, so the order is irrelevant to it,
+//     and the inverse runs the same passes backwards (decimation in time).
+//   * DC and Nyquist are both real; they share entry 0 (re = DC, im = Nyquist)
+//     so that one spectrum is exactly M complex values = 8*N bytes.
+//   * Shared memory is padded by one float2 every 16 so that the stride-R
+//     accesses of the last pass are bank-conflict free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcv {
+
+// ---- compile-time plan ----------------------------------------------------
+// Q = 2^q is the length of each half transform.  Radix exponents per pass,
+// first pass in the low nibble.
+__host__ __device__ constexpr int plan_code(int q) {
+    return q == 12 ? 0x444 : q == 11 ? 0x344 : q == 10 ? 0x334 : q == 9 ? 0x333
+         : q == 8 ? 0x44 : q == 7 ? 0x34 : q == 6 ? 0x33 : q == 5 ? 0x23 : 0;
+}
+__host__ __device__ constexpr int plan_npass(int q) {
+    return (plan_code(q) >> 8) ? 3 : 2;
+}
+__host__ __device__ constexpr int plan_lr(int q, int t) { return (plan_code(q) >> (4 * t)) & 0xF; }
+// log2 of the block length pass t works on, and of its butterfly stride
+__host__ __device__ constexpr int plan_lqt(int q, int t) {
+    int l = q;
+    for (int s = 0; s < t; s++) l -= plan_lr(q, s);
+    return l;
+}
+__host__ __device__ constexpr int plan_ls(int q, int t) { return plan_lqt(q, t) - plan_lr(q, t); }
+// bin k' -> position in the half array (mixed-radix digit reversal) and back
+__host__ __device__ constexpr int plan_rev(int q, int k) {
+    int pos = 0, sh = 0;
+    for (int t = 0; t < plan_npass(q); t++) {
+        const int lr = plan_lr(q, t);
+        pos |= ((k >> sh) & ((1 << lr) - 1)) << plan_ls(q, t);
+        sh += lr;
+    }
+    return pos;
+}
+__host__ __device__ constexpr int plan_revinv(int q, int pos) {
+    int k = 0, sh = 0;
+    for (int t = 0; t < plan_npass(q); t++) {
+        const int lr = plan_lr(q, t);
+        k |= ((pos >> plan_ls(q, t)) & ((1 << lr) - 1)) << sh;
+        sh += lr;
+    }
+    return k;
+}
+__host__ __device__ constexpr int fft_threads(int log2n) {
+    const int n = 1 << log2n;
+    return (n / 32) > 256 ? 256 : ((n / 32) < 32 ? 32 : (n / 32));
+}
+__host__ __device__ constexpr int smem_pad(int e) { return e + (e >> 4); }
+__host__ __device__ constexpr size_t fft_smem_bytes(int log2n) {
+    return (size_t)smem_pad(1 << log2n) * sizeof(float2) + 64;
+}
+
+// Twiddle tables for one partition size, resident in device memory.
+struct FftTables {
+    const float2 *twA;     // [Q]   w_M^n = exp(-2 pi i n / M)
+    const float2 *twU;     // [M]   exp(-i pi k / M) for the bin stored at entry e
+    const float2 *twP[3];  // per pass t with stride S_t > 1: [(k1-1)*S_t + u] = exp(-2 pi i u k1 / Q_t)
+};
+
+// ---- complex helpers --------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulconj(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// multiply by DIR*i  (DIR = -1: forward transform, +1: inverse)
+template <int DIR>
+__device__ __forceinline__ float2 mul_i(float2 a) {
+    return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+// multiply by (c + DIR*i*s)
+template <int DIR>
+__device__ __forceinline__ float2 mul_w(float2 a, float c, float s) {
+    const float ss = DIR < 0 ? -s : s;
+    return make_float2(a.x * c - a.y * ss, a.x * ss + a.y * c);
+}
+
+// ---- register butterflies ---------------------------------------------------
+// run<DIR>(v): v <- DFT_R(v) with kernel exp(DIR * 2 pi i j k / R).
+// The result for bin k is left in register out(r) == k, i.e. register r holds
+// bin out(r).
+template <int R> struct Bfly;
+
+template <> struct Bfly<2> {
+    __host__ __device__ static constexpr int out(int r) { return r; }
+    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[2]) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <int DIR>
+__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
+    const float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = mul_i<DIR>(csub(b, d));
+    a = cadd(s0, s1);
+    c = csub(s0, s1);
+    b = cadd(d0, d1);
+    d = csub(d0, d1);
+}
+
+template <> struct Bfly<4> {
+    __host__ __device__ static constexpr int out(int r) { return r; }
+    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[4]) {
+        dft4<DIR>(v[0], v[1], v[2], v[3]);
+    }
+};
+
+// j = j0 + 4 j1 (j1 in {0,1}), k = k1 + 2 k0: register k0 + 4 k1 holds bin k1 + 2 k0
+template <> struct Bfly<8> {
+    __host__ __device__ static constexpr int out(int r) { return (r >> 2) + 2 * (r & 3); }
+    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[8]) {
+        constexpr float C2 = 0.70710678118654752440f;
+#pragma unroll
+        for (int j0 = 0; j0 < 4; j0++) {
+            const float2 a = v[j0], b = v[j0 + 4];
+            v[j0] = cadd(a, b);
+            v[j0 + 4] = csub(a, b);
+        }
+        // twiddle w_8^(j0*k1), k1 = 1 row only
+        v[5] = mul_w<DIR>(v[5], C2, C2);
+        v[6] = mul_i<DIR>(v[6]);
+        v[7] = mul_w<DIR>(v[7], -C2, C2);
+        dft4<DIR>(v[0], v[1], v[2], v[3]);
+        dft4<DIR>(v[4], v[5], v[6], v[7]);
+    }
+};
+
+// j = j0 + 4 j1, k = k1 + 4 k0: register k0 + 4 k1 holds bin k1 + 4 k0
+template <> struct Bfly<16> {
+    __host__ __device__ static constexpr int out(int r) { return (r >> 2) + 4 * (r & 3); }
+    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[16]) {
+        constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
+        constexpr float S1 = 0.38268343236508977173f;  // sin(pi/8)
+        constexpr float C2 = 0.70710678118654752440f;
+#pragma unroll
+        for (int j0 = 0; j0 < 4; j0++) dft4<DIR>(v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12]);
+        // v[j0 + 4 k1] *= w_16^(j0 k1)
+        v[5] = mul_w<DIR>(v[5], C1, S1);     // 1
+        v[6] = mul_w<DIR>(v[6], C2, C2);     // 2
+        v[7] = mul_w<DIR>(v[7], S1, C1);     // 3
+        v[9] = mul_w<DIR>(v[9], C2, C2);     // 2
+        v[10] = mul_i<DIR>(v[10]);           // 4
+        v[11] = mul_w<DIR>(v[11], -C2, C2);  // 6
+        v[13] = mul_w<DIR>(v[13], S1, C1);   // 3
+        v[14] = mul_w<DIR>(v[14], -C2, C2);  // 6
+        v[15] = mul_w<DIR>(v[15], -C1, -S1); // 9
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) dft4<DIR>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    }
+};
+
+// ---- passes over both half transforms ----------------------------------------
+template <int Q_LOG2, int T, int NT>
+__device__ __forceinline__ void fwd_pass(float2 *sm, const float2 *__restrict__ tw, int tid) {
+    constexpr int LR = plan_lr(Q_LOG2, T), R = 1 << LR;
+    constexpr int LS = plan_ls(Q_LOG2, T), S = 1 << LS;
+    constexpr int LQT = plan_lqt(Q_LOG2, T);
+    constexpr int NB = (2 << Q_LOG2) >> LR;
+    for (int b = tid; b < NB; b += NT) {
+        const int u = b & (S - 1);
+        const int base = ((b >> LS) << LQT) + u;
+        float2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) v[j] = sm[smem_pad(base + (j << LS))];
+        Bfly<R>::template run<-1>(v);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k1 = Bfly<R>::out(r);
+            float2 x = v[r];
+            if (S > 1 && k1 > 0) x = cmul(x, __ldg(&tw[(k1 - 1) * S + u]));
+            sm[smem_pad(base + (k1 << LS))] = x;
+        }
+    }
+    __syncthreads();
+}
+
+template <int Q_LOG2, int T, int NT>
+__device__ __forceinline__ void inv_pass(float2 *sm, const float2 *__restrict__ tw, int tid) {
+    constexpr int LR = plan_lr(Q_LOG2, T), R = 1 << LR;
+    constexpr int LS = plan_ls(Q_LOG2, T), S = 1 << LS;
+    constexpr int LQT = plan_lqt(Q_LOG2, T);
+    constexpr int NB = (2 << Q_LOG2) >> LR;
+    for (int b = tid; b < NB; b += NT) {
+        const int u = b & (S - 1);
+        const int base = ((b >> LS) << LQT) + u;
+        float2 v[R];
+#pragma unroll
+        for (int k1 = 0; k1 < R; k1++) {
+            float2 x = sm[smem_pad(base + (k1 << LS))];
+            if (S > 1 && k1 > 0) x = cmulconj(x, __ldg(&tw[(k1 - 1) * S + u]));
+            v[k1] = x;
+        }
+        Bfly<R>::template run<+1>(v);
+#pragma unroll
+        for (int r = 0; r < R; r++) sm[smem_pad(base + (Bfly<R>::out(r) << LS))] = v[r];
+    }
+    __syncthreads();
+}
+
+template <int Q_LOG2, int NT>
+__device__ __forceinline__ void fwd_passes(float2 *sm, const FftTables &tb, int tid) {
+    fwd_pass<Q_LOG2, 0, NT>(sm, tb.twP[0], tid);
+    fwd_pass<Q_LOG2, 1, NT>(sm, tb.twP[1], tid);
+    if constexpr (plan_npass(Q_LOG2) == 3) fwd_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
+}
+template <int Q_LOG2, int NT>
+__device__ __forceinline__ void inv_passes(float2 *sm, const FftTables &tb, int tid) {
+    if constexpr (plan_npass(Q_LOG2) == 3) inv_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
+    inv_pass<Q_LOG2, 1, NT>(sm, tb.twP[1], tid);
+    inv_pass<Q_LOG2, 0, NT>(sm, tb.twP[0], tid);
+}
+
+// entry e of the packed-permuted layout <-> its conjugate-partner entry
+template <int Q_LOG2>
+__device__ __forceinline__ int partner_entry(int e, int &kp_out, int &kpp_out) {
+    constexpr int Q = 1 << Q_LOG2;
+    const int half = e >> Q_LOG2;
+    const int kp = plan_revinv(Q_LOG2, e & (Q - 1));
+    const int kpp = half ? (Q - 1 - kp) : ((Q - kp) & (Q - 1));
+    kp_out = kp;
+    kpp_out = kpp;
+    return (half << Q_LOG2) + plan_rev(Q_LOG2, kpp);
+}
+
+// ---- PCM wire formats ---------------------------------------------------------
+enum { PCM_F32 = 0, PCM_S16 = 1, PCM_S24 = 2 };
+
+__device__ __forceinline__ float pcm_load(const void *p, int fmt, size_t idx) {
+    if (fmt == PCM_F32) return __ldg((const float *)p + idx);
+    if (fmt == PCM_S16) return (float)__ldg((const short *)p + idx) * (1.0f / 32768.0f);
+    return (float)__ldg((const int *)p + idx) * (1.0f / 8388608.0f);
+}
+__device__ __forceinline__ void pcm_store(void *p, int fmt, size_t idx, float v) {
+    if (fmt == PCM_F32) { ((float *)p)[idx] = v; return; }
+    if (fmt == PCM_S16) {
+        // libsndfile f2s_array without clipping: lrintf(x * 0x7FFF), stored to a short (wraps)
+        ((short *)p)[idx] = (short)__float2int_rn(v * 32767.0f);
+        return;
+    }
+    ((int *)p)[idx] = __float2int_rn(v * 8388607.0f);
+}
+
+// ---- forward: one zero-padded partition -> packed-permuted spectrum -----------
+// in: interleaved PCM, `nchan` channels, channel `chan`; frames >= frames_valid read as 0.
+template <int LOG2N>
+__device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const void *in, int fmt,
+                                         int nchan, int chan, int frames_valid, float scale,
+                                         float2 *__restrict__ out_row) {
+    constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
+    constexpr int NT = fft_threads(LOG2N);
+    const int tid = threadIdx.x;
+    for (int n = tid; n < Q; n += NT) {
+        const int f0 = 2 * n, f1 = 2 * n + 1;
+        float2 z;
+        z.x = f0 < frames_valid ? pcm_load(in, fmt, (size_t)f0 * nchan + chan) * scale : 0.0f;
+        z.y = f1 < frames_valid ? pcm_load(in, fmt, (size_t)f1 * nchan + chan) * scale : 0.0f;
+        sm[smem_pad(n)] = z;
+        sm[smem_pad(Q + n)] = cmul(z, __ldg(&tb.twA[n]));
+    }
+    __syncthreads();
+    fwd_passes<QL, NT>(sm, tb, tid);
+    for (int e = tid; e < M; e += NT) {
+        int kp, kpp;
+        const int e2 = partner_entry<QL>(e, kp, kpp);
+        const float2 zk = sm[smem_pad(e)];
+        const float2 zp = sm[smem_pad(e2)];
+        float2 x;
+        if (e == 0) {
+            x = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
+        } else {
+            const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+            const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
+            const float2 t = cmul(__ldg(&tb.twU[e]), dv);
+            x = make_float2(ev.x + t.y, ev.y - t.x);  // E - i w D
+        }
+        out_row[e] = x;
+    }
+}
+
+// ---- inverse: packed-permuted spectrum (already in smem) -> 2N real samples -----
+// On entry sm holds the accumulated spectrum Y (entry 0 = DC, Nyquist).  On
+// return half 0 / half 1 hold a'[n] / b'[n]; the caller combines them:
+//   z[n] = a' + conj(twA[n]) b' -> samples 2n, 2n+1;  z[n+Q] = a' - conj(twA[n]) b' -> samples N+2n, N+2n+1.
+template <int LOG2N>
+__device__ __forceinline__ void inv_body(float2 *sm, const FftTables &tb) {
+    constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
+    constexpr int NT = fft_threads(LOG2N);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < M; e += NT) {
+        int kp, kpp;
+        const int e2 = partner_entry<QL>(e, kp, kpp);
+        if (kp > kpp) continue;  // the pair is handled by its lower member
+        const float2 yk = sm[smem_pad(e)];
+        if (e == 0) {
+            sm[smem_pad(0)] = make_float2(yk.x + yk.y, yk.x - yk.y);
+            continue;
+        }
+        const float2 yp = sm[smem_pad(e2)];
+        const float2 ev = make_float2(yk.x + yp.x, yk.y - yp.y);
+        const float2 dv = make_float2(yk.x - yp.x, yk.y + yp.y);
+        const float2 t = cmulconj(dv, __ldg(&tb.twU[e]));
+        sm[smem_pad(e)] = make_float2(ev.x - t.y, ev.y + t.x);
+        if (e2 != e) sm[smem_pad(e2)] = make_float2(ev.x + t.y, -ev.y + t.x);
+    }
+    __syncthreads();
+    inv_passes<QL, NT>(sm, tb, tid);
+}
+
+}  // namespace fcv

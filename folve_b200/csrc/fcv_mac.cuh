@@ -1,0 +1,126 @@
+// fcv_mac.cuh -- frequency-domain complex multiply-accumulate over the partition
+// history and the input x output matrix: the roofline kernel.
+//
+// Role in the reference path: the inner loops of zita-convolver's
+// Convlevel::process() (for each output, for each MAC node, for j < npar:
+// freq_data[k] += ffta[ptind - j][k] * fftb[j][k]), reached from
+// SoundProcessor::Process() at /root/reference/sound-processor.cc:113.
+//
+//   Y[s][o][e] = sum over (i, j) with H[i][o][j] present of
+//                X[s][i][(pt - j) mod P][e] * H[i][o][j][e]
+//
+// e runs over the M = fragm entries of the packed-permuted spectrum layout
+// (fcv_fft.cuh).  Entry 0 holds two REAL bins (DC, Nyquist); this kernel
+// treats it as complex like every other entry and the inverse-FFT kernel
+// overwrites it with the correct real products, so there is no special case
+// in the streaming loop.
+//
+// Pure streaming: every X row is read from HBM exactly once per launch; the
+// filter rows H are shared by all streams and stay L2 resident; S streams per
+// thread reuse each H value from registers.  0.5-1 flop per byte -> HBM bound,
+// no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcv {
+
+// Per-stream device descriptor (array owned by a batch or a single stream).
+struct StreamDev {
+    float2 *xring;  // [ninp][P][M] input-spectra ring
+    float *tail;    // [nout][N]    overlap tails
+    const void *din;  // interleaved PCM in,  [N][ninp] wire format
+    void *dout;       // interleaved PCM out, [N][nout] wire format
+    float *maxv;    // running signed maximum
+};
+
+constexpr int MAC_NO_MAX = 8;
+
+// One (input, partition) pair that feeds at least one output of the group.
+struct MacStep {
+    int inp;
+    int part;
+    int row[MAC_NO_MAX];  // filter row per output of the group, -1 = absent
+};
+
+__device__ __forceinline__ void cmac2(float4 &acc, const float4 x, const float4 h) {
+    acc.x = fmaf(x.x, h.x, acc.x);
+    acc.x = fmaf(-x.y, h.y, acc.x);
+    acc.y = fmaf(x.x, h.y, acc.y);
+    acc.y = fmaf(x.y, h.x, acc.y);
+    acc.z = fmaf(x.z, h.z, acc.z);
+    acc.z = fmaf(-x.w, h.w, acc.z);
+    acc.w = fmaf(x.z, h.w, acc.w);
+    acc.w = fmaf(x.w, h.z, acc.w);
+}
+
+// Streaming (read-once) 16-byte load: keep it out of L1 so that the shared
+// filter rows (read through ld_keep) stay cached.
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_keep(const float4 *p) {
+    return __ldg(p);
+}
+
+// grid: x = M/2/TPB (tiles of 2*TPB entries), y = ceil(nstreams/S), z = output groups.
+template <int NO, int S, int TPB>
+__global__ void __launch_bounds__(TPB)
+mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__restrict__ steps,
+           const int *__restrict__ group_off, const float4 *__restrict__ H, float4 *__restrict__ Y,
+           int M4, int P, int pt, int nout) {
+    const int e4 = blockIdx.x * TPB + threadIdx.x;
+    const int b0 = blockIdx.y * S;
+    const int g = blockIdx.z;
+
+    const float4 *xb[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int b = min(b0 + s, nstreams - 1);
+        xb[s] = reinterpret_cast<const float4 *>(st[b].xring) + e4;
+    }
+    float4 acc[NO][S];
+#pragma unroll
+    for (int o = 0; o < NO; o++)
+#pragma unroll
+        for (int s = 0; s < S; s++) acc[o][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int t0 = group_off[g], t1 = group_off[g + 1];
+#pragma unroll 2
+    for (int t = t0; t < t1; t++) {
+        const MacStep *sp = steps + t;
+        const int inp = __ldg(&sp->inp), part = __ldg(&sp->part);
+        int slot = pt - part;
+        if (slot < 0) slot += P;
+        const size_t xo = (size_t)(inp * P + slot) * (size_t)M4;
+        float4 x[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) x[s] = ld_stream(xb[s] + xo);
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+            const int row = __ldg(&sp->row[o]);
+            if (row >= 0) {
+                const float4 h = ld_keep(H + (size_t)row * (size_t)M4 + e4);
+#pragma unroll
+                for (int s = 0; s < S; s++) cmac2(acc[o][s], x[s], h);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NO; o++) {
+        const int oo = g * NO + o;
+        if (oo < nout) {
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (b0 + s < nstreams)
+                    __stcs(Y + ((size_t)(b0 + s) * nout + oo) * (size_t)M4 + e4, acc[o][s]);
+            }
+        }
+    }
+}
+
+}  // namespace fcv

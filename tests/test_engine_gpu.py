@@ -1,0 +1,249 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle and the
+float64 ground truth on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): float32 output within 1e-5 of full scale
+of the oracle; <= 1 LSB after 16-bit quantisation.
+"""
+import numpy as np
+import pytest
+
+from folve_b200 import capi
+from oracle_py import FilterSpec, OracleConvproc, run_blocks, truth_f64
+
+pytestmark = pytest.mark.gpu
+
+TOL_FS = 1e-5
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _engine(spec):
+    return spec.load(capi.Filter(spec.ninp, spec.nout, spec.size, spec.fragm)).commit(0)
+
+
+def _oracle(spec):
+    return spec.load(OracleConvproc(spec.ninp, spec.nout, spec.size, reset_is_fresh=True))
+
+
+def _three_way(spec, x):
+    f = _engine(spec)
+    s = capi.Stream(f)
+    y = run_blocks(s, x, spec.fragm)
+    yo = run_blocks(_oracle(spec), x, spec.fragm)
+    t = truth_f64(x, spec.impulses(), spec.nout)
+    fs = max(1.0, np.abs(t).max())
+    e_eo = np.abs(y - yo).max() / fs
+    e_et = np.abs(y - t).max() / fs
+    e_ot = np.abs(yo - t).max() / fs
+    assert y.shape == yo.shape == t.shape
+    assert e_eo < TOL_FS, (e_eo, e_et, e_ot)
+    assert e_et < TOL_FS, (e_eo, e_et, e_ot)
+    s.close()
+    f.close()
+    return y, yo, t
+
+
+@pytest.mark.parametrize("size", [20, 100, 200, 400, 900, 1800, 3000, 4096, 5000])
+def test_all_partition_sizes_mono(size):
+    """fragm = 64 ... 8192 (every FFT plan)."""
+    r = _rng(size)
+    spec = FilterSpec(1, 1, size).add(0, 0, r.standard_normal(size) / np.sqrt(size))
+    x = r.uniform(-0.5, 0.5, (3 * spec.fragm + 5, 1)).astype(np.float32)
+    _three_way(spec, x)
+
+
+def test_filter_spectra_match_oracle():
+    r = _rng(11)
+    spec = FilterSpec(2, 2, 30000)
+    spec.add(0, 0, r.standard_normal(20000) * 0.01, 500).add(1, 1, r.standard_normal(9000) * 0.01, 0)
+    spec.add(0, 0, [0.4], 0)
+    f, o = _engine(spec), _oracle(spec)
+    assert f.partitions == o.npar == 4
+    for (i, out) in ((0, 0), (1, 1), (0, 1)):
+        for j in range(4):
+            a, b = f.spectrum(i, out, j), o.fftb(i, out, j)
+            if b is None or not np.any(b):
+                assert a is None
+                continue
+            assert a is not None
+            assert np.abs(a - b).max() <= 2e-6 * max(np.abs(b).max(), 1e-3), (i, out, j)
+    f.close()
+
+
+def test_input_spectrum_matches_oracle():
+    r = _rng(12)
+    spec = FilterSpec(2, 2, 20000).add(0, 0, r.standard_normal(100)).add(1, 1, r.standard_normal(100))
+    f, o = _engine(spec), _oracle(spec)
+    s = capi.Stream(f)
+    x = r.uniform(-1, 1, (8192, 2)).astype(np.float32)
+    s.process(x)
+    o.process(x)
+    for ch in range(2):
+        a, b = s.input_spectrum(ch, 0), o.ffta(ch, 0)
+        assert np.abs(a - b).max() <= 3e-6 * np.abs(b).max()
+    s.close()
+    f.close()
+
+
+def test_stereo_long_reverb_shape():
+    """SantaLucia-shaped: 178193-tap IR at delay 500 plus a dirac, stereo diagonal."""
+    r = _rng(13)
+    spec = FilterSpec(2, 2, 204800)
+    env = np.exp(-np.arange(178193) / 40000.0)
+    for ch in range(2):
+        spec.add(ch, ch, r.standard_normal(178193) * env * 0.004, 500)
+        spec.add(ch, ch, [0.4], 0)
+    x = r.uniform(-0.03, 0.03, (30 * 8192 + 1234, 2)).astype(np.float32)
+    f = _engine(spec)
+    assert f.partitions == 25 and f.ring_depth == 22 and f.active_rows == 44
+    f.close()
+    y, yo, t = _three_way(spec, x)
+    # <= 1 LSB after 16-bit quantisation (lrintf(y * 32767), libsndfile convention)
+    q, qo = np.rint(y * 32767.0), np.rint(yo * 32767.0)
+    assert np.abs(q - qo).max() <= 1
+
+
+def test_mimo_crossfeed_with_link():
+    r = _rng(14)
+    spec = FilterSpec(2, 2, 10000)
+    spec.add(0, 0, r.standard_normal(4096) * 0.02).add(1, 1, r.standard_normal(4096) * 0.02)
+    spec.link(0, 0, 1, 0)
+    spec.add(0, 0, [0.25], 9000)
+    spec.add(0, 1, [0.3], 700)
+    x = r.uniform(-0.2, 0.2, (4 * 8192 + 5, 2)).astype(np.float32)
+    _three_way(spec, x)
+
+
+@pytest.mark.parametrize("nin,nout", [(1, 2), (3, 1), (6, 6), (5, 9)])
+def test_mimo_dense(nin, nout):
+    r = _rng(100 * nin + nout)
+    spec = FilterSpec(nin, nout, 9000)
+    for i in range(nin):
+        for o in range(nout):
+            if (i + o) % 3 != 2:  # leave some pairs empty
+                spec.add(i, o, r.standard_normal(2000 + 500 * o) * 0.01, 100 * i)
+    x = r.uniform(-0.3, 0.3, (3 * 8192 + 11, nin)).astype(np.float32)
+    _three_way(spec, x)
+
+
+def test_block_edges_clicks_and_short_files():
+    r = _rng(15)
+    spec = FilterSpec(1, 1, 20000).add(0, 0, r.standard_normal(20000) * 0.01)
+    N = spec.fragm
+    for frames in (1, N - 1, N, N + 1, 3 * N + 7):
+        x = np.zeros((frames, 1), np.float32)
+        for pos in (0, N - 1, N, 2 * N - 1):
+            if pos < frames:
+                x[pos, 0] = 1.0
+        _three_way(spec, x)
+
+
+def test_impulse_returns_filter_exact_positions():
+    r = _rng(16)
+    h = (r.standard_normal(9000) * 0.01).astype(np.float32)
+    spec = FilterSpec(1, 1, 9000).add(0, 0, h)
+    x = np.zeros((3 * 8192, 1), np.float32)
+    x[0, 0] = 1.0
+    y, _, _ = _three_way(spec, x)
+    assert np.abs(y[:9000, 0] - h).max() < 2e-6
+    assert np.abs(y[9000:, 0]).max() < 2e-6
+
+
+def test_reset_equals_fresh_and_signed_max():
+    r = _rng(17)
+    spec = FilterSpec(1, 1, 300).add(0, 0, [-1.0])   # inverter: negative peaks become positive
+    f = _engine(spec)
+    s = capi.Stream(f)
+    x = r.uniform(-0.5, 0.25, (3 * spec.fragm, 1)).astype(np.float32)
+    y1 = run_blocks(s, x, spec.fragm)
+    # sound-processor.cc:120-123: signed comparison, no fabs
+    assert s.max_value == pytest.approx(max(0.0, float(y1.max())), abs=1e-6)
+    s.process(x[:spec.fragm])          # odd number of extra blocks, then reset
+    s.reset()
+    assert s.max_value == 0.0
+    y2 = run_blocks(s, x, spec.fragm)
+    assert np.array_equal(y1, y2)
+    s.close()
+    f.close()
+
+
+def test_batch_matches_single_streams_and_formats():
+    r = _rng(18)
+    spec = FilterSpec(2, 2, 20000)
+    for ch in range(2):
+        spec.add(ch, ch, r.standard_normal(20000) * 0.005, 0)
+    f = _engine(spec)
+    N, B, nblk = spec.fragm, 7, 4
+    x = r.uniform(-0.4, 0.4, (B, nblk * N, 2)).astype(np.float32)
+    ref = [run_blocks(capi.Stream(f), x[b], N) for b in range(B)]
+    bt = capi.Batch(f, B)
+    outs = []
+    for k in range(nblk):
+        bt.host_in[:] = x[:, k * N:(k + 1) * N]
+        bt.process()
+        outs.append(bt.host_out.copy())
+    y = np.concatenate(outs, axis=1)
+    for b in range(B):
+        assert np.array_equal(y[b], ref[b])
+    mx = bt.get_max()
+    assert np.allclose(mx, np.maximum(0.0, y.max(axis=(1, 2))), atol=1e-7)
+    bt.close()
+
+    # int16 wire format, fused conversion: x/32768 in, lrintf(y*32767) out
+    xi = np.rint(x * 20000).astype(np.int16)
+    bs = capi.Batch(f, B, capi.PCM_S16, capi.PCM_S16)
+    oi = []
+    for k in range(nblk):
+        bs.host_in[:] = xi[:, k * N:(k + 1) * N]
+        bs.process()
+        oi.append(bs.host_out.copy())
+    yi = np.concatenate(oi, axis=1)
+    o = _oracle(spec)
+    yo = run_blocks(o, xi[0].astype(np.float32) / 32768.0, N)
+    assert np.abs(yi[0].astype(np.int64) - np.rint(yo * 32767.0).astype(np.int64)).max() <= 1
+    bs.close()
+    f.close()
+
+
+def test_batch_frames_valid_and_slot_reset():
+    r = _rng(19)
+    spec = FilterSpec(1, 1, 5000).add(0, 0, r.standard_normal(5000) * 0.01)
+    f = _engine(spec)
+    N, B = spec.fragm, 5
+    bt = capi.Batch(f, B)
+    x = r.uniform(-0.4, 0.4, (B, N, 1)).astype(np.float32)
+    fv = np.array([N, 1, N // 2, 0, N - 1], np.int32)
+    bt.host_in[:] = x
+    bt.process(fv)
+    o = _oracle(spec)
+    for b in range(B):
+        o.reset()
+        if fv[b]:
+            yo = o.process(x[b, :fv[b]])
+            assert np.abs(bt.host_out[b, :fv[b]] - yo).max() < TOL_FS
+    # reset slot 0 only: slot 0 behaves fresh, slot 4 keeps its history
+    bt.reset_slot(0)
+    bt.host_in[:] = 0
+    bt.process()
+    assert np.all(bt.host_out[0] == 0.0)
+    assert np.abs(bt.host_out[4]).max() > 0.0
+    bt.close()
+    f.close()
+
+
+def test_errors_are_reported_not_fatal():
+    L = capi.lib()
+    assert not L.fcv_filter_begin(0, 2, 100, 64)
+    assert b"out of range" in L.fcv_last_error()
+    assert not L.fcv_filter_begin(2, 2, 100, 100)       # fragm not a power of two
+    f = capi.Filter(1, 1, 100, 64)
+    with pytest.raises(capi.FcvError):
+        f.add(1, 0, [1.0], 0)
+    with pytest.raises(capi.FcvError):
+        capi.Stream(f)                                   # not committed
+    f.commit(0)
+    with pytest.raises(capi.FcvError):
+        f.add(0, 0, [1.0], 0)                            # immutable after commit
+    f.close()

@@ -1,0 +1,121 @@
+"""CPU: the zita-convolver restatement (oracle/) against the float64 ground truth.
+
+The reference ships no golden vectors, so the oracle is pinned
+against the mathematical definition of the path: y[o] = sum_i h[i,o] * x[i],
+output length == input length, zero latency.
+"""
+import numpy as np
+import pytest
+
+from oracle_py import FilterSpec, OracleConvproc, fragm_for, run_blocks, truth_f64
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _check(spec, x, tol=2e-6):
+    o = spec.load(OracleConvproc(spec.ninp, spec.nout, spec.size))
+    y = run_blocks(o, x, spec.fragm)
+    t = truth_f64(x, spec.impulses(), spec.nout)
+    scale = max(1.0, np.abs(t).max())
+    err = np.abs(y - t).max() / scale
+    assert y.shape == t.shape
+    assert err < tol, err
+    return y, t
+
+
+def test_fragm_rule():
+    # zita-fconfig.cc:74-77
+    assert fragm_for(65536) == 8192
+    assert fragm_for(204800) == 8192
+    assert fragm_for(4097) == 8192
+    assert fragm_for(4096) == 4096
+    assert fragm_for(2048) == 2048
+    assert fragm_for(100) == 128
+    assert fragm_for(64) == 64
+    assert fragm_for(1) == 64
+
+
+@pytest.mark.parametrize("size,taps", [(64, 40), (300, 300), (1000, 777), (5000, 5000), (20000, 20000)])
+def test_mono_random_filter(size, taps):
+    r = _rng(size)
+    spec = FilterSpec(1, 1, size).add(0, 0, r.standard_normal(taps) / np.sqrt(taps))
+    x = r.uniform(-0.5, 0.5, (3 * spec.fragm + 17, 1)).astype(np.float32)
+    _check(spec, x)
+
+
+def test_impulse_returns_filter():
+    r = _rng(1)
+    h = (r.standard_normal(9000) * 0.01).astype(np.float32)
+    spec = FilterSpec(1, 1, 9000).add(0, 0, h)
+    x = np.zeros((3 * 8192, 1), np.float32)
+    x[0, 0] = 1.0
+    y, _ = _check(spec, x)
+    assert np.abs(y[:9000, 0] - h).max() < 1e-6
+    assert np.abs(y[9000:, 0]).max() < 1e-6
+
+
+def test_stereo_diag_accumulate_and_dirac():
+    # the SantaLucia pattern: /impulse/read and /impulse/dirac on the same pair add
+    r = _rng(2)
+    spec = FilterSpec(2, 2, 30000)
+    for ch in range(2):
+        spec.add(ch, ch, r.standard_normal(20000) * 0.004, 500)
+        spec.add(ch, ch, [0.4], 0)
+    x = r.uniform(-0.03, 0.03, (5 * 8192 + 123, 2)).astype(np.float32)
+    _check(spec, x)
+
+
+def test_mimo_with_link():
+    r = _rng(3)
+    spec = FilterSpec(2, 2, 10000)
+    spec.add(0, 0, r.standard_normal(4096) * 0.02)
+    spec.add(1, 1, r.standard_normal(4096) * 0.02)
+    spec.link(0, 0, 1, 0)           # cross path uses the spectra of (0,0)
+    spec.add(0, 0, [0.25], 9000)    # later addition to the source is seen by the link
+    spec.add(0, 1, [0.3], 700)
+    x = r.uniform(-0.2, 0.2, (4 * 8192 + 5, 2)).astype(np.float32)
+    _check(spec, x)
+
+
+def test_block_edges_and_short_files():
+    r = _rng(4)
+    spec = FilterSpec(1, 1, 20000).add(0, 0, r.standard_normal(20000) * 0.01)
+    N = spec.fragm
+    for frames in (1, N - 1, N, N + 1, 3 * N + 7):
+        x = np.zeros((frames, 1), np.float32)
+        for pos in (0, N - 1, N, 2 * N - 1):
+            if pos < frames:
+                x[pos, 0] = 1.0
+        _check(spec, x)
+
+
+def test_reset_quirk_documented():
+    """with the recalled library behaviour a Reset()
+    after an odd number of blocks leaves Convproc::_inpoffs in the second half,
+    so the re-used processor lags by one block; with reset_is_fresh it does not."""
+    r = _rng(5)
+    h = r.standard_normal(100) * 0.1
+    x = r.uniform(-0.5, 0.5, (2 * 128, 1)).astype(np.float32)
+    t = truth_f64(x, {(0, 0): h}, 1)
+    for fresh in (False, True):
+        o = OracleConvproc(1, 1, 100, reset_is_fresh=fresh)
+        o.add(0, 0, h, 0)
+        o.reset()
+        o.process(x[:128])          # one (odd) block
+        o.reset()                   # ProcessorPool::Return -> Reset
+        y = run_blocks(o, x, 128)
+        if fresh:
+            assert np.abs(y - t).max() < 1e-5
+        else:
+            assert np.abs(y[:128]).max() == 0.0          # one block of silence
+            assert np.abs(y[128:] - t[:128]).max() < 1e-5  # then everything one block late
+
+
+def test_unused_output_is_silent():
+    spec = FilterSpec(2, 2, 100).add(0, 0, [1.0])
+    x = _rng(6).uniform(-1, 1, (300, 2)).astype(np.float32)
+    y, _ = _check(spec, x)
+    assert np.all(y[:, 1] == 0.0)
+    assert np.abs(y[:, 0] - x[:, 0]).max() < 1e-6
