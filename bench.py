@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- the convolution hot path on N B200s of one node.
+
+Metric (BASELINE.json): convolved audio-seconds per second (x realtime).
+A step = one block of `fragm` frames for every stream of the batch (forward FFT
+of each input channel, complex MAC over the partition history, inverse FFT +
+overlap-add) -- SoundProcessor::Process() (sound-processor.cc:98-127) for
+`--streams` independent SoundProcessors per GPU at once.
+
+  value : device-resident (PCM already in HBM), CUDA events, max over ranks
+  e2e   : through the C-ABI call fcv_batch_process with pinned HOST buffers,
+          host->device and device->host copies inside the timed region
+  roofline : the complex-MAC kernel against the measured HBM copy bandwidth
+  cpu_baseline : the zita-convolver restatement on all host cores (rank 0, N=1)
+
+`--impl reference` times the CPU path (one Convproc per stream, one stream per
+thread, all cores) on the same workload; see DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from folve_b200 import workloads  # noqa: E402
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 100 ms (NVML)."""
+
+    BITS = {
+        0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
+    }
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join()
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _oracle_lib():
+    so = os.path.join(ROOT, "oracle", "libzita_oracle.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    L = C.CDLL(so)
+
+    class Imp(C.Structure):
+        _fields_ = [("inp", C.c_int), ("out", C.c_int), ("ind0", C.c_int), ("len", C.c_int),
+                    ("data", C.POINTER(C.c_float))]
+
+    L.zb_run.restype = C.c_double
+    L.zb_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int,
+                         C.POINTER(Imp), C.c_float, C.POINTER(C.c_double)]
+    return L, Imp
+
+
+def cpu_run(wl, nthreads, nblocks, amplitude=0.03):
+    """One Convproc per stream, one stream per thread; returns (audio_s, wall_s)."""
+    L, Imp = _oracle_lib()
+    keep = [np.ascontiguousarray(d, np.float32) for (_, _, d, _) in wl.adds]
+    imps = (Imp * len(wl.adds))()
+    for k, (i, o, d, i0) in enumerate(wl.adds):
+        imps[k].inp, imps[k].out, imps[k].ind0, imps[k].len = i, o, i0, len(d)
+        imps[k].data = keep[k].ctypes.data_as(C.POINTER(C.c_float))
+    cs = C.c_double(0)
+    wall = L.zb_run(nthreads, nblocks, wl.ninp, wl.nout, wl.size, wl.fragm, len(wl.adds), imps,
+                    amplitude, C.byref(cs))
+    if wall <= 0:
+        raise RuntimeError("cpu baseline failed")
+    return nthreads * nblocks * wl.fragm / wl.fs, wall
+
+
+def cpu_baseline(wl, target_s=12.0):
+    cores = len(os.sched_getaffinity(0))
+    audio, wall = cpu_run(wl, cores, 8)           # calibration (also warms the cores)
+    nb = max(8, min(4096, int(8 * target_s / wall)))
+    audio, wall = cpu_run(wl, cores, nb)
+    return {
+        "value": audio / wall, "unit": "x realtime (audio-s per wall-s)", "cores": cores, "kind": "port",
+        "sample": f"{cores} streams x {nb} blocks of {wl.fragm} frames ({wl.name}), one restated Convproc per "
+                  f"stream, one stream per thread; {wall:.1f} s wall",
+    }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wl = workloads.WORKLOADS[args.workload]()
+    cores = len(os.sched_getaffinity(0))
+    audio, wall = cpu_run(wl, cores, 4)
+    nb = max(4, min(2048, int(4 * 4.0 / wall)))   # ~4 s of CPU work per step
+    for _ in range(args.warmup):
+        cpu_run(wl, cores, max(2, nb // 4))
+    t_audio = t_wall = 0.0
+    for _ in range(args.steps):
+        a, w = cpu_run(wl, cores, nb)
+        t_audio += a
+        t_wall += w
+    v = t_audio / t_wall
+    unit = "x realtime (audio-s per wall-s)"
+    line = {
+        "impl": "reference", "metric": "convolved audio-seconds per second", "value": v, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "fs": wl.fs, "channels": wl.ninp, "fragm": wl.fragm,
+                   "streams": cores, "blocks_per_step": nb},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"per step: {cores} streams x {nb} blocks of {wl.fragm} frames, one restated "
+                                   "Convproc (oracle/zita_oracle.c) per stream, one stream per thread"},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(wl_name, streams):
+    """dram bytes per MAC launch from the committed ncu --set full summary, if one matches."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "mac_traffic.json")))
+        e = d.get(f"{wl_name}:{streams}")
+        return float(e["dram_bytes_per_launch"]) if e else None
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="santalucia", choices=sorted(workloads.WORKLOADS))
+    ap.add_argument("--streams", type=int, default=1024, help="concurrent streams PER GPU")
+    ap.add_argument("--wire", default="f32", choices=["f32", "s16"], help="PCM format of the host buffers")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from folve_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = workloads.WORKLOADS[args.workload]()
+    flt = wl.load(capi.Filter(wl.ninp, wl.nout, wl.size, wl.fragm)).commit(local_rank)
+    B, N, K, W = args.streams, wl.fragm, args.steps, args.warmup
+    fmt = capi.PCM_F32 if args.wire == "f32" else capi.PCM_S16
+    batch = capi.Batch(flt, B, fmt, fmt)
+    x = workloads.synthetic_pcm(B, N, wl.ninp, 0.03, 1000 + rank)
+    batch.host_in[:] = x if fmt == capi.PCM_F32 else np.rint(x * 32768.0).astype(np.int16)
+    L = capi.lib()
+
+    clocks = ClockSampler(local_rank)
+
+    # ---- end to end through the C ABI: pinned host in -> pinned host out, every step
+    for _ in range(W):
+        batch.process()
+    barrier()
+    clocks.start()
+    n0 = L.fcv_kernel_launches()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        batch.process()          # synchronous: returns when host_out is complete
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    launches_e2e = L.fcv_kernel_launches() - n0
+    barrier()
+
+    # ---- device resident: PCM already in HBM (left there by the steps above)
+    batch.set_profiling(True)
+    for _ in range(W):
+        batch.process_device()
+    batch.profile()              # drop warm-up timings
+    barrier()
+    n0 = L.fcv_kernel_launches()
+    batch.event_record(0)
+    for _ in range(K):
+        batch.process_device()
+    batch.event_record(1)
+    batch.sync()
+    torch.cuda.synchronize()
+    dev_ms = max_over_ranks(batch.event_elapsed_ms(0, 1))
+    launches = L.fcv_kernel_launches() - n0
+    kms, ksteps = batch.profile()
+    clk = clocks.stop()
+    barrier()
+
+    audio_per_step = world * B * N / wl.fs
+    value = audio_per_step * K / (dev_ms * 1e-3)
+    e2e_value = audio_per_step * K / e2e_s
+
+    # roofline of the complex-MAC kernel: SURVEY section 8(d) algorithmic bytes
+    P, rows, I, O = flt.ring_depth, flt.active_rows, wl.ninp, wl.nout
+    bytes_mac = 8 * (N + 1) * (B * P * I + rows + B * O)
+    mac_ms = kms[1] / max(1, ksteps)
+    peak, peak_src = measured_peak()
+    achieved = bytes_mac / (mac_ms * 1e-3) / 1e9
+    traffic = ncu_traffic(wl.name, B)
+
+    if rank == 0:
+        wire_bytes = 4 if fmt == capi.PCM_F32 else 2
+        line = {
+            "metric": "convolved audio-seconds per second", "value": value,
+            "unit": "x realtime (audio-s per wall-s)", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{wl.name}: {wl.ninp}x{wl.nout} fs={wl.fs} size={wl.size} fragm={N} "
+                            f"partitions={flt.partitions} (non-zero ring depth {P}, {rows} filter rows)",
+                "streams_per_gpu": B, "blocks_per_step": 1, "frames_per_block": N,
+                "audio_seconds_per_step": audio_per_step, "wire_format": args.wire,
+                "l2": f"per-step working set {(bytes_mac + 0) / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2)",
+                "parallelism": f"{world} x independent stream shards, no collective",
+            },
+            "e2e": {"value": e2e_value, "unit": "x realtime (audio-s per wall-s)",
+                    "h2d_bytes_per_step": B * N * I * wire_bytes, "d2h_bytes_per_step": B * N * O * wire_bytes,
+                    "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
+            "kernel_ms_per_step": {"fwd_fft": kms[0] / max(1, ksteps), "mac": mac_ms,
+                                   "inv_fft": kms[2] / max(1, ksteps)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "mac_kernel",
+                         "algorithmic_bytes_per_launch": bytes_mac, "peak_source": peak_src},
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+
+    batch.close()
+    flt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
         "fcv_batch_reset_slot": (i, [vp, i]),
         "fcv_batch_get_max": (i, [vp, fp]),
         "fcv_batch_cuda_stream": (vp, [vp]),
+        "fcv_batch_event_record": (i, [vp, i]),
+        "fcv_batch_event_elapsed_ms": (i, [vp, i, i, fp]),
         "fcv_batch_set_profiling": (i, [vp, i]),
         "fcv_batch_profile": (i, [vp, fp, ip]),
         "fcv_kernel_launches": (C.c_ulonglong, []),
@@ -247,6 +249,14 @@ class Batch:
     def device_in(self): return lib().fcv_batch_device_in(self._h)
     @property
     def device_out(self): return lib().fcv_batch_device_out(self._h)
+
+    def event_record(self, slot):
+        _check(lib().fcv_batch_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, slot0, slot1):
+        ms = C.c_float(0)
+        _check(lib().fcv_batch_event_elapsed_ms(self._h, slot0, slot1, C.byref(ms)))
+        return ms.value
 
     def set_profiling(self, on):
         _check(lib().fcv_batch_set_profiling(self._h, 1 if on else 0))

@@ -576,6 +576,8 @@ struct fcv_batch {
     // streams
     static const int NQ = 4;
     cudaStream_t q[NQ] = {};
+    // stopwatch
+    cudaEvent_t sw[16] = {};
     // profiling
     bool profiling = false;
     std::vector<cudaEvent_t> ev;  // 4 events per step: t0 | fwd | mac | inv
@@ -589,6 +591,7 @@ static void batch_free(fcv_batch *b) {
     if (!b) return;
     if (b->f && b->f->device >= 0) cudaSetDevice(b->f->device);
     for (auto e : b->ev) cudaEventDestroy(e);
+    for (int i = 0; i < 16; i++) if (b->sw[i]) cudaEventDestroy(b->sw[i]);
     for (int i = 0; i < fcv_batch::NQ; i++)
         if (b->q[i]) { cudaStreamSynchronize(b->q[i]); cudaStreamDestroy(b->q[i]); }
     if (b->dmem) cudaFree(b->dmem);
@@ -835,6 +838,23 @@ extern "C" int fcv_batch_get_max(fcv_batch *b, float *max_out) {
     int rc = fcv_batch_sync(b);
     if (rc) return rc;
     CU_TRY(cudaMemcpy(max_out, b->maxv, (size_t)b->B * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int fcv_batch_event_record(fcv_batch *b, int slot) {
+    if (!b || slot < 0 || slot >= 16) return fail(FCV_E_PARAM, "bad event slot");
+    CU_TRY(cudaSetDevice(b->f->device));
+    if (!b->sw[slot]) CU_TRY(cudaEventCreate(&b->sw[slot]));
+    CU_TRY(cudaEventRecord(b->sw[slot], b->q[0]));
+    return 0;
+}
+
+extern "C" int fcv_batch_event_elapsed_ms(fcv_batch *b, int slot0, int slot1, float *ms) {
+    if (!b || !ms || slot0 < 0 || slot0 >= 16 || slot1 < 0 || slot1 >= 16 || !b->sw[slot0] || !b->sw[slot1])
+        return fail(FCV_E_PARAM, "bad event slot");
+    CU_TRY(cudaSetDevice(b->f->device));
+    CU_TRY(cudaEventSynchronize(b->sw[slot1]));
+    CU_TRY(cudaEventElapsedTime(ms, b->sw[slot0], b->sw[slot1]));
     return 0;
 }
 

@@ -178,6 +178,11 @@ int fcv_batch_get_max(fcv_batch *b, float *max_out /* [nstreams] */);
 /* cudaStream_t the batch launches on (as void*), for CUDA-event timing by the caller. */
 void *fcv_batch_cuda_stream(fcv_batch *b);
 
+/* CUDA-event stopwatch on the batch's stream: record event `slot` (0..15) now,
+ * and later read the device time between two recorded slots (synchronises). */
+int fcv_batch_event_record(fcv_batch *b, int slot);
+int fcv_batch_event_elapsed_ms(fcv_batch *b, int slot0, int slot1, float *ms);
+
 /* Per-kernel timing: when enabled, every launch is bracketed by CUDA events on
  * the batch's stream.  fcv_batch_profile() synchronises and returns the summed
  * device milliseconds per kernel since the last call and the number of blocks

@@ -232,6 +232,14 @@ static void level_reset(zo_level *L, uint32_t inpsize, uint32_t outsize, float *
     L->opind = 0;
 }
 
+/* The inner loop of Convlevel::process: freq_data[k] += ffta[k] * fftb[k]. */
+static void mac_row(float *restrict fd, const float *restrict a, const float *restrict b, uint32_t n) {
+    for (uint32_t k = 0; k < n; k++) {
+        fd[2 * k] += a[2 * k] * b[2 * k] - a[2 * k + 1] * b[2 * k + 1];
+        fd[2 * k + 1] += a[2 * k] * b[2 * k + 1] + a[2 * k + 1] * b[2 * k];
+    }
+}
+
 /* Convlevel::process(skip = false) */
 static void level_process(zo_level *L) {
     uint32_t i1 = L->inpoffs, n1 = L->parsize, n2 = 0;
@@ -263,12 +271,7 @@ static void level_process(zo_level *L) {
                 const float *ffta = X->ffta[i];
                 const float *fftb = M->link ? (M->link->fftb ? M->link->fftb[j] : NULL)
                                             : (M->fftb ? M->fftb[j] : NULL);
-                if (fftb) {
-                    for (uint32_t k = 0; k <= ps; k++) {
-                        fd[2 * k] += ffta[2 * k] * fftb[2 * k] - ffta[2 * k + 1] * fftb[2 * k + 1];
-                        fd[2 * k + 1] += ffta[2 * k] * fftb[2 * k + 1] + ffta[2 * k + 1] * fftb[2 * k];
-                    }
-                }
+                if (fftb) mac_row(fd, ffta, fftb, ps + 1);
                 if (i == 0) i = L->npar;
                 i--;
             }
