@@ -27,6 +27,10 @@
 
 using namespace fcv;
 
+#ifndef FFT_MIN_CTAS
+#define FFT_MIN_CTAS 2
+#endif
+
 // ---------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------
@@ -59,7 +63,7 @@ static int fail(int code, const char *fmt, ...) {
 // fused int/float conversion + de-interleave + zero padding + real FFT, written
 // into ring slot `pt` of the stream's input-spectra ring.
 template <int LOG2N>
-__global__ void __launch_bounds__(fft_threads(LOG2N))
+__global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
                   int ninp, int P, int pt, int in_fmt, int reset_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,26 +75,65 @@ fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     float2 *row = s.xring + (size_t)(i * P + pt) * N;
     // per-block maximum mode: the inverse kernel of this block starts from zero
     if (reset_max && i == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
-    fwd_body<LOG2N>(sm, tb, s.din, in_fmt, ninp, i, frames, 1.0f, row);
+    if (in_fmt == PCM_F32) fwd_body<LOG2N, PCM_F32>(sm, tb, s.din, ninp, i, frames, row);
+    else if (in_fmt == PCM_S16) fwd_body<LOG2N, PCM_S16>(sm, tb, s.din, ninp, i, frames, row);
+    else fwd_body<LOG2N, PCM_S24>(sm, tb, s.din, ninp, i, frames, row);
 }
 
 // Forward transform of raw float partitions (filter preparation, K6):
 // src[row][N] -> dst[row][M].
 template <int LOG2N>
-__global__ void __launch_bounds__(fft_threads(LOG2N))
+__global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 fwd_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, FftTables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     constexpr int N = 1 << LOG2N;
     const size_t r = blockIdx.x;
-    fwd_body<LOG2N>(sm, tb, src + r * N, PCM_F32, 1, 0, N, 1.0f, dst + r * N);
+    fwd_body<LOG2N, PCM_F32>(sm, tb, src + r * N, 1, 0, N, dst + r * N);
+}
+
+// Overlap-add, tail save, re-interleave, float/int conversion and signed maximum
+// of one output channel; returns this thread's maximum over the valid frames.
+template <int LOG2N, int FMT>
+__device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables &tb, float2 *__restrict__ tail,
+                                              void *dout, int nout, int o, int frames) {
+    constexpr int N = 1 << LOG2N, Q = N / 2;
+    constexpr int NT = fft_threads(LOG2N);
+    constexpr int CH = (Q / NT) < 8 ? (Q / NT) : 8;
+    const int tid = threadIdx.x;
+    float lmax = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < Q / NT; c += CH) {
+        float2 w[CH], tl[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int n = tid + (c + i) * NT;
+            w[i] = __ldg(&tb.twA[n]);
+            tl[i] = tail[n];
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int n = tid + (c + i) * NT;
+            const float2 a = sm[smem_pad(n)];
+            const float2 t = cmulconj(sm[smem_pad(Q + n)], w[i]);
+            const float y0 = a.x + t.x + tl[i].x;
+            const float y1 = a.y + t.y + tl[i].y;
+            tail[n] = make_float2(a.x - t.x, a.y - t.y);
+            const int f0 = 2 * n;
+            pcm_store<FMT>(dout, (size_t)f0 * nout + o, y0);
+            pcm_store<FMT>(dout, (size_t)(f0 + 1) * nout + o, y1);
+            if (f0 < frames) lmax = fmaxf(lmax, y0);
+            if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
+        }
+    }
+    return lmax;
 }
 
 // Inverse transform of every (stream, output channel) with fused DC/Nyquist
 // products, overlap-add, tail save, re-interleave, float/int conversion and
 // running signed maximum.
 template <int LOG2N>
-__global__ void __launch_bounds__(fft_threads(LOG2N))
+__global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
                   const float2 *__restrict__ Y, const MacStep *__restrict__ steps,
                   const int *__restrict__ group_off, const float2 *__restrict__ H, int group_no,
@@ -98,15 +141,12 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     __shared__ float red[32];
-    constexpr int N = 1 << LOG2N, Q = N / 2, M = N;
+    constexpr int N = 1 << LOG2N, M = N;
     constexpr int NT = fft_threads(LOG2N);
     const int tid = threadIdx.x;
     const int o = blockIdx.x, b = blockIdx.y;
     const StreamDev s = st[b];
     const int frames = fv ? fv[b] : N;
-
-    const float2 *yrow = Y + ((size_t)b * nout + o) * M;
-    for (int e = tid; e < M; e += NT) sm[smem_pad(e)] = __ldcs(&yrow[e]);
 
     // DC and Nyquist are real bins sharing entry 0: redo their products as two
     // real multiply-accumulates (the MAC kernel treated the entry as complex).
@@ -124,6 +164,9 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
                 ny = fmaf(x.y, h.y, ny);
             }
         }
+    }
+    inv_load<LOG2N>(sm, Y + ((size_t)b * nout + o) * M);
+    if (tid < 32) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             dc += __shfl_xor_sync(0xffffffffu, dc, d);
@@ -137,20 +180,10 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     inv_body<LOG2N>(sm, tb);
 
     float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
-    float lmax = 0.0f;
-    for (int n = tid; n < Q; n += NT) {
-        const float2 a = sm[smem_pad(n)];
-        const float2 t = cmulconj(sm[smem_pad(Q + n)], __ldg(&tb.twA[n]));
-        const float2 tl = tail[n];
-        const float y0 = a.x + t.x + tl.x;
-        const float y1 = a.y + t.y + tl.y;
-        tail[n] = make_float2(a.x - t.x, a.y - t.y);
-        const int f0 = 2 * n;
-        pcm_store(s.dout, out_fmt, (size_t)f0 * nout + o, y0);
-        pcm_store(s.dout, out_fmt, (size_t)(f0 + 1) * nout + o, y1);
-        if (f0 < frames) lmax = fmaxf(lmax, y0);
-        if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
-    }
+    float lmax;
+    if (out_fmt == PCM_F32) lmax = inv_epilogue<LOG2N, PCM_F32>(sm, tb, tail, s.dout, nout, o, frames);
+    else if (out_fmt == PCM_S16) lmax = inv_epilogue<LOG2N, PCM_S16>(sm, tb, tail, s.dout, nout, o, frames);
+    else lmax = inv_epilogue<LOG2N, PCM_S24>(sm, tb, tail, s.dout, nout, o, frames);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
     if ((tid & 31) == 0) red[tid >> 5] = lmax;

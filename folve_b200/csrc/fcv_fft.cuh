@@ -255,82 +255,158 @@ __device__ __forceinline__ int partner_entry(int e, int &kp_out, int &kpp_out) {
 // ---- PCM wire formats ---------------------------------------------------------
 enum { PCM_F32 = 0, PCM_S16 = 1, PCM_S24 = 2 };
 
-__device__ __forceinline__ float pcm_load(const void *p, int fmt, size_t idx) {
-    if (fmt == PCM_F32) return __ldg((const float *)p + idx);
-    if (fmt == PCM_S16) return (float)__ldg((const short *)p + idx) * (1.0f / 32768.0f);
-    return (float)__ldg((const int *)p + idx) * (1.0f / 8388608.0f);
-}
-__device__ __forceinline__ void pcm_store(void *p, int fmt, size_t idx, float v) {
-    if (fmt == PCM_F32) { ((float *)p)[idx] = v; return; }
-    if (fmt == PCM_S16) {
-        // libsndfile f2s_array without clipping: lrintf(x * 0x7FFF), stored to a short (wraps)
-        ((short *)p)[idx] = (short)__float2int_rn(v * 32767.0f);
-        return;
+// Frames 2n and 2n+1 of channel `chan` of an interleaved block as (x[2n], x[2n+1]).
+// Stereo and mono blocks use one vector load per pair of frames.
+template <int FMT>
+__device__ __forceinline__ float2 pcm_load2(const void *in, int nchan, int chan, int n) {
+    if (FMT == PCM_F32) {
+        if (nchan == 2) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(in) + n);
+            return chan ? make_float2(v.y, v.w) : make_float2(v.x, v.z);
+        }
+        if (nchan == 1) return __ldg(reinterpret_cast<const float2 *>(in) + n);
+        const float *p = reinterpret_cast<const float *>(in) + (size_t)(2 * n) * nchan + chan;
+        return make_float2(__ldg(p), __ldg(p + nchan));
+    } else if (FMT == PCM_S16) {
+        constexpr float K = 1.0f / 32768.0f;
+        if (nchan == 2) {
+            const short4 v = __ldg(reinterpret_cast<const short4 *>(in) + n);
+            return chan ? make_float2(v.y * K, v.w * K) : make_float2(v.x * K, v.z * K);
+        }
+        if (nchan == 1) {
+            const short2 v = __ldg(reinterpret_cast<const short2 *>(in) + n);
+            return make_float2(v.x * K, v.y * K);
+        }
+        const short *p = reinterpret_cast<const short *>(in) + (size_t)(2 * n) * nchan + chan;
+        return make_float2(__ldg(p) * K, __ldg(p + nchan) * K);
+    } else {
+        constexpr float K = 1.0f / 8388608.0f;
+        if (nchan == 2) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(in) + n);
+            return chan ? make_float2(v.y * K, v.w * K) : make_float2(v.x * K, v.z * K);
+        }
+        const int *p = reinterpret_cast<const int *>(in) + (size_t)(2 * n) * nchan + chan;
+        return make_float2(__ldg(p) * K, __ldg(p + nchan) * K);
     }
-    ((int *)p)[idx] = __float2int_rn(v * 8388607.0f);
+}
+
+template <int FMT>
+__device__ __forceinline__ void pcm_store(void *p, size_t idx, float v) {
+    if (FMT == PCM_F32) {
+        reinterpret_cast<float *>(p)[idx] = v;
+    } else if (FMT == PCM_S16) {
+        // libsndfile f2s_array without clipping: lrintf(x * 0x7FFF) stored to a short (wraps)
+        reinterpret_cast<short *>(p)[idx] = (short)__float2int_rn(v * 32767.0f);
+    } else {
+        reinterpret_cast<int *>(p)[idx] = __float2int_rn(v * 8388607.0f);
+    }
 }
 
 // ---- forward: one zero-padded partition -> packed-permuted spectrum -----------
 // in: interleaved PCM, `nchan` channels, channel `chan`; frames >= frames_valid read as 0.
-template <int LOG2N>
-__device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const void *in, int fmt,
-                                         int nchan, int chan, int frames_valid, float scale,
-                                         float2 *__restrict__ out_row) {
+// All global loads of a stage are issued before their first use (the stages are
+// latency bound otherwise: one CTA only has 8 warps).
+template <int LOG2N, int FMT>
+__device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const void *in, int nchan,
+                                         int chan, int frames_valid, float2 *__restrict__ out_row) {
     constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
     constexpr int NT = fft_threads(LOG2N);
+    constexpr int IT = Q / NT;
     const int tid = threadIdx.x;
-    for (int n = tid; n < Q; n += NT) {
-        const int f0 = 2 * n, f1 = 2 * n + 1;
-        float2 z;
-        z.x = f0 < frames_valid ? pcm_load(in, fmt, (size_t)f0 * nchan + chan) * scale : 0.0f;
-        z.y = f1 < frames_valid ? pcm_load(in, fmt, (size_t)f1 * nchan + chan) * scale : 0.0f;
-        sm[smem_pad(n)] = z;
-        sm[smem_pad(Q + n)] = cmul(z, __ldg(&tb.twA[n]));
+    {
+        float2 z[IT], w[IT];
+#pragma unroll
+        for (int it = 0; it < IT; it++) z[it] = pcm_load2<FMT>(in, nchan, chan, tid + it * NT);
+#pragma unroll
+        for (int it = 0; it < IT; it++) w[it] = __ldg(&tb.twA[tid + it * NT]);
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int n = tid + it * NT;
+            float2 v = z[it];
+            if (2 * n >= frames_valid) v.x = 0.0f;
+            if (2 * n + 1 >= frames_valid) v.y = 0.0f;
+            sm[smem_pad(n)] = v;
+            sm[smem_pad(Q + n)] = cmul(v, w[it]);
+        }
     }
     __syncthreads();
     fwd_passes<QL, NT>(sm, tb, tid);
-    for (int e = tid; e < M; e += NT) {
-        int kp, kpp;
-        const int e2 = partner_entry<QL>(e, kp, kpp);
-        const float2 zk = sm[smem_pad(e)];
-        const float2 zp = sm[smem_pad(e2)];
-        float2 x;
-        if (e == 0) {
-            x = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
-        } else {
-            const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-            const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
-            const float2 t = cmul(__ldg(&tb.twU[e]), dv);
-            x = make_float2(ev.x + t.y, ev.y - t.x);  // E - i w D
+    constexpr int CH = (M / NT) < 8 ? (M / NT) : 8;
+#pragma unroll 1
+    for (int c = 0; c < M / NT; c += CH) {
+        float2 w[CH], x[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int e = tid + (c + i) * NT;
+            int kp, kpp;
+            const int e2 = partner_entry<QL>(e, kp, kpp);
+            const float2 zk = sm[smem_pad(e)];
+            const float2 zp = sm[smem_pad(e2)];
+            if (e == 0) {
+                x[i] = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
+            } else {
+                const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+                const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
+                const float2 t = cmul(w[i], dv);
+                x[i] = make_float2(ev.x + t.y, ev.y - t.x);  // E - i w D
+            }
         }
-        out_row[e] = x;
+#pragma unroll
+        for (int i = 0; i < CH; i++) out_row[tid + (c + i) * NT] = x[i];
     }
 }
 
-// ---- inverse: packed-permuted spectrum (already in smem) -> 2N real samples -----
-// On entry sm holds the accumulated spectrum Y (entry 0 = DC, Nyquist).  On
-// return half 0 / half 1 hold a'[n] / b'[n]; the caller combines them:
+// ---- inverse: packed-permuted spectrum -> 2N real samples ------------------------
+// inv_load brings the accumulated spectrum Y into shared memory; inv_body turns it
+// in place into a'[n] (half 0) and b'[n] (half 1); the caller combines them:
 //   z[n] = a' + conj(twA[n]) b' -> samples 2n, 2n+1;  z[n+Q] = a' - conj(twA[n]) b' -> samples N+2n, N+2n+1.
+template <int LOG2N>
+__device__ __forceinline__ void inv_load(float2 *sm, const float2 *__restrict__ yrow) {
+    constexpr int M = 1 << LOG2N;
+    constexpr int NT = fft_threads(LOG2N);
+    constexpr int CH = (M / NT) < 16 ? (M / NT) : 16;
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int c = 0; c < M / NT; c += CH) {
+        float2 y[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) y[i] = __ldcs(&yrow[tid + (c + i) * NT]);
+#pragma unroll
+        for (int i = 0; i < CH; i++) sm[smem_pad(tid + (c + i) * NT)] = y[i];
+    }
+}
+
 template <int LOG2N>
 __device__ __forceinline__ void inv_body(float2 *sm, const FftTables &tb) {
     constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
     constexpr int NT = fft_threads(LOG2N);
+    constexpr int CH = (M / NT) < 8 ? (M / NT) : 8;
     const int tid = threadIdx.x;
-    for (int e = tid; e < M; e += NT) {
-        int kp, kpp;
-        const int e2 = partner_entry<QL>(e, kp, kpp);
-        if (kp > kpp) continue;  // the pair is handled by its lower member
-        const float2 yk = sm[smem_pad(e)];
-        if (e == 0) {
-            sm[smem_pad(0)] = make_float2(yk.x + yk.y, yk.x - yk.y);
-            continue;
+#pragma unroll 1
+    for (int c = 0; c < M / NT; c += CH) {
+        float2 w[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int e = tid + (c + i) * NT;
+            int kp, kpp;
+            const int e2 = partner_entry<QL>(e, kp, kpp);
+            if (kp > kpp) continue;  // the pair is handled by its lower member
+            const float2 yk = sm[smem_pad(e)];
+            if (e == 0) {
+                sm[smem_pad(0)] = make_float2(yk.x + yk.y, yk.x - yk.y);
+                continue;
+            }
+            const float2 yp = sm[smem_pad(e2)];
+            const float2 ev = make_float2(yk.x + yp.x, yk.y - yp.y);
+            const float2 dv = make_float2(yk.x - yp.x, yk.y + yp.y);
+            const float2 t = cmulconj(dv, w[i]);
+            sm[smem_pad(e)] = make_float2(ev.x - t.y, ev.y + t.x);
+            if (e2 != e) sm[smem_pad(e2)] = make_float2(ev.x + t.y, -ev.y + t.x);
         }
-        const float2 yp = sm[smem_pad(e2)];
-        const float2 ev = make_float2(yk.x + yp.x, yk.y - yp.y);
-        const float2 dv = make_float2(yk.x - yp.x, yk.y + yp.y);
-        const float2 t = cmulconj(dv, __ldg(&tb.twU[e]));
-        sm[smem_pad(e)] = make_float2(ev.x - t.y, ev.y + t.x);
-        if (e2 != e) sm[smem_pad(e2)] = make_float2(ev.x + t.y, -ev.y + t.x);
     }
     __syncthreads();
     inv_passes<QL, NT>(sm, tb, tid);
