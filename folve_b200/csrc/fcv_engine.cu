@@ -165,16 +165,15 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
             }
         }
     }
-    inv_load<LOG2N>(sm, Y + ((size_t)b * nout + o) * M);
+    inv_load<LOG2N>(sm, tb, Y + ((size_t)b * nout + o) * M);
     if (tid < 32) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             dc += __shfl_xor_sync(0xffffffffu, dc, d);
             ny += __shfl_xor_sync(0xffffffffu, ny, d);
         }
+        if (tid == 0) sm[0] = make_float2(dc + ny, dc - ny);  // Zc[0] from the two real bins
     }
-    __syncthreads();
-    if (tid == 0) sm[0] = make_float2(dc, ny);
     __syncthreads();
 
     inv_body<LOG2N>(sm, tb);
@@ -302,10 +301,21 @@ static int get_tables(int device, int log2n, FftTables *out) {
                     }
             }
         }
+        // conjugate-partner entry of every entry: bin k <-> bin M - k (same half)
+        std::vector<unsigned short> part((size_t)M);
+        for (int e = 0; e < M; e++) {
+            const int half = e >> q, kp = plan_revinv(q, e & (Q - 1));
+            const int kpp = half ? (Q - 1 - kp) : ((Q - kp) & (Q - 1));
+            part[e] = (unsigned short)((half << q) + plan_rev(q, kpp));
+        }
         float2 *d = nullptr;
+        unsigned short *dpart = nullptr;
         CU_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
         CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMalloc(&dpart, part.size() * sizeof(unsigned short)));
+        CU_TRY(cudaMemcpy(dpart, part.data(), part.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
         FftTables tb;
+        tb.part = dpart;
         tb.twA = d + offA;
         tb.twU = d + offU;
         for (int t = 0; t < 3; t++) tb.twP[t] = d + offP[t];

@@ -81,6 +81,7 @@ struct FftTables {
     const float2 *twA;     // [Q]   w_M^n = exp(-2 pi i n / M)
     const float2 *twU;     // [M]   exp(-i pi k / M) for the bin stored at entry e
     const float2 *twP[3];  // per pass t with stride S_t > 1: [(k1-1)*S_t + u] = exp(-2 pi i u k1 / Q_t)
+    const unsigned short *part;  // [M] entry holding the conjugate-partner bin (M - k) of entry e
 };
 
 // ---- complex helpers --------------------------------------------------------
@@ -256,24 +257,25 @@ __device__ __forceinline__ int partner_entry(int e, int &kp_out, int &kpp_out) {
 enum { PCM_F32 = 0, PCM_S16 = 1, PCM_S24 = 2 };
 
 // Frames 2n and 2n+1 of channel `chan` of an interleaved block as (x[2n], x[2n+1]).
-// Stereo and mono blocks use one vector load per pair of frames.
-template <int FMT>
+// NCH = 2 / 1: stereo / mono blocks, one vector load per pair of frames;
+// NCH = 0: any channel count, two scalar loads.
+template <int FMT, int NCH>
 __device__ __forceinline__ float2 pcm_load2(const void *in, int nchan, int chan, int n) {
     if (FMT == PCM_F32) {
-        if (nchan == 2) {
+        if (NCH == 2) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(in) + n);
             return chan ? make_float2(v.y, v.w) : make_float2(v.x, v.z);
         }
-        if (nchan == 1) return __ldg(reinterpret_cast<const float2 *>(in) + n);
+        if (NCH == 1) return __ldg(reinterpret_cast<const float2 *>(in) + n);
         const float *p = reinterpret_cast<const float *>(in) + (size_t)(2 * n) * nchan + chan;
         return make_float2(__ldg(p), __ldg(p + nchan));
     } else if (FMT == PCM_S16) {
         constexpr float K = 1.0f / 32768.0f;
-        if (nchan == 2) {
+        if (NCH == 2) {
             const short4 v = __ldg(reinterpret_cast<const short4 *>(in) + n);
             return chan ? make_float2(v.y * K, v.w * K) : make_float2(v.x * K, v.z * K);
         }
-        if (nchan == 1) {
+        if (NCH == 1) {
             const short2 v = __ldg(reinterpret_cast<const short2 *>(in) + n);
             return make_float2(v.x * K, v.y * K);
         }
@@ -281,9 +283,13 @@ __device__ __forceinline__ float2 pcm_load2(const void *in, int nchan, int chan,
         return make_float2(__ldg(p) * K, __ldg(p + nchan) * K);
     } else {
         constexpr float K = 1.0f / 8388608.0f;
-        if (nchan == 2) {
+        if (NCH == 2) {
             const int4 v = __ldg(reinterpret_cast<const int4 *>(in) + n);
             return chan ? make_float2(v.y * K, v.w * K) : make_float2(v.x * K, v.z * K);
+        }
+        if (NCH == 1) {
+            const int2 v = __ldg(reinterpret_cast<const int2 *>(in) + n);
+            return make_float2(v.x * K, v.y * K);
         }
         const int *p = reinterpret_cast<const int *>(in) + (size_t)(2 * n) * nchan + chan;
         return make_float2(__ldg(p) * K, __ldg(p + nchan) * K);
@@ -306,52 +312,65 @@ __device__ __forceinline__ void pcm_store(void *p, size_t idx, float v) {
 // in: interleaved PCM, `nchan` channels, channel `chan`; frames >= frames_valid read as 0.
 // All global loads of a stage are issued before their first use (the stages are
 // latency bound otherwise: one CTA only has 8 warps).
+template <int LOG2N, int FMT, int NCH>
+__device__ __forceinline__ void fwd_load(float2 *sm, const FftTables &tb, const void *in, int nchan,
+                                         int chan, int frames_valid) {
+    constexpr int QL = LOG2N - 1, Q = 1 << QL;
+    constexpr int NT = fft_threads(LOG2N);
+    constexpr int IT = Q / NT;
+    constexpr int CH = IT < 8 ? IT : 8;
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int c = 0; c < IT; c += CH) {
+        float2 z[CH], w[CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++) z[i] = pcm_load2<FMT, NCH>(in, nchan, chan, tid + (c + i) * NT);
+#pragma unroll
+        for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twA[tid + (c + i) * NT]);
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int n = tid + (c + i) * NT;
+            float2 v = z[i];
+            if (2 * n >= frames_valid) v.x = 0.0f;
+            if (2 * n + 1 >= frames_valid) v.y = 0.0f;
+            sm[smem_pad(n)] = v;
+            sm[smem_pad(Q + n)] = cmul(v, w[i]);
+        }
+    }
+}
+
 template <int LOG2N, int FMT>
 __device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const void *in, int nchan,
                                          int chan, int frames_valid, float2 *__restrict__ out_row) {
     constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
     constexpr int NT = fft_threads(LOG2N);
-    constexpr int IT = Q / NT;
     const int tid = threadIdx.x;
-    {
-        float2 z[IT], w[IT];
-#pragma unroll
-        for (int it = 0; it < IT; it++) z[it] = pcm_load2<FMT>(in, nchan, chan, tid + it * NT);
-#pragma unroll
-        for (int it = 0; it < IT; it++) w[it] = __ldg(&tb.twA[tid + it * NT]);
-#pragma unroll
-        for (int it = 0; it < IT; it++) {
-            const int n = tid + it * NT;
-            float2 v = z[it];
-            if (2 * n >= frames_valid) v.x = 0.0f;
-            if (2 * n + 1 >= frames_valid) v.y = 0.0f;
-            sm[smem_pad(n)] = v;
-            sm[smem_pad(Q + n)] = cmul(v, w[it]);
-        }
-    }
+    if (nchan == 2) fwd_load<LOG2N, FMT, 2>(sm, tb, in, nchan, chan, frames_valid);
+    else if (nchan == 1) fwd_load<LOG2N, FMT, 1>(sm, tb, in, nchan, chan, frames_valid);
+    else fwd_load<LOG2N, FMT, 0>(sm, tb, in, nchan, chan, frames_valid);
     __syncthreads();
     fwd_passes<QL, NT>(sm, tb, tid);
+    // unpack: X[k] = E - i w D from the bin and its conjugate partner
     constexpr int CH = (M / NT) < 8 ? (M / NT) : 8;
 #pragma unroll 1
     for (int c = 0; c < M / NT; c += CH) {
         float2 w[CH], x[CH];
+        int e2[CH];
 #pragma unroll
-        for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+        for (int i = 0; i < CH; i++) {
+            w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+            e2[i] = __ldg(&tb.part[tid + (c + i) * NT]);
+        }
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             const int e = tid + (c + i) * NT;
-            int kp, kpp;
-            const int e2 = partner_entry<QL>(e, kp, kpp);
             const float2 zk = sm[smem_pad(e)];
-            const float2 zp = sm[smem_pad(e2)];
-            if (e == 0) {
-                x[i] = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
-            } else {
-                const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-                const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
-                const float2 t = cmul(w[i], dv);
-                x[i] = make_float2(ev.x + t.y, ev.y - t.x);  // E - i w D
-            }
+            const float2 zp = sm[smem_pad(e2[i])];
+            const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+            const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
+            const float2 t = cmul(w[i], dv);
+            x[i] = make_float2(ev.x + t.y, ev.y - t.x);              // E - i w D
+            if (e == 0) x[i] = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
         }
 #pragma unroll
         for (int i = 0; i < CH; i++) out_row[tid + (c + i) * NT] = x[i];
@@ -359,57 +378,48 @@ __device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const 
 }
 
 // ---- inverse: packed-permuted spectrum -> 2N real samples ------------------------
-// inv_load brings the accumulated spectrum Y into shared memory; inv_body turns it
-// in place into a'[n] (half 0) and b'[n] (half 1); the caller combines them:
+// inv_load reads the accumulated spectrum Y and its conjugate partners straight
+// from global memory (the partner reads hit L2: the same CTA has just fetched
+// the row) and stores Zc[k] = (Y[k] + conj Y[M-k]) + i conj(w) (Y[k] - conj Y[M-k])
+// to shared memory; entry 0 (DC, Nyquist) is supplied by the caller.
+// inv_body then turns it in place into a'[n] (half 0) and b'[n] (half 1); the
+// caller combines them:
 //   z[n] = a' + conj(twA[n]) b' -> samples 2n, 2n+1;  z[n+Q] = a' - conj(twA[n]) b' -> samples N+2n, N+2n+1.
 template <int LOG2N>
-__device__ __forceinline__ void inv_load(float2 *sm, const float2 *__restrict__ yrow) {
+__device__ __forceinline__ void inv_load(float2 *sm, const FftTables &tb, const float2 *__restrict__ yrow) {
     constexpr int M = 1 << LOG2N;
-    constexpr int NT = fft_threads(LOG2N);
-    constexpr int CH = (M / NT) < 16 ? (M / NT) : 16;
-    const int tid = threadIdx.x;
-#pragma unroll 1
-    for (int c = 0; c < M / NT; c += CH) {
-        float2 y[CH];
-#pragma unroll
-        for (int i = 0; i < CH; i++) y[i] = __ldcs(&yrow[tid + (c + i) * NT]);
-#pragma unroll
-        for (int i = 0; i < CH; i++) sm[smem_pad(tid + (c + i) * NT)] = y[i];
-    }
-}
-
-template <int LOG2N>
-__device__ __forceinline__ void inv_body(float2 *sm, const FftTables &tb) {
-    constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
     constexpr int NT = fft_threads(LOG2N);
     constexpr int CH = (M / NT) < 8 ? (M / NT) : 8;
     const int tid = threadIdx.x;
 #pragma unroll 1
     for (int c = 0; c < M / NT; c += CH) {
-        float2 w[CH];
+        float2 y[CH], yp[CH], w[CH];
+        int e2[CH];
 #pragma unroll
-        for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+        for (int i = 0; i < CH; i++) e2[i] = __ldg(&tb.part[tid + (c + i) * NT]);
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            y[i] = __ldg(&yrow[tid + (c + i) * NT]);
+            w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) yp[i] = __ldg(&yrow[e2[i]]);
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             const int e = tid + (c + i) * NT;
-            int kp, kpp;
-            const int e2 = partner_entry<QL>(e, kp, kpp);
-            if (kp > kpp) continue;  // the pair is handled by its lower member
-            const float2 yk = sm[smem_pad(e)];
-            if (e == 0) {
-                sm[smem_pad(0)] = make_float2(yk.x + yk.y, yk.x - yk.y);
-                continue;
-            }
-            const float2 yp = sm[smem_pad(e2)];
-            const float2 ev = make_float2(yk.x + yp.x, yk.y - yp.y);
-            const float2 dv = make_float2(yk.x - yp.x, yk.y + yp.y);
+            const float2 ev = make_float2(y[i].x + yp[i].x, y[i].y - yp[i].y);
+            const float2 dv = make_float2(y[i].x - yp[i].x, y[i].y + yp[i].y);
             const float2 t = cmulconj(dv, w[i]);
-            sm[smem_pad(e)] = make_float2(ev.x - t.y, ev.y + t.x);
-            if (e2 != e) sm[smem_pad(e2)] = make_float2(ev.x + t.y, -ev.y + t.x);
+            if (e != 0) sm[smem_pad(e)] = make_float2(ev.x - t.y, ev.y + t.x);  // E + i conj(w) D
         }
     }
-    __syncthreads();
-    inv_passes<QL, NT>(sm, tb, tid);
+}
+
+template <int LOG2N>
+__device__ __forceinline__ void inv_body(float2 *sm, const FftTables &tb) {
+    constexpr int QL = LOG2N - 1;
+    constexpr int NT = fft_threads(LOG2N);
+    inv_passes<QL, NT>(sm, tb, threadIdx.x);
 }
 
 }  // namespace fcv
