@@ -17,3 +17,22 @@ clean:
 	rm -f $(LIB) $(CSRC)/ptxas.log
 
 .PHONY: all clean
+
+# ---- C++ host layer: SoundProcessor / filter-config / ProcessorPool + test harness
+HOST = folve_b200/host
+HOSTLIB = folve_b200/libfolve_host.so
+HOST_SRCS = $(HOST)/sound-processor.cc $(HOST)/filter-config.cc $(HOST)/processor-pool.cc \
+            $(HOST)/harness.cc $(HOST)/sndfile_shim/sndfile_shim.cc
+HOST_HDRS = $(HOST)/sound-processor.h $(HOST)/filter-config.h $(HOST)/processor-pool.h \
+            $(HOST)/sndfile_shim/sndfile.h include/folve_b200.h
+# same optimisation flags as oracle/Makefile so that float expressions in the
+# config loader (hilbert taps, gains) round identically on both sides
+HOST_FLAGS = -O3 -march=x86-64-v3 -fno-math-errno -fno-trapping-math -std=c++17 -fPIC -Wall -Wextra \
+             -I$(HOST)/sndfile_shim -I$(HOST) -Iinclude
+
+host: $(HOSTLIB)
+
+$(HOSTLIB): $(HOST_SRCS) $(HOST_HDRS) $(LIB)
+	$(CXX) $(HOST_FLAGS) -shared -Wl,-Bsymbolic -o $@ $(HOST_SRCS) -L folve_b200 -lfolve_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+
+all: host

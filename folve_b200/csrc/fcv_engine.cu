@@ -590,6 +590,21 @@ extern "C" int fcv_filter_get_spectrum(fcv_filter *f, int inp, int out, int j, f
     return 1;
 }
 
+extern "C" int fcv_filter_get_impulse(fcv_filter *f, int inp, int out, float *dst, int capacity) {
+    if (!f || !dst || capacity < 0) return fail(FCV_E_PARAM, "null argument");
+    if (f->committed) return fail(FCV_E_STATE, "impulses are dropped at commit");
+    if (inp < 0 || inp >= f->ninp || out < 0 || out >= f->nout) return fail(FCV_E_PARAM, "bad index");
+    const Pair &p = f->pairs[(size_t)inp * f->nout + out];
+    if (!p.exists) return 0;
+    const Pair *src = &p;
+    if (p.link >= 0) src = &f->pairs[(size_t)p.link];
+    const size_t total = (size_t)f->npar * f->fragm;
+    const size_t n = total < (size_t)capacity ? total : (size_t)capacity;
+    memset(dst, 0, (size_t)capacity * sizeof(float));
+    if (src->link < 0 && !src->h.empty()) memcpy(dst, src->h.data(), n * sizeof(float));
+    return p.link >= 0 ? 2 : 1;
+}
+
 // ---------------------------------------------------------------------------
 // batch
 // ---------------------------------------------------------------------------

@@ -1,0 +1,349 @@
+// harness.cc -- C entry points that drive SoundProcessor / ProcessorPool the way
+// folve's ConvolveFileHandler does, over in-memory PCM instead of FLAC files.
+//
+// The same source is compiled twice:
+//   * against this directory's sound-processor.h / processor-pool.h (the B200
+//     product)                                   -> folve_b200/libfolve_host.so
+//   * with -DFOLVE_HARNESS_REFERENCE=1 against the reference's own headers and
+//     unmodified sources in /root/reference      -> oracle/_ref/libfolve_ref.so
+// so the parity tests and the benchmark run literally the same caller code on
+// both.  The caller protocol restated here is
+// ConvolveFileHandler::AddMoreSoundData (convolve-file-handler.cc:370-424) and
+// ConvolveFileHandler::PassoverProcessor (convolve-file-handler.cc:328-351).
+#include <sndfile.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+// Angle brackets on purpose: these must come from the -I path of the build
+// (the reference's directory or this one), not from the directory of this file.
+#include <processor-pool.h>
+#include <sound-processor.h>
+
+#if FOLVE_HARNESS_REFERENCE
+#include <zita-config.h>
+#else
+#include <filter-config.h>
+#include <folve_b200.h>
+#endif
+
+#if FOLVE_HARNESS_REFERENCE
+extern "C" {
+zo_shim_impdata_hook zo_shim_on_impdata = 0;
+zo_shim_link_hook zo_shim_on_link = 0;
+void *zo_shim_hook_user = 0;
+int zo_shim_reset_is_fresh = 0;
+}
+#endif
+
+namespace {
+
+struct FileJob {
+    SNDFILE *in = nullptr;
+    SNDFILE *out = nullptr;
+    long frames_total = 0;
+    long frames_left = 0;
+    SoundProcessor *processor = nullptr;
+    bool opened = false, closed = false;
+    bool in_gapless = false, out_gapless = false;
+    float max_value = 0.0f;
+    bool HasStarted() const { return frames_total != frames_left; }
+};
+
+struct Chain {
+    ProcessorPool *pool;
+    std::string filter_dir;
+    int samplerate, channels, bits;
+    bool gapless;
+    std::vector<FileJob> files;
+    std::string error;
+
+    bool Open(FileJob &f) {
+        if (f.opened) return f.processor != nullptr;
+        f.opened = true;
+        std::string err;
+        f.processor = pool->GetOrCreate(filter_dir, samplerate, channels, bits, &err);
+        if (!f.processor) error = err;
+        return f.processor != nullptr;
+    }
+
+    void Close(FileJob &f) {
+        if (f.closed) return;
+        f.closed = true;
+        if (f.processor) {
+            f.max_value = f.processor->max_output_value();
+            pool->Return(f.processor);
+            f.processor = nullptr;
+        }
+    }
+
+    // convolve-file-handler.cc:328-351
+    bool Passover(FileJob &b, SoundProcessor *passover) {
+        if (b.HasStarted()) return false;
+        if (!b.processor) return false;
+        if (passover->config_file() != b.processor->config_file() ||
+            passover->config_file_timestamp() != b.processor->config_file_timestamp())
+            return false;
+        pool->Return(b.processor);
+        b.processor = passover;
+        if (!b.processor->is_input_buffer_complete()) {
+            // fill with our beginning so that the donor can finish its block
+            b.frames_left -= b.processor->FillBuffer(b.in);
+        }
+        b.in_gapless = true;
+        return true;
+    }
+
+    // convolve-file-handler.cc:370-424
+    bool AddMoreSoundData(size_t k) {
+        FileJob &a = files[k];
+        if (!a.frames_left) return false;
+        if (a.processor->pending_writes() > 0) {
+            a.processor->WriteProcessed(a.out, a.processor->pending_writes());
+            return a.frames_left;
+        }
+        const int r = a.processor->FillBuffer(a.in);
+        if (r == 0) {  // premature EOF
+            a.frames_left = 0;
+            Close(a);
+            return false;
+        }
+        a.frames_left -= r;
+        if (!a.frames_left && !a.processor->is_input_buffer_complete() && gapless) {
+            FileJob *next = (k + 1 < files.size()) ? &files[k + 1] : nullptr;
+            const bool passed = next && Open(*next) && Passover(*next, a.processor);
+            a.processor->WriteProcessed(a.out, r);
+            if (passed) {
+                a.out_gapless = true;
+                a.max_value = a.processor->max_output_value();
+                a.processor = nullptr;  // ownership handed over
+                Close(a);
+            }
+        } else {
+            a.processor->WriteProcessed(a.out, r);
+        }
+        if (a.frames_left == 0) Close(a);
+        return a.frames_left;
+    }
+};
+
+size_t SampleBytes(int subformat) {
+    return subformat == SF_FORMAT_PCM_16 ? 2 : 4;
+}
+
+ProcessorPool *g_pool = nullptr;
+
+}  // namespace
+
+extern "C" {
+
+const char *fh_version(void) {
+#if FOLVE_HARNESS_REFERENCE
+    return "reference";
+#else
+    return "b200";
+#endif
+}
+
+// Reset()-equals-fresh switch of the restated Convproc (reference build only;
+// see oracle/zita_oracle.h).  No effect on the product, whose Reset is always fresh.
+void fh_set_reset_is_fresh(int on) {
+#if FOLVE_HARNESS_REFERENCE
+    zo_shim_reset_is_fresh = on;
+#else
+    (void)on;
+#endif
+}
+
+// Drop the process-wide processor pool (idle processors are deleted).
+void fh_drop_pool(void) {
+#if !FOLVE_HARNESS_REFERENCE
+    delete g_pool;  // the reference's ProcessorPool has no destructor; it just leaks
+#endif
+    g_pool = nullptr;
+}
+
+// Runs `nfiles` in-memory files (alphabetical order == array order) through the
+// caller protocol.  pcm[i]: interleaved `channels`-channel samples in
+// `in_subformat` (SF_FORMAT_PCM_16: int16, PCM_24/PCM_32: int32, FLOAT: float).
+// out_pcm[i] receives frames[i] * nout samples in `out_subformat`.
+// Returns the number of output channels, or <0 with a message in errbuf.
+int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits, int gapless, int nfiles,
+                 const void *const *pcm, const long *frames, int in_subformat, int out_subformat,
+                 void *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags, char *errbuf,
+                 int errcap) {
+    if (!g_pool) g_pool = new ProcessorPool(3);  // folve-filesystem.cc:50
+    Chain chain;
+    chain.pool = g_pool;
+    chain.filter_dir = filter_dir;
+    chain.samplerate = samplerate;
+    chain.channels = channels;
+    chain.bits = bits;
+    chain.gapless = gapless != 0;
+    chain.files.resize((size_t)nfiles);
+    int nout = -1;
+    int rc = 0;
+    for (int i = 0; i < nfiles; i++) {
+        FileJob &f = chain.files[(size_t)i];
+        f.in = sf_shim_open_memory_read(pcm[i], frames[i], channels, samplerate, in_subformat);
+        f.frames_total = f.frames_left = frames[i];
+    }
+    for (int i = 0; i < nfiles && rc == 0; i++) {
+        FileJob &f = chain.files[(size_t)i];
+        if (!chain.Open(f)) {
+            if (errbuf && errcap > 0) snprintf(errbuf, (size_t)errcap, "%s", chain.error.c_str());
+            rc = -1;
+            break;
+        }
+        if (f.processor) {
+            if (nout < 0) nout = f.processor->output_channels();
+        }
+        // the output file is created lazily, once the channel count is known
+        for (int j = i; j < nfiles && j <= i + 1; j++) {
+            FileJob &g = chain.files[(size_t)j];
+            if (!g.out) g.out = sf_shim_open_memory_write(nout, samplerate, out_subformat);
+        }
+        while (chain.AddMoreSoundData((size_t)i)) {}
+        chain.Close(f);
+    }
+    for (int i = 0; i < nfiles; i++) {
+        FileJob &f = chain.files[(size_t)i];
+        chain.Close(f);
+        const long n = f.out ? (long)sf_shim_memory_frames(f.out) : 0;
+        if (out_frames) out_frames[i] = n;
+        if (f.out && out_pcm && out_pcm[i] && n > 0)
+            memcpy(out_pcm[i], sf_shim_memory_data(f.out), (size_t)n * (size_t)nout * SampleBytes(out_subformat));
+        if (max_values) max_values[i] = f.max_value;
+        if (gapless_flags) gapless_flags[i] = (f.in_gapless ? 1 : 0) | (f.out_gapless ? 2 : 0);
+        if (f.in) sf_close(f.in);
+        if (f.out) sf_close(f.out);
+    }
+    return rc ? rc : nout;
+}
+
+// ---- what a configuration file loads ------------------------------------------
+// Parses `config_file` with the library's own loader and reports, per (in,out)
+// pair, the accumulated time-domain impulse as it is handed to the convolver
+// (scaled by 0.5/fragm, the scaling zita applies in impdata_create).
+struct fh_config {
+    int rc = 0;
+    int created = 0;  // would SoundProcessor::Create succeed
+    int ninp = 0, nout = 0, size = 0, fragm = 0, npar = 0;
+#if FOLVE_HARNESS_REFERENCE
+    struct PairData { bool exists = false; int link = -1; std::vector<float> h; };
+    std::vector<PairData> pairs;
+#else
+    folve_b200::FilterConfig cfg;
+#endif
+};
+
+#if FOLVE_HARNESS_REFERENCE
+static void RefOnImpdata(void *user, unsigned inp, unsigned out, int step, const float *data, int ind0, int ind1) {
+    // mirror of fcv_filter_add's accumulation (fcv_engine.cu) on the calls the reference's parser makes
+    fh_config *c = (fh_config *)user;
+    if ((int)inp >= c->ninp || (int)out >= c->nout) return;
+    const long n = (long)ind1 - ind0, total = (long)c->npar * c->fragm, i0 = -(long)ind0;
+    if (i0 >= n || i0 + total <= 0) return;
+    fh_config::PairData &p = c->pairs[(size_t)inp * c->nout + out];
+    p.exists = true;
+    if (p.link >= 0 || !data) return;
+    if (p.h.empty()) p.h.assign((size_t)total, 0.0f);
+    const float norm = 0.5f / (float)c->fragm;
+    const long j0 = i0 < 0 ? 0 : i0, j1 = (i0 + total > n) ? n : i0 + total;
+    for (long j = j0; j < j1; j++) p.h[(size_t)(j - i0)] += norm * data[j * step];
+}
+static void RefOnLink(void *user, unsigned inp1, unsigned out1, unsigned inp2, unsigned out2) {
+    fh_config *c = (fh_config *)user;
+    if ((int)inp1 >= c->ninp || (int)out1 >= c->nout || (int)inp2 >= c->ninp || (int)out2 >= c->nout) return;
+    if (inp1 == inp2 && out1 == out2) return;
+    const int src = (int)(inp1 * c->nout + out1), dst = (int)(inp2 * c->nout + out2);
+    if (!c->pairs[(size_t)src].exists) return;
+    c->pairs[(size_t)dst].exists = true;
+    c->pairs[(size_t)dst].h.clear();
+    c->pairs[(size_t)dst].link = src;
+}
+#endif
+
+fh_config *fh_config_open(const char *config_file, int samplerate, int channels) {
+    fh_config *c = new fh_config();
+#if FOLVE_HARNESS_REFERENCE
+    // what SoundProcessor::Create does (sound-processor.cc:36-48), with observers
+    // on the impdata calls; the pair table is sized once /convolver/new is seen,
+    // i.e. lazily inside the first callback.
+    ZitaConfig zita;
+    memset(&zita, 0, sizeof(zita));
+    zita.fsamp = samplerate;
+    zita.ninp = channels;
+    zita.nout = channels;
+    zita.convproc = new Convproc();
+    struct Ctx { fh_config *c; ZitaConfig *z; } ctx = {c, &zita};
+    zo_shim_hook_user = &ctx;
+    zo_shim_on_impdata = [](void *u, unsigned inp, unsigned out, int step, const float *data, int i0, int i1) {
+        Ctx *x = (Ctx *)u;
+        if (x->c->pairs.empty()) {
+            x->c->ninp = x->z->ninp; x->c->nout = x->z->nout; x->c->fragm = x->z->fragm;
+            x->c->npar = (x->z->size + x->z->fragm - 1) / x->z->fragm;
+            x->c->pairs.resize((size_t)x->c->ninp * x->c->nout);
+        }
+        RefOnImpdata(x->c, inp, out, step, data, i0, i1);
+    };
+    zo_shim_on_link = [](void *u, unsigned a, unsigned b, unsigned d, unsigned e) {
+        Ctx *x = (Ctx *)u;
+        if (x->c->pairs.empty()) return;
+        RefOnLink(x->c, a, b, d, e);
+    };
+    c->rc = config(&zita, config_file);
+    zo_shim_on_impdata = 0;
+    zo_shim_on_link = 0;
+    zo_shim_hook_user = 0;
+    c->created = c->rc == 0 && zita.convproc->state() != Convproc::ST_IDLE &&
+                 zita.convproc->inpdata(zita.ninp - 1) != NULL && zita.convproc->outdata(zita.nout - 1) != NULL;
+    c->ninp = zita.ninp; c->nout = zita.nout; c->size = zita.size; c->fragm = zita.fragm;
+    c->npar = zita.fragm ? (zita.size + zita.fragm - 1) / zita.fragm : 0;
+    if (c->pairs.empty() && c->created) c->pairs.resize((size_t)c->ninp * c->nout);
+    delete zita.convproc;
+#else
+    c->cfg.fsamp = samplerate;
+    c->cfg.ninp = channels;
+    c->cfg.nout = channels;
+    c->rc = folve_b200::LoadFilterConfig(&c->cfg, config_file);
+    c->created = c->rc == 0 && c->cfg.filter != nullptr;
+    c->ninp = c->cfg.ninp; c->nout = c->cfg.nout; c->size = c->cfg.size; c->fragm = c->cfg.fragm;
+    c->npar = c->cfg.filter ? fcv_filter_partitions(c->cfg.filter) : 0;
+#endif
+    return c;
+}
+
+// out[0..6] = rc, created, ninp, nout, size, fragm, partitions
+void fh_config_info(const fh_config *c, int *out) {
+    out[0] = c->rc; out[1] = c->created; out[2] = c->ninp; out[3] = c->nout;
+    out[4] = c->size; out[5] = c->fragm; out[6] = c->npar;
+}
+
+// 0: pair absent, 1: owns data, 2: link (dst gets the source's data); capacity in floats
+int fh_config_impulse(fh_config *c, int inp, int out, float *dst, int capacity) {
+    if (!c->created || inp < 0 || inp >= c->ninp || out < 0 || out >= c->nout) return -1;
+#if FOLVE_HARNESS_REFERENCE
+    const fh_config::PairData &p = c->pairs[(size_t)inp * c->nout + out];
+    if (!p.exists) return 0;
+    const fh_config::PairData *src = p.link >= 0 ? &c->pairs[(size_t)p.link] : &p;
+    memset(dst, 0, sizeof(float) * (size_t)capacity);
+    if (src->link < 0 && !src->h.empty())
+        memcpy(dst, src->h.data(), sizeof(float) * (src->h.size() < (size_t)capacity ? src->h.size() : (size_t)capacity));
+    return p.link >= 0 ? 2 : 1;
+#else
+    return fcv_filter_get_impulse(c->cfg.filter, inp, out, dst, capacity);
+#endif
+}
+
+void fh_config_close(fh_config *c) {
+#if !FOLVE_HARNESS_REFERENCE
+    if (c && c->cfg.filter) fcv_filter_unref(c->cfg.filter);
+#endif
+    delete c;
+}
+
+}  // extern "C"

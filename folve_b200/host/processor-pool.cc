@@ -1,0 +1,81 @@
+// processor-pool.cc -- see processor-pool.h; behaviour follows
+// /root/reference/processor-pool.cc:48-131.
+#include "processor-pool.h"
+
+#include <stdio.h>
+#include <string.h>
+#include <syslog.h>
+#include <unistd.h>
+
+#include "sound-processor.h"
+
+ProcessorPool::ProcessorPool(int max_available)
+    : max_per_config_(max_available) {}
+
+ProcessorPool::~ProcessorPool() {
+    for (auto &kv : pool_)
+        for (SoundProcessor *p : kv.second) delete p;
+}
+
+SoundProcessor *ProcessorPool::GetOrCreate(const std::string &base_dir,
+                                           int sampling_rate, int channels,
+                                           int bits, std::string *errmsg) {
+    // From specific to non-specific (processor-pool.cc:53-61).
+    char name[3][96];
+    snprintf(name[0], sizeof(name[0]), "/filter-%d-%d-%d.conf", sampling_rate, channels, bits);
+    snprintf(name[1], sizeof(name[1]), "/filter-%d-%d.conf", sampling_rate, channels);
+    snprintf(name[2], sizeof(name[2]), "/filter-%d.conf", sampling_rate);
+    std::string config_path;
+    for (int i = 0; i < 3 && config_path.empty(); ++i) {
+        const std::string candidate = base_dir + name[i];
+        if (access(candidate.c_str(), R_OK) == 0) config_path = candidate;
+    }
+    if (config_path.empty()) {
+        const size_t slash = base_dir.find_last_of('/');
+        const std::string short_dir = slash == std::string::npos ? base_dir : base_dir.substr(slash + 1);
+        char msg[256];
+        snprintf(msg, sizeof(msg), "No filter in %s for %.1fkHz/%d ch/%d bits",
+                 short_dir.c_str(), sampling_rate / 1000.0, channels, bits);
+        if (errmsg) *errmsg = msg;
+        return NULL;
+    }
+
+    SoundProcessor *result;
+    while ((result = CheckOutOfPool(config_path)) != NULL) {
+        if (result->ConfigStillUpToDate()) return result;
+        delete result;  // configuration file was touched since
+    }
+    result = SoundProcessor::Create(config_path, sampling_rate, channels);
+    if (result == NULL) {
+        if (errmsg) *errmsg = "Problem parsing " + config_path;
+        syslog(LOG_ERR, "filter-config %s is broken.", config_path.c_str());
+    }
+    return result;
+}
+
+void ProcessorPool::Return(SoundProcessor *processor) {
+    if (processor == NULL) return;
+    if (!processor->ConfigStillUpToDate()) {
+        delete processor;
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> l(pool_mutex_);
+        ProcessorList &list = pool_[processor->config_file()];
+        if (list.size() < max_per_config_) {
+            processor->Reset();
+            list.push_back(processor);
+            return;
+        }
+    }
+    delete processor;  // enough idle processors for this configuration
+}
+
+SoundProcessor *ProcessorPool::CheckOutOfPool(const std::string &config_path) {
+    std::lock_guard<std::mutex> l(pool_mutex_);
+    PoolMap::iterator found = pool_.find(config_path);
+    if (found == pool_.end() || found->second.empty()) return NULL;
+    SoundProcessor *result = found->second.front();
+    found->second.pop_front();
+    return result;
+}

@@ -1,0 +1,47 @@
+// -*- c++ -*-
+// processor-pool.h -- pool of SoundProcessors per configuration file; same
+// interface as /root/reference/processor-pool.h:30-55.
+//
+// Processors are worth pooling for a different reason than in the reference:
+// creating one no longer re-parses the filter or recomputes its spectra (those
+// are cached in HBM per (config path, mtime), see sound-processor.cc), but a
+// pooled processor keeps its device state and pinned block allocated.
+#ifndef FOLVE_B200_PROCESSOR_POOL_H
+#define FOLVE_B200_PROCESSOR_POOL_H
+
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+
+class SoundProcessor;
+
+class ProcessorPool {
+public:
+  // Stores at most "max_per_config" idle processors per configuration file.
+  explicit ProcessorPool(int max_per_config);
+  ~ProcessorPool();
+
+  // Resolve base_dir/filter-<rate>-<channels>-<bits>.conf, then
+  // filter-<rate>-<channels>.conf, then filter-<rate>.conf and hand out a
+  // processor for the first one that is readable.  NULL + *errmsg on failure.
+  SoundProcessor *GetOrCreate(const std::string &base_dir,
+                              int sampling_rate, int channels, int bits,
+                              std::string *errmsg);
+
+  // Give a processor back; it is reset and kept, or deleted if its
+  // configuration changed or the pool is full.
+  void Return(SoundProcessor *processor);
+
+private:
+  typedef std::deque<SoundProcessor*> ProcessorList;
+  typedef std::map<std::string, ProcessorList> PoolMap;
+
+  SoundProcessor *CheckOutOfPool(const std::string &config_path);
+
+  const size_t max_per_config_;
+  std::mutex pool_mutex_;
+  PoolMap pool_;
+};
+
+#endif  // FOLVE_B200_PROCESSOR_POOL_H

@@ -1,0 +1,86 @@
+// -*- c++ -*-
+// sound-processor.h -- drop-in replacement for folve's SoundProcessor
+// (/root/reference/sound-processor.h:28-85) on top of the B200 engine.
+//
+// The public interface is the reference's, member for member, so that
+// ConvolveFileHandler (convolve-file-handler.cc:78-80,335-348,373-377,408,418)
+// and ProcessorPool (processor-pool.cc:72,83,95,109) compile and behave
+// unchanged.  What differs is behind it: instead of a Convproc the object
+// owns one fcv_stream (device-resident input-spectra ring + overlap tails) and
+// a reference on a shared, HBM-resident fcv_filter; `buffer_` is the stream's
+// pinned host block.
+#ifndef FOLVE_B200_SOUND_PROCESSOR_H
+#define FOLVE_B200_SOUND_PROCESSOR_H
+
+#include <sndfile.h>
+#include <time.h>
+
+#include <string>
+
+struct fcv_filter;
+struct fcv_stream;
+
+class SoundProcessor {
+public:
+  // NULL if the configuration cannot be parsed, defines no convolver, or no
+  // usable GPU is present (there is no CPU fallback).
+  static SoundProcessor *Create(const std::string &config_file,
+                                int samplerate, int channels);
+  ~SoundProcessor();
+
+  // Fill Buffer from given sound file. Returns number of samples read.
+  int FillBuffer(SNDFILE *in);
+
+  inline int input_channels() const { return ninp_; }
+  inline int output_channels() const { return nout_; }
+
+  // True once a whole block of `fragm` frames is buffered.
+  bool is_input_buffer_complete() const { return fragm_ == input_pos_; }
+
+  // Processed frames not yet written (non-zero after a gapless hand-over).
+  int pending_writes() const {
+    return output_pos_ >= 0 ? fragm_ - output_pos_ : 0;
+  }
+
+  // Write `sample_count` processed frames, processing the block first if needed.
+  void WriteProcessed(SNDFILE *out, int sample_count);
+
+  // Reset processor for re-use: state identical to a freshly created one.
+  void Reset();
+
+  // Largest (signed) output sample observed (>= 0.0).
+  float max_output_value() const { return max_out_value_observed_; }
+  void ResetMaxValues();
+
+  const std::string &config_file() const { return config_file_; }
+  time_t config_file_timestamp() const { return config_file_timestamp_; }
+  bool ConfigStillUpToDate() const;
+
+  // --- additions (not in the reference) ---
+  // CUDA device new processors are created on (default: $FOLVE_B200_DEVICE or 0).
+  static void SetDevice(int device);
+  static int Device();
+  // Block size and the engine handles, for the batched submit layer.
+  int fragment_size() const { return fragm_; }
+  fcv_stream *stream() const { return stream_; }
+  // Drops every cached filter (spectra in HBM) that no processor uses any more.
+  static void PurgeFilterCache();
+
+private:
+  SoundProcessor(fcv_filter *filter, fcv_stream *stream, int fragm, int ninp,
+                 int nout, const std::string &cfg_file, time_t cfg_mtime);
+  void Process();
+
+  fcv_filter *const filter_;
+  fcv_stream *const stream_;
+  const int fragm_, ninp_, nout_;
+  const std::string config_file_;
+  const time_t config_file_timestamp_;
+
+  float *const buffer_;  // pinned, owned by stream_; fragm * max(ninp, nout) floats
+  int input_pos_;
+  int output_pos_;  // written position. -1, if not processed yet.
+  float max_out_value_observed_;
+};
+
+#endif  // FOLVE_B200_SOUND_PROCESSOR_H

@@ -199,6 +199,12 @@ unsigned long long fcv_kernel_launches(void);
  * 1 if present, 0 if the partition is absent (all zero), <0 on error.
  * fcv_stream_get_input_spectrum: ring slot `age` blocks back (0 = newest). */
 int fcv_filter_get_spectrum(fcv_filter *f, int inp, int out, int j, float *dst);
+/* Before commit (no GPU needed): the accumulated time-domain impulse of pair
+ * (inp,out) as it will be transformed, i.e. already scaled by 0.5/fragm;
+ * `capacity` floats at most (partitions*fragm are available).  Returns 0 if
+ * the pair has no MAC node, 1 if it owns data (possibly all zero), 2 if it is
+ * a link (dst receives the source pair's data), <0 on error. */
+int fcv_filter_get_impulse(fcv_filter *f, int inp, int out, float *dst, int capacity);
 int fcv_stream_get_input_spectrum(fcv_stream *s, int inp, int age, float *dst);
 
 #ifdef __cplusplus

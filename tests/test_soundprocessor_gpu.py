@@ -1,0 +1,195 @@
+"""GPU: this repo's SoundProcessor / ProcessorPool (C++ host layer over the CUDA
+engine) against the reference's own SoundProcessor run through the SAME caller
+code (folve_b200/host/harness.cc compiled twice), and against the committed
+golden outputs of the reference build (tests/golden/chains.npz).
+
+Tolerances (BASELINE.json north_star): float32 within 1e-5 of full scale; <= 1 LSB
+after 16-bit quantisation; 24-bit reported against the float64 truth."""
+import os
+
+import numpy as np
+import pytest
+
+import harness_py as H
+from configs import make_filter_dirs
+from oracle_py import truth_f64
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chains.npz")
+
+
+@pytest.fixture(scope="module")
+def dirs(tmp_path_factory):
+    return make_filter_dirs(tmp_path_factory.mktemp("filters"))
+
+
+@pytest.fixture(autouse=True)
+def _fresh_pools():
+    P = H.product()
+    P.drop_pool()
+    if H.have_reference():
+        R = H.reference()
+        R.drop_pool()
+        R.set_reset_is_fresh(True)
+    yield
+    P.drop_pool()
+
+
+def _noise(frames, ch, peak, seed):
+    r = np.random.default_rng(seed)
+    return (np.rint(r.uniform(-peak, peak, (frames, ch)) * 32768) / 32768).astype(np.float32)
+
+
+def _fragm(d, rate, ch):
+    conf = [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".conf")][0]
+    return H.product().load_config(conf, rate, ch)
+
+
+def test_product_library_is_the_cuda_one():
+    assert H.product().kind == "b200"
+
+
+def test_golden_chains_from_the_reference_build(dirs):
+    from golden.make_golden import CASES, case_inputs
+    g = np.load(GOLDEN)
+    P = H.product()
+    for name, fdir, lens, gapless, seed in CASES:
+        d, rate, ch, bits = dirs[fdir]
+        fragm = _fragm(d, rate, ch)["fragm"]
+        files = case_inputs(fragm, ch, lens, seed)
+        P.drop_pool()
+        outs, mx, flags = P.run_chain(d, rate, ch, bits, files, gapless=gapless)
+        assert list(g[f"{name}/flags"]) == flags, name
+        assert np.allclose(g[f"{name}/max"], mx, atol=2e-6), name
+        for k, y in enumerate(outs):
+            assert y.shape[0] == int(g[f"{name}/{k}/frames"][0]), (name, k)
+            if y.shape[0] == 0:
+                continue
+            assert np.abs(y[:1024] - g[f"{name}/{k}/head"]).max() < 1e-5, (name, k)
+            assert np.abs(y[-1024:] - g[f"{name}/{k}/tail"]).max() < 1e-5, (name, k)
+            assert np.allclose(y.astype(np.float64).sum(axis=0), g[f"{name}/{k}/sum"], atol=1e-5 * y.shape[0] ** 0.5 + 1e-4)
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="needs oracle/_ref/libfolve_ref.so")
+@pytest.mark.parametrize("name", ["crossfeed", "tiny", "hilbert", "surround51", "roomcorr96", "quoting",
+                                  "missing_wav", "dirac_beyond_size", "size_zero", "copy_no_source"])
+def test_single_file_product_vs_reference(dirs, name):
+    d, rate, ch, bits = dirs[name]
+    c = _fragm(d, rate, ch)
+    N = c["fragm"]
+    x = _noise(2 * N + N // 3, ch, 0.25, 7)
+    (y,), mx, fl = H.product().run_chain(d, rate, ch, bits, [x])
+    (yr,), mxr, flr = H.reference().run_chain(d, rate, ch, bits, [x])
+    assert y.shape == yr.shape
+    assert np.abs(y - yr).max() < 1e-5
+    assert mx[0] == pytest.approx(mxr[0], abs=2e-6)
+    h = {k: v[1].astype(np.float64) * 2 * N for k, v in c["pairs"].items()}
+    t = truth_f64(x, h, c["nout"])
+    assert np.abs(y - t).max() < 1e-5
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="needs oracle/_ref/libfolve_ref.so")
+@pytest.mark.parametrize("broken", ["no_convolver", "impulse_before_new", "bad_ionum", "syntax", "unknown_cmd",
+                                    "too_many_inputs", "copy_self", "indented_command", "quoting_bad"])
+def test_broken_configs_fail_on_both_sides(dirs, broken):
+    d, rate, ch, bits = dirs[broken]
+    x = _noise(100, ch, 0.25, 1)
+    for side in (H.product(), H.reference()):
+        with pytest.raises(RuntimeError, match="Problem parsing"):
+            side.run_chain(d, rate, ch, bits, [x])
+    with pytest.raises(RuntimeError, match="No filter in"):
+        H.product().run_chain(d, rate + 1, ch, bits, [x])
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="needs oracle/_ref/libfolve_ref.so")
+def test_gapless_boundaries_and_quirks(dirs):
+    P, R = H.product(), H.reference()
+    d, rate, ch, bits = dirs["crossfeed"]
+    N = _fragm(d, rate, ch)["fragm"]
+    cases = []
+    for r in (1, N // 2, N - 1):
+        cases.append([N + r, 2 * N + 5, N + N // 3])
+    cases.append([2 * N, N + 7])            # quirk 3: multiple of fragm -> no hand-off
+    cases.append([N + 100, 50])             # quirk 4: successor swallowed by the top-up
+    cases.append([N + 100, N - 100, 333])   # successor exactly completes the block
+    cases.append([5, 6, 7, 3 * N])          # several files inside one block: only the first hand-off happens
+    for lens in cases:
+        x = _noise(sum(lens), ch, 0.25, sum(lens))
+        files = np.split(x, np.cumsum(lens)[:-1])
+        for gapless in (True, False):
+            P.drop_pool(); R.drop_pool()
+            outs, mx, fl = P.run_chain(d, rate, ch, bits, files, gapless=gapless)
+            outr, mxr, flr = R.run_chain(d, rate, ch, bits, files, gapless=gapless)
+            assert fl == flr, (lens, gapless)
+            assert [o.shape for o in outs] == [o.shape for o in outr], (lens, gapless)
+            for a, b in zip(outs, outr):
+                if a.size:
+                    assert np.abs(a - b).max() < 1e-5, (lens, gapless)
+            assert np.allclose(mx, mxr, atol=2e-6)
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="needs oracle/_ref/libfolve_ref.so")
+def test_quantised_output_within_one_lsb(dirs):
+    P, R = H.product(), H.reference()
+    d, rate, ch, bits = dirs["roomcorr96"]
+    N = _fragm(d, rate, ch)["fragm"]
+    r = np.random.default_rng(3)
+    lens = [2 * N + 77, N + 1000]
+    # 16-bit in / 16-bit out across a gapless boundary
+    xi = r.integers(-16000, 16000, (sum(lens), ch)).astype(np.int16)
+    files = np.split(xi, [lens[0]])
+    a, _, _ = P.run_chain(d, rate, ch, bits, files, in_format=H.SF_FORMAT_PCM_16, out_format=H.SF_FORMAT_PCM_16)
+    b, _, _ = R.run_chain(d, rate, ch, bits, files, in_format=H.SF_FORMAT_PCM_16, out_format=H.SF_FORMAT_PCM_16)
+    for u, v in zip(a, b):
+        assert np.abs(u.astype(np.int64) - v.astype(np.int64)).max() <= 1
+    # 24-bit: 1 LSB is 1.2e-7 of full scale, at float32's own noise floor for a
+    # 16384-point transform; report the histogram, require <= 4 LSB vs the
+    # reference and that the engine is not further from the float64 truth than it.
+    x24 = r.integers(-2**22, 2**22, (sum(lens), ch)).astype(np.int32)
+    files = np.split(x24, [lens[0]])
+    a, _, _ = P.run_chain(d, rate, ch, bits, files, in_format=H.SF_FORMAT_PCM_24, out_format=H.SF_FORMAT_PCM_24)
+    b, _, _ = R.run_chain(d, rate, ch, bits, files, in_format=H.SF_FORMAT_PCM_24, out_format=H.SF_FORMAT_PCM_24)
+    ya, yb = np.concatenate(a).astype(np.int64), np.concatenate(b).astype(np.int64)
+    diff = np.abs(ya - yb)
+    hist = np.bincount(np.minimum(diff.reshape(-1), 8), minlength=9)
+    print("24-bit |engine - reference| LSB histogram 0..8+:", hist.tolist())
+    assert diff.max() <= 4
+    assert hist[:2].sum() / hist.sum() > 0.97
+    c = _fragm(d, rate, ch)
+    h = {k: v[1].astype(np.float64) * 2 * N for k, v in c["pairs"].items()}
+    t = np.rint(truth_f64(x24.astype(np.float64) / 8388608.0, h, c["nout"]) * 8388607.0).astype(np.int64)
+    assert np.abs(ya - t).mean() <= np.abs(yb - t).mean() * 1.25 + 0.05
+
+
+def test_pool_reuse_reset_is_fresh(dirs):
+    """ProcessorPool::Return -> Reset(): a reused processor behaves like a new one,
+    also after an odd number of blocks (where the reference lags, quirk 5)."""
+    P = H.product()
+    d, rate, ch, bits = dirs["tiny"]
+    c = _fragm(d, rate, ch)
+    N = c["fragm"]
+    a, b = _noise(N, ch, 0.5, 11), _noise(3 * N + 9, ch, 0.5, 12)
+    (y0,), _, _ = P.run_chain(d, rate, ch, bits, [b], gapless=False)
+    P.run_chain(d, rate, ch, bits, [a], gapless=False)      # one block, back to the pool
+    (y1,), mx, _ = P.run_chain(d, rate, ch, bits, [b], gapless=False)
+    assert np.array_equal(y0, y1)
+    assert mx[0] == pytest.approx(max(0.0, float(y1.max())), abs=1e-7)
+
+
+def test_config_change_invalidates_pool_and_filter_cache(dirs, tmp_path):
+    import shutil, time
+    P = H.product()
+    src, rate, ch, bits = dirs["tiny"]
+    d = str(tmp_path / "tiny_copy")
+    shutil.copytree(src, d)
+    x = _noise(700, ch, 0.5, 21)
+    (y0,), _, _ = P.run_chain(d, rate, ch, bits, [x])
+    conf = os.path.join(d, f"filter-{rate}.conf")
+    with open(conf, "a") as f:
+        f.write("/impulse/dirac 1 1 0.5 3\n")
+    os.utime(conf, (time.time() + 5, time.time() + 5))
+    (y1,), _, _ = P.run_chain(d, rate, ch, bits, [x])
+    expect = y0.copy()
+    expect[3:] += 0.5 * x[:-3]
+    assert np.abs(y1 - expect).max() < 1e-5
