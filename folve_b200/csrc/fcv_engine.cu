@@ -472,7 +472,7 @@ extern "C" int fcv_filter_commit(fcv_filter *f, int device) {
     std::vector<float> rows;
     int nrows = 0, last_part = -1;
     for (auto &p : f->pairs) {
-        p.row.assign((size_t)f->npar, -1);
+        p.row.assign((size_t)(f->npar > 0 ? f->npar : 1), -1);  // at least one slot: ring depth is >= 1
         if (!p.exists || p.link >= 0 || p.h.empty()) continue;
         for (int j = 0; j < f->npar; j++) {
             const float *src = p.h.data() + (size_t)j * N;
