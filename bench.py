@@ -69,7 +69,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv:
@@ -122,32 +122,63 @@ def cpu_run(wl, nthreads, nblocks, amplitude=0.03):
     return nthreads * nblocks * wl.fragm / wl.fs, wall
 
 
-def cpu_baseline(wl, target_s=12.0):
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfolve_ref.so")
+HOST_SO = os.path.join(ROOT, "folve_b200", "libfolve_host.so")
+
+
+def harness_run(so, wl, filter_dir, nthreads, nblocks):
+    """The block loop of ConvolveFileHandler::AddMoreSoundData through SoundProcessor
+    (FillBuffer / WriteProcessed), one file per thread; returns (audio_s, wall_s)."""
+    L = C.CDLL(so)
+    L.fh_bench_threads.restype = C.c_double
+    L.fh_bench_threads.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    fragm = C.c_int(0)
+    wall = L.fh_bench_threads(filter_dir.encode(), wl.fs, wl.ninp, 16, nthreads, nblocks, C.byref(fragm))
+    if wall <= 0:
+        raise RuntimeError(f"fh_bench_threads failed in {so}")
+    return nthreads * nblocks * fragm.value / wl.fs, wall
+
+
+def cpu_arm(wl, filter_dir):
+    """-> (kind, runner(nthreads, nblocks) -> (audio_s, wall_s), description)"""
+    if os.path.exists(REF_SO):
+        return ("reference", lambda nt, nb: harness_run(REF_SO, wl, filter_dir, nt, nb),
+                "the reference's own sound-processor.cc / zita-config.cc / processor-pool.cc (compiled unmodified "
+                "into oracle/_ref) on the restated zita-convolver (oracle/zita_oracle.c, own float32 FFT, no FFTW)")
+    return ("port", lambda nt, nb: cpu_run(wl, nt, nb), "restated Convproc (oracle/zita_oracle.c)")
+
+
+def cpu_baseline(wl, filter_dir, target_s=12.0):
     cores = len(os.sched_getaffinity(0))
-    audio, wall = cpu_run(wl, cores, 8)           # calibration (also warms the cores)
-    nb = max(8, min(4096, int(8 * target_s / wall)))
-    audio, wall = cpu_run(wl, cores, nb)
+    kind, run, what = cpu_arm(wl, filter_dir)
+    audio, wall = run(cores, 8)                     # calibration (also warms the cores)
+    nb = max(8, min(100000, int(8 * target_s / wall)))
+    audio, wall = run(cores, nb)
     return {
-        "value": audio / wall, "unit": "x realtime (audio-s per wall-s)", "cores": cores, "kind": "port",
-        "sample": f"{cores} streams x {nb} blocks of {wl.fragm} frames ({wl.name}), one restated Convproc per "
-                  f"stream, one stream per thread; {wall:.1f} s wall",
+        "value": audio / wall, "unit": "x realtime (audio-s per wall-s)", "cores": cores, "kind": kind,
+        "sample": f"{cores} files x {nb} blocks of {wl.fragm} frames ({wl.name}), one SoundProcessor/Convproc per "
+                  f"file, one file per thread, {wall:.1f} s wall; {what}",
     }
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    import tempfile
     wl = workloads.WORKLOADS[args.workload]()
     cores = len(os.sched_getaffinity(0))
-    audio, wall = cpu_run(wl, cores, 4)
-    nb = max(4, min(2048, int(4 * 4.0 / wall)))   # ~4 s of CPU work per step
-    for _ in range(args.warmup):
-        cpu_run(wl, cores, max(2, nb // 4))
-    t_audio = t_wall = 0.0
-    for _ in range(args.steps):
-        a, w = cpu_run(wl, cores, nb)
-        t_audio += a
-        t_wall += w
+    with tempfile.TemporaryDirectory() as tmp:
+        filter_dir = workloads.write_filter_dir(wl, os.path.join(tmp, wl.name))
+        kind, run, what = cpu_arm(wl, filter_dir)
+        audio, wall = run(cores, 8)
+        nb = max(8, min(20000, int(8 * 4.0 / wall)))   # ~4 s of CPU work per step
+        for _ in range(args.warmup):
+            run(cores, max(4, nb // 8))
+        t_audio = t_wall = 0.0
+        for _ in range(args.steps):
+            a, w = run(cores, nb)
+            t_audio += a
+            t_wall += w
     v = t_audio / t_wall
     unit = "x realtime (audio-s per wall-s)"
     line = {
@@ -156,10 +187,10 @@ def run_reference(args, rank, world):
         "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "fs": wl.fs, "channels": wl.ninp, "fragm": wl.fragm,
-                   "streams": cores, "blocks_per_step": nb},
-        "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": f"per step: {cores} streams x {nb} blocks of {wl.fragm} frames, one restated "
-                                   "Convproc (oracle/zita_oracle.c) per stream, one stream per thread"},
+                   "files": cores, "blocks_per_step": nb},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind,
+                         "sample": f"per step: {cores} files x {nb} blocks of {wl.fragm} frames, one file per "
+                                   f"thread; {what}"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -187,7 +218,7 @@ def ncu_traffic(wl_name, streams):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="santalucia", choices=sorted(workloads.WORKLOADS))
@@ -309,7 +340,19 @@ def main():
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            import tempfile
+            with tempfile.TemporaryDirectory() as tmp:
+                filter_dir = workloads.write_filter_dir(wl, os.path.join(tmp, wl.name))
+                line["cpu_baseline"] = cpu_baseline(wl, filter_dir)
+                if os.path.exists(HOST_SO) and not args.skip_e2e:
+                    # the drop-in API itself: one synchronous SoundProcessor per host thread on the GPU
+                    cores = len(os.sched_getaffinity(0))
+                    harness_run(HOST_SO, wl, filter_dir, cores, 20)
+                    a, w = harness_run(HOST_SO, wl, filter_dir, cores, 400)
+                    line["e2e"]["soundprocessor_sync"] = {
+                        "value": a / w, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
+                        "what": "SoundProcessor::FillBuffer/WriteProcessed block loop, one file per host thread, "
+                                "one synchronous fcv_stream_process per block"}
         print(json.dumps(line), flush=True)
 
     batch.close()

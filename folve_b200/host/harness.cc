@@ -15,6 +15,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <pthread.h>
+#include <time.h>
+
 #include <string>
 #include <vector>
 
@@ -130,6 +133,9 @@ struct Chain {
     }
 };
 
+// largest block size any configuration can have (Convproc::MAXQUANT)
+int Convproc_MAXQUANT_for_probe() { return 8192; }
+
 size_t SampleBytes(int subformat) {
     return subformat == SF_FORMAT_PCM_16 ? 2 : 4;
 }
@@ -222,6 +228,98 @@ int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits,
         if (f.out) sf_close(f.out);
     }
     return rc ? rc : nout;
+}
+
+// ---- throughput of the synchronous drop-in API ---------------------------------
+// `nthreads` independent files, one SoundProcessor each (from the pool, i.e. via
+// SoundProcessor::Create and the filter-config parser), one file per thread --
+// the way folve uses its cores (README.md:361-362).  Every thread runs the
+// FillBuffer / WriteProcessed block loop of AddMoreSoundData for `nblocks` full
+// blocks on in-memory float PCM (a 16-block loop of white noise, re-read by
+// seeking back) into a discarding sink.  Returns the wall seconds of the block
+// loops (processor creation excluded), <0 on error.
+struct BenchJob {
+    ProcessorPool *pool;
+    const char *dir;
+    int rate, channels, bits, nblocks, index;
+    pthread_barrier_t *start, *stop;
+    int ok;
+    int fragm;
+    float max_value;
+};
+
+static void *BenchWorker(void *arg) {
+    BenchJob *j = (BenchJob *)arg;
+    std::string err;
+    SoundProcessor *p = j->pool->GetOrCreate(j->dir, j->rate, j->channels, j->bits, &err);
+    j->ok = p != nullptr;
+    std::vector<float> pcm;
+    SNDFILE *in = nullptr, *out = nullptr;
+    const int loop_blocks = 16;
+    int fragm = 0;
+    if (p) {
+        // a processor that just came out of Create has an empty block: its size is
+        // what one FillBuffer on a long enough file returns
+        std::vector<float> probe((size_t)Convproc_MAXQUANT_for_probe() * (size_t)j->channels, 0.0f);
+        SNDFILE *ps = sf_shim_open_memory_read(probe.data(), (sf_count_t)(probe.size() / (size_t)j->channels),
+                                               j->channels, j->rate, SF_FORMAT_FLOAT);
+        fragm = p->FillBuffer(ps);
+        sf_close(ps);
+        p->Reset();
+        j->fragm = fragm;
+        pcm.resize((size_t)fragm * (size_t)loop_blocks * (size_t)j->channels);
+        uint32_t s = (uint32_t)(j->index + 1) * 2654435761u + 12345u;
+        for (size_t i = 0; i < pcm.size(); i++) {
+            s = s * 1664525u + 1013904223u;
+            pcm[i] = 0.03f * ((float)(s >> 8) * (1.0f / 8388608.0f) - 1.0f);
+        }
+        in = sf_shim_open_memory_read(pcm.data(), (sf_count_t)fragm * loop_blocks, j->channels, j->rate, SF_FORMAT_FLOAT);
+        out = sf_shim_open_null_write(p->output_channels(), j->rate, SF_FORMAT_FLOAT);
+    }
+    pthread_barrier_wait(j->start);
+    if (p) {
+        for (int b = 0; b < j->nblocks; b++) {
+            if (b % loop_blocks == 0) sf_seek(in, 0, SEEK_SET);
+            const int r = p->FillBuffer(in);
+            p->WriteProcessed(out, r);
+        }
+        j->max_value = p->max_output_value();
+    }
+    pthread_barrier_wait(j->stop);
+    if (in) sf_close(in);
+    if (out) sf_close(out);
+    if (p) j->pool->Return(p);
+    return nullptr;
+}
+
+double fh_bench_threads(const char *filter_dir, int samplerate, int channels, int bits, int nthreads, int nblocks,
+                        int *fragm_out) {
+    if (nthreads < 1) return -1.0;
+    ProcessorPool pool(0);  // nothing is kept: every thread creates and finally deletes its processor
+    std::vector<pthread_t> th((size_t)nthreads);
+    std::vector<BenchJob> jobs((size_t)nthreads);
+    pthread_barrier_t start, stop;
+    pthread_barrier_init(&start, nullptr, (unsigned)nthreads + 1);
+    pthread_barrier_init(&stop, nullptr, (unsigned)nthreads + 1);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[(size_t)t] = BenchJob{&pool, filter_dir, samplerate, channels, bits, nblocks, t, &start, &stop, 0, 0, 0.f};
+        pthread_create(&th[(size_t)t], nullptr, BenchWorker, &jobs[(size_t)t]);
+    }
+    pthread_barrier_wait(&start);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_barrier_wait(&stop);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    int ok = 1;
+    for (int t = 0; t < nthreads; t++) {
+        pthread_join(th[(size_t)t], nullptr);
+        ok &= jobs[(size_t)t].ok;
+    }
+    pthread_barrier_destroy(&start);
+    pthread_barrier_destroy(&stop);
+    if (fragm_out) *fragm_out = jobs[0].fragm;
+    if (!ok) return -1.0;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
 // ---- what a configuration file loads ------------------------------------------

@@ -95,6 +95,9 @@ SNDFILE *sf_shim_open_memory_read(const void *pcm, sf_count_t frames, int channe
                                   int format);
 /* Write-only sink that quantises to `format` and keeps the samples in memory. */
 SNDFILE *sf_shim_open_memory_write(int channels, int samplerate, int format);
+/* Write-only sink that converts like `format` would but discards the samples
+ * (benchmarks: no memory growth). */
+SNDFILE *sf_shim_open_null_write(int channels, int samplerate, int format);
 /* Frames written so far and a pointer to the interleaved samples (int16_t for
  * PCM_16, int32_t for PCM_24/PCM_32, float for FLOAT); valid until sf_close. */
 sf_count_t sf_shim_memory_frames(SNDFILE *sndfile);

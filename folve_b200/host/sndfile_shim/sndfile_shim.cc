@@ -19,6 +19,7 @@ struct SNDFILE_tag {
     int subformat = 0;
     bool clipping = false;
     sf_count_t pos = 0;  // in frames
+    bool discard = false;
     // file-backed read
     FILE *fp = nullptr;
     long data_offset = 0;
@@ -152,6 +153,12 @@ extern "C" SNDFILE *sf_shim_open_memory_write(int channels, int samplerate, int 
     return s;
 }
 
+extern "C" SNDFILE *sf_shim_open_null_write(int channels, int samplerate, int format) {
+    SNDFILE *s = sf_shim_open_memory_write(channels, samplerate, format);
+    if (s) s->discard = true;
+    return s;
+}
+
 extern "C" int sf_close(SNDFILE *s) {
     if (!s) return 1;
     if (s->fp) fclose(s->fp);
@@ -242,6 +249,17 @@ static inline long quant(float x, float scale, long lo, long hi, bool clip) {
 extern "C" sf_count_t sf_writef_float(SNDFILE *s, const float *ptr, sf_count_t frames) {
     if (!s || s->mode != SFM_WRITE || frames <= 0) return 0;
     const size_t n = (size_t)frames * (size_t)s->info.channels;
+    if (s->discard) {
+        // keep the conversion cost of the format, drop the result
+        long acc = 0;
+        if (s->subformat == SF_FORMAT_PCM_16) for (size_t i = 0; i < n; i++) acc += quant(ptr[i], 32767.0f, -32768, 32767, s->clipping);
+        else if (s->subformat == SF_FORMAT_PCM_24) for (size_t i = 0; i < n; i++) acc += quant(ptr[i], 8388607.0f, -8388608, 8388607, s->clipping);
+        s->scratch.resize(sizeof(long));
+        memcpy(s->scratch.data(), &acc, sizeof(long));
+        s->pos += frames;
+        s->info.frames = s->pos;
+        return frames;
+    }
     switch (s->subformat) {
         case SF_FORMAT_PCM_16:
             for (size_t i = 0; i < n; i++) s->w16.push_back((int16_t)quant(ptr[i], 32767.0f, -32768, 32767, s->clipping));

@@ -89,6 +89,41 @@ def surround51(fs=48000, dense=False):
     return Workload("surround51_dense" if dense else "surround51", fs, 6, 6, 65536, adds)
 
 
+def write_float_wav(path, data, rate):
+    """Mono/multi-channel IEEE float32 RIFF/WAVE, [frames, channels]."""
+    import struct
+    data = np.asarray(data, "<f4")
+    if data.ndim == 1:
+        data = data[:, None]
+    raw = data.tobytes()
+    ch = data.shape[1]
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " + struct.pack(
+        "<IHHIIHH", 16, 3, ch, rate, rate * ch * 4, ch * 4, 32) + b"data" + struct.pack("<I", len(raw))
+    with open(path, "wb") as f:
+        f.write(hdr + raw)
+
+
+def write_filter_dir(wl, directory):
+    """The workload as a folve filter directory in the reference's .conf syntax:
+    filter-<rate>.conf plus one float32 WAV per multi-tap impulse."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    lines = [f"# synthetic stand-in for the {wl.name} workload (folve_b200/workloads.py)",
+             f"/convolver/new {wl.ninp} {wl.nout} 256 {wl.size}"]
+    for k, (i, o, d, i0) in enumerate(wl.adds):
+        if len(d) == 1:
+            lines.append(f"/impulse/dirac {i + 1} {o + 1} {float(d[0])!r} {i0}")
+        else:
+            name = f"ir_{k}.wav"
+            write_float_wav(os.path.join(directory, name), d, wl.fs)
+            lines.append(f"/impulse/read {i + 1} {o + 1} 1.0 {i0} 0 0 1 {name}")
+    for (i1, o1, i2, o2) in wl.links:   # fcv/zita order: source first; config order: destination first
+        lines.append(f"/impulse/copy {i2 + 1} {o2 + 1} {i1 + 1} {o1 + 1}")
+    with open(os.path.join(directory, f"filter-{wl.fs}.conf"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return directory
+
+
 WORKLOADS = {
     "santalucia": santalucia,
     "lowpass": lowpass,
