@@ -78,6 +78,10 @@ def lib() -> C.CDLL:
         "fcv_batch_device_in": (vp, [vp]),
         "fcv_batch_device_out": (vp, [vp]),
         "fcv_batch_process": (i, [vp, ip]),
+        "fcv_batch_host_in_slot": (vp, [vp, i]),
+        "fcv_batch_host_out_slot": (vp, [vp, i]),
+        "fcv_batch_submit": (i, [vp, i, ip]),
+        "fcv_batch_wait": (i, [vp, i]),
         "fcv_batch_process_device": (i, [vp, ip]),
         "fcv_batch_sync": (i, [vp]),
         "fcv_batch_reset_slot": (i, [vp, i]),
@@ -228,6 +232,21 @@ class Batch:
     def process(self, frames_valid=None):
         keep, p = self._fv(frames_valid)
         _check(lib().fcv_batch_process(self._h, p))
+
+    def slot_views(self, slot):
+        """numpy views of the pinned in/out staging of `slot` (0 or 1)."""
+        L = lib()
+        ibuf = (C.c_char * self.in_bytes).from_address(L.fcv_batch_host_in_slot(self._h, slot))
+        obuf = (C.c_char * self.out_bytes).from_address(L.fcv_batch_host_out_slot(self._h, slot))
+        return (np.frombuffer(ibuf, dtype=self.host_in.dtype).reshape(self.host_in.shape),
+                np.frombuffer(obuf, dtype=self.host_out.dtype).reshape(self.host_out.shape))
+
+    def submit(self, slot, frames_valid=None):
+        keep, p = self._fv(frames_valid)
+        _check(lib().fcv_batch_submit(self._h, slot, p))
+
+    def wait(self, slot):
+        _check(lib().fcv_batch_wait(self._h, slot))
 
     def process_device(self, frames_valid=None):
         keep, p = self._fv(frames_valid)

@@ -631,6 +631,11 @@ struct fcv_batch {
     // host
     unsigned char *hin = nullptr, *hout = nullptr;
     int *hfv = nullptr;
+    // second host staging slot + per-slot completion events for the asynchronous submit/wait pair
+    unsigned char *hin1 = nullptr, *hout1 = nullptr;
+    int *dfv1 = nullptr, *hfv1 = nullptr;
+    cudaEvent_t slot_done[2][4] = {};
+    bool slot_busy[2] = {false, false};
     // streams
     static const int NQ = 4;
     cudaStream_t q[NQ] = {};
@@ -656,6 +661,13 @@ static void batch_free(fcv_batch *b) {
     if (b->hin) cudaFreeHost(b->hin);
     if (b->hout) cudaFreeHost(b->hout);
     if (b->hfv) cudaFreeHost(b->hfv);
+    if (b->hin1) cudaFreeHost(b->hin1);
+    if (b->hout1) cudaFreeHost(b->hout1);
+    if (b->hfv1) cudaFreeHost(b->hfv1);
+    if (b->dfv1) cudaFree(b->dfv1);
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < 4; i++)
+            if (b->slot_done[k][i]) cudaEventDestroy(b->slot_done[k][i]);
     if (b->f) fcv_filter_unref(b->f);
     delete b;
 }
@@ -758,10 +770,10 @@ static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_
 }
 
 // The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
-static int run_kernels(fcv_batch *b, int off, int cnt, bool use_fv, cudaStream_t q, cudaEvent_t *ev) {
+static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaStream_t q, cudaEvent_t *ev) {
     fcv_filter *f = b->f;
     const int pt = (int)(b->step % (unsigned long long)f->ring);
-    const int *fv = use_fv ? b->dfv + off : nullptr;
+    const int *fv = fv_base ? fv_base + off : nullptr;
     const FftTables tb = f->tb;
     if (ev) cudaEventRecord(ev[0], q);
     DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(f->ninp, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
@@ -833,7 +845,7 @@ extern "C" int fcv_batch_process_device(fcv_batch *b, const int *frames_valid) {
         int rc = stage_fv(b, frames_valid, b->q[0]);
         if (rc) return rc;
     }
-    int rc = run_kernels(b, 0, b->B, frames_valid != nullptr, b->q[0], prof_events(b));
+    int rc = run_kernels(b, 0, b->B, frames_valid ? b->dfv : nullptr, b->q[0], prof_events(b));
     if (rc) return rc;
     b->step++;
     return 0;
@@ -847,36 +859,95 @@ extern "C" int fcv_batch_sync(fcv_batch *b) {
     return 0;
 }
 
-extern "C" int fcv_batch_process(fcv_batch *b, const int *frames_valid) {
-    if (!b) return fail(FCV_E_PARAM, "null batch");
+static int ensure_slot1(fcv_batch *b) {
+    if (b->hin1) return 0;
+    const size_t B = (size_t)b->B;
+    CU_TRY(cudaHostAlloc((void **)&b->hin1, B * b->in_block, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc((void **)&b->hout1, B * b->out_block, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc((void **)&b->hfv1, B * sizeof(int), cudaHostAllocDefault));
+    CU_TRY(cudaMalloc((void **)&b->dfv1, B * sizeof(int)));
+    memset(b->hin1, 0, B * b->in_block);
+    memset(b->hout1, 0, B * b->out_block);
+    return 0;
+}
+
+extern "C" void *fcv_batch_host_in_slot(fcv_batch *b, int slot) {
+    if (!b || !b->hout || slot < 0 || slot > 1) return nullptr;
+    if (slot == 1 && (cudaSetDevice(b->f->device) != cudaSuccess || ensure_slot1(b))) return nullptr;
+    return slot ? b->hin1 : b->hin;
+}
+extern "C" void *fcv_batch_host_out_slot(fcv_batch *b, int slot) {
+    if (!b || !b->hout || slot < 0 || slot > 1) return nullptr;
+    if (slot == 1 && (cudaSetDevice(b->f->device) != cudaSuccess || ensure_slot1(b))) return nullptr;
+    return slot ? b->hout1 : b->hout;
+}
+
+extern "C" int fcv_batch_wait(fcv_batch *b, int slot) {
+    if (!b || slot < 0 || slot > 1) return fail(FCV_E_PARAM, "bad slot");
+    if (!b->slot_busy[slot]) return 0;
+    CU_TRY(cudaSetDevice(b->f->device));
+    for (int i = 0; i < fcv_batch::NQ; i++)
+        if (b->slot_done[slot][i]) CU_TRY(cudaEventSynchronize(b->slot_done[slot][i]));
+    b->slot_busy[slot] = false;
+    return 0;
+}
+
+// Enqueue one block for every stream from host staging slot `slot`:
+// per chunk of streams host->device copy, the three kernels, device->host copy,
+// round-robin over NQ CUDA streams.  Chunks of consecutive submits run in order
+// on their stream, so the device state needs no double buffering; only the host
+// staging has two slots.
+extern "C" int fcv_batch_submit(fcv_batch *b, int slot, const int *frames_valid) {
+    if (!b || slot < 0 || slot > 1) return fail(FCV_E_PARAM, "bad slot");
     if (!b->hout) return fail(FCV_E_STATE, "batch has no host staging");
     CU_TRY(cudaSetDevice(b->f->device));
+    if (slot == 1) { int rc = ensure_slot1(b); if (rc) return rc; }
+    int rc = fcv_batch_wait(b, slot);  // the slot's previous submit must have drained
+    if (rc) return rc;
+    unsigned char *hin = slot ? b->hin1 : b->hin, *hout = slot ? b->hout1 : b->hout;
+    int *hfv = slot ? b->hfv1 : b->hfv, *dfv = slot ? b->dfv1 : b->dfv;
     if (frames_valid) {
-        int rc = stage_fv(b, frames_valid, b->q[0]);
-        if (rc) return rc;
-        CU_TRY(cudaStreamSynchronize(b->q[0]));
+        for (int s = 0; s < b->B; s++) {
+            const int v = frames_valid[s];
+            if (v < 0 || v > b->f->fragm) return fail(FCV_E_PARAM, "frames_valid[%d] = %d out of range", s, v);
+            hfv[s] = v;
+        }
     }
-    // Independent streams: cut the batch into chunks and pipeline
-    // host->device copy, kernels and device->host copy over NQ CUDA streams.
     int nchunk = 1;
     if (!b->profiling) {
-        nchunk = b->B / 128;
-        if (nchunk > 8) nchunk = 8;
+        static const int env_chunks = getenv("FCV_CHUNKS") ? atoi(getenv("FCV_CHUNKS")) : 0;  // tuning knob
+        nchunk = env_chunks > 0 ? env_chunks : b->B / 128;
+        if (nchunk > 16) nchunk = 16;
+        if (nchunk > b->B) nchunk = b->B;
         if (nchunk < 1) nchunk = 1;
     }
+    static const bool env_nokernels = getenv("FCV_COPY_ONLY") != nullptr;  // diagnostic: copies without kernels
     const int per = (b->B + nchunk - 1) / nchunk;
     for (int c = 0, off = 0; off < b->B; c++, off += per) {
         const int cnt = (b->B - off) < per ? (b->B - off) : per;
         cudaStream_t q = b->q[nchunk == 1 ? 0 : c % fcv_batch::NQ];
-        CU_TRY(cudaMemcpyAsync(b->din + (size_t)off * b->in_block, b->hin + (size_t)off * b->in_block,
+        if (frames_valid)
+            CU_TRY(cudaMemcpyAsync(dfv + off, hfv + off, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, q));
+        CU_TRY(cudaMemcpyAsync(b->din + (size_t)off * b->in_block, hin + (size_t)off * b->in_block,
                                (size_t)cnt * b->in_block, cudaMemcpyHostToDevice, q));
-        int rc = run_kernels(b, off, cnt, frames_valid != nullptr, q, nchunk == 1 ? prof_events(b) : nullptr);
+        if (!env_nokernels) rc = run_kernels(b, off, cnt, frames_valid ? dfv : nullptr, q, nchunk == 1 ? prof_events(b) : nullptr);
         if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(b->hout + (size_t)off * b->out_block, b->dout + (size_t)off * b->out_block,
+        CU_TRY(cudaMemcpyAsync(hout + (size_t)off * b->out_block, b->dout + (size_t)off * b->out_block,
                                (size_t)cnt * b->out_block, cudaMemcpyDeviceToHost, q));
     }
+    for (int i = 0; i < fcv_batch::NQ; i++) {
+        if (!b->slot_done[slot][i]) CU_TRY(cudaEventCreateWithFlags(&b->slot_done[slot][i], cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(b->slot_done[slot][i], b->q[i]));
+    }
+    b->slot_busy[slot] = true;
     b->step++;
-    return fcv_batch_sync(b);
+    return 0;
+}
+
+extern "C" int fcv_batch_process(fcv_batch *b, const int *frames_valid) {
+    int rc = fcv_batch_submit(b, 0, frames_valid);
+    if (rc) return rc;
+    return fcv_batch_wait(b, 0);
 }
 
 extern "C" int fcv_batch_reset_slot(fcv_batch *b, int slot) {
@@ -985,7 +1056,7 @@ extern "C" int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_in
     CU_TRY(cudaMemcpyAsync(b->dfv, b->hfv, sizeof(int), cudaMemcpyHostToDevice, q));
     if (frames_valid > 0)
         CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)frames_valid * f->ninp * sizeof(float), cudaMemcpyHostToDevice, q));
-    int rc = run_kernels(b, 0, 1, true, q, nullptr);
+    int rc = run_kernels(b, 0, 1, b->dfv, q, nullptr);
     if (rc) return rc;
     b->step++;
     // one copy brings back the whole output block and the running maximum behind it

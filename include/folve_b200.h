@@ -164,6 +164,16 @@ void *fcv_batch_device_out(fcv_batch *b);
  * NULL (all blocks full) or an array of nstreams counts in [0, fragm]. */
 int fcv_batch_process(fcv_batch *b, const int *frames_valid);
 
+/* Asynchronous form with two host staging slots (slot 0 is host_in/host_out
+ * above), so that the copies of consecutive blocks overlap: submit enqueues
+ * host_in_slot(slot) -> device, convolve, device -> host_out_slot(slot) and
+ * returns; wait blocks until that slot's output is complete.  Blocks are
+ * processed in submit order.  fcv_batch_process == submit(0) + wait(0). */
+void *fcv_batch_host_in_slot(fcv_batch *b, int slot);
+void *fcv_batch_host_out_slot(fcv_batch *b, int slot);
+int fcv_batch_submit(fcv_batch *b, int slot, const int *frames_valid);
+int fcv_batch_wait(fcv_batch *b, int slot);
+
 /* One block for every stream on device-resident PCM (device_in -> device_out),
  * asynchronous on the batch's CUDA stream; no host copies.  Call
  * fcv_batch_sync() to wait. */

@@ -233,6 +233,39 @@ def test_batch_frames_valid_and_slot_reset():
     f.close()
 
 
+def test_async_submit_wait_two_slots():
+    r = _rng(20)
+    spec = FilterSpec(2, 2, 20000)
+    for ch in range(2):
+        spec.add(ch, ch, r.standard_normal(20000) * 0.005, 0)
+    f = _engine(spec)
+    N, B, nblk = spec.fragm, 300, 5          # > 256 streams: several chunks over several CUDA streams
+    x = r.uniform(-0.4, 0.4, (B, nblk * N, 2)).astype(np.float32)
+    ref = capi.Batch(f, B)
+    want = []
+    for k in range(nblk):
+        ref.host_in[:] = x[:, k * N:(k + 1) * N]
+        ref.process()
+        want.append(ref.host_out.copy())
+    ref.close()
+    bt = capi.Batch(f, B)
+    views = [bt.slot_views(0), bt.slot_views(1)]
+    got = []
+    views[0][0][:] = x[:, :N]
+    bt.submit(0)
+    for k in range(1, nblk):
+        views[k & 1][0][:] = x[:, k * N:(k + 1) * N]
+        bt.submit(k & 1)
+        bt.wait((k - 1) & 1)
+        got.append(views[(k - 1) & 1][1].copy())
+    bt.wait((nblk - 1) & 1)
+    got.append(views[(nblk - 1) & 1][1].copy())
+    for k in range(nblk):
+        assert np.array_equal(got[k], want[k]), k
+    bt.close()
+    f.close()
+
+
 def test_errors_are_reported_not_fatal():
     L = capi.lib()
     assert not L.fcv_filter_begin(0, 2, 100, 64)
