@@ -22,8 +22,10 @@ clean:
 HOST = folve_b200/host
 HOSTLIB = folve_b200/libfolve_host.so
 HOST_SRCS = $(HOST)/sound-processor.cc $(HOST)/filter-config.cc $(HOST)/processor-pool.cc \
+            $(HOST)/batch-convolver.cc \
             $(HOST)/harness.cc $(HOST)/sndfile_shim/sndfile_shim.cc
 HOST_HDRS = $(HOST)/sound-processor.h $(HOST)/filter-config.h $(HOST)/processor-pool.h \
+            $(HOST)/batch-convolver.h \
             $(HOST)/sndfile_shim/sndfile.h include/folve_b200.h
 # same optimisation flags as oracle/Makefile so that float expressions in the
 # config loader (hilbert taps, gains) round identically on both sides

@@ -955,9 +955,14 @@ extern "C" int fcv_batch_reset_slot(fcv_batch *b, int slot) {
     CU_TRY(cudaSetDevice(b->f->device));
     const fcv_filter *f = b->f;
     const size_t N = (size_t)f->fragm;
+    // chunks of a batch run on several CUDA streams: order the reset after everything
+    // already enqueued and before anything enqueued later
+    int rc = fcv_batch_sync(b);
+    if (rc) return rc;
     CU_TRY(cudaMemsetAsync(b->xring + (size_t)slot * f->ninp * f->ring * N, 0, b->state_bytes_per_stream, b->q[0]));
     CU_TRY(cudaMemsetAsync(b->tail + (size_t)slot * f->nout * N, 0, (size_t)f->nout * N * sizeof(float), b->q[0]));
     CU_TRY(cudaMemsetAsync(b->maxv + slot, 0, sizeof(float), b->q[0]));
+    CU_TRY(cudaStreamSynchronize(b->q[0]));
     return 0;
 }
 
@@ -1037,9 +1042,7 @@ extern "C" void fcv_stream_destroy(fcv_stream *s) {
 
 extern "C" int fcv_stream_reset(fcv_stream *s) {
     if (!s) return fail(FCV_E_PARAM, "null stream");
-    int rc = fcv_batch_reset_slot(s->b, 0);
-    if (rc) return rc;
-    return fcv_batch_sync(s->b);
+    return fcv_batch_reset_slot(s->b, 0);
 }
 
 extern "C" float *fcv_stream_buffer(fcv_stream *s) { return s ? (float *)s->b->hin : nullptr; }

@@ -1,0 +1,78 @@
+// -*- c++ -*-
+// batch-convolver.h -- the batched submit layer: many files / gapless album chains
+// convolved at once on one GPU.
+//
+// Role in the reference: what BufferThread + ConversionBuffer::FillUntil +
+// ConvolveFileHandler::AddMoreSoundData do one file and ~one block per scheduler
+// turn (buffer-thread.cc:73-105, conversion-buffer.cc:151-163,
+// convolve-file-handler.cc:370-424) -- here every active chain contributes one
+// block per step and all blocks go through ONE fcv_batch launch sequence.
+//
+// Results are those of the per-file SoundProcessor path, including the gapless
+// hand-off rules of PassoverProcessor (convolve-file-handler.cc:328-351) and
+// their corner cases:
+//   * a file that ends inside a block is topped up ONCE from the alphabetically
+//     next file; the block's output is split between the two;
+//   * a file whose length is a multiple of the block size hands nothing over:
+//     its successor starts from a reset state;
+//   * a successor that is swallowed whole by the top-up produces no output and
+//     ends the hand-off; the file after it starts from a reset state.
+#ifndef FOLVE_B200_BATCH_CONVOLVER_H
+#define FOLVE_B200_BATCH_CONVOLVER_H
+
+#include <sndfile.h>
+
+#include <string>
+#include <vector>
+
+struct fcv_filter;
+struct fcv_batch;
+
+namespace folve_b200 {
+
+struct ChainFile {
+    SNDFILE *in = nullptr;   // borrowed; `frames` frames of `channels` channels
+    SNDFILE *out = nullptr;  // borrowed; receives exactly the frames this file would get from folve
+    long frames = 0;
+    // results
+    long written = 0;
+    bool in_gapless = false, out_gapless = false;
+    float max_value = 0.0f;  // SoundProcessor::max_output_value() at the moment the file was finished
+};
+
+typedef std::vector<ChainFile> Chain;  // files of one directory, alphabetical order
+
+class BatchConvolver {
+public:
+    // `slots` chains are in flight at once.  NULL on configuration or GPU failure.
+    static BatchConvolver *Create(const std::string &config_file, int samplerate, int channels, int slots,
+                                  bool gapless, int device);
+    ~BatchConvolver();
+
+    int fragment_size() const { return fragm_; }
+    int input_channels() const { return ninp_; }
+    int output_channels() const { return nout_; }
+
+    // Convolves every chain (pointers must stay valid until the call returns).
+    // `threads` host threads move PCM between the SNDFILEs and the pinned staging.
+    bool Run(const std::vector<Chain *> &chains, int threads);
+
+    long blocks_processed() const { return blocks_; }
+    long steps() const { return steps_; }
+
+private:
+    BatchConvolver() {}
+    struct Slot;
+    void FillSlot(Slot &s, float *in_block);
+    void DrainSlot(Slot &s, const float *out_block, float running_max);
+
+    fcv_filter *filter_ = nullptr;
+    fcv_batch *batch_ = nullptr;
+    int fragm_ = 0, ninp_ = 0, nout_ = 0, slots_ = 0;
+    bool gapless_ = true;
+    long blocks_ = 0, steps_ = 0;
+};
+
+}  // namespace folve_b200
+
+#endif

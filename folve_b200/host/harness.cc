@@ -29,6 +29,7 @@
 #if FOLVE_HARNESS_REFERENCE
 #include <zita-config.h>
 #else
+#include <batch-convolver.h>
 #include <filter-config.h>
 #include <folve_b200.h>
 #endif
@@ -229,6 +230,49 @@ int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits,
     }
     return rc ? rc : nout;
 }
+
+#if !FOLVE_HARNESS_REFERENCE
+// ---- the batched submit layer ----------------------------------------------------
+// Runs a whole library -- file i belongs to chain chain_of_file[i] (non-decreasing),
+// files of a chain in alphabetical order -- through folve_b200::BatchConvolver with
+// `slots` chains in flight.  PCM in/out is float, [frames][channels].
+// Returns the number of output channels, <0 on failure.
+int fh_run_library(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
+                   int nfiles, const int *chain_of_file, const float *const *pcm, const long *frames,
+                   float *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags, long *steps_out) {
+    folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
+        config_file, samplerate, channels, slots, gapless != 0, SoundProcessor::Device());
+    if (!bc) return -1;
+    const int nout = bc->output_channels();
+    std::vector<folve_b200::Chain> chains;
+    for (int i = 0; i < nfiles; i++) {
+        if (chains.empty() || (i > 0 && chain_of_file[i] != chain_of_file[i - 1])) chains.emplace_back();
+        folve_b200::ChainFile f;
+        f.in = sf_shim_open_memory_read(pcm[i], frames[i], channels, samplerate, SF_FORMAT_FLOAT);
+        f.out = sf_shim_open_memory_write(nout, samplerate, SF_FORMAT_FLOAT);
+        f.frames = frames[i];
+        chains.back().push_back(f);
+    }
+    std::vector<folve_b200::Chain *> ptrs;
+    for (auto &c : chains) ptrs.push_back(&c);
+    const bool ok = bc->Run(ptrs, threads);
+    int i = 0;
+    for (auto &c : chains)
+        for (auto &f : c) {
+            const long n = (long)sf_shim_memory_frames(f.out);
+            out_frames[i] = n;
+            if (n > 0) memcpy(out_pcm[i], sf_shim_memory_data(f.out), (size_t)n * (size_t)nout * sizeof(float));
+            max_values[i] = f.max_value;
+            gapless_flags[i] = (f.in_gapless ? 1 : 0) | (f.out_gapless ? 2 : 0);
+            sf_close(f.in);
+            sf_close(f.out);
+            i++;
+        }
+    if (steps_out) *steps_out = bc->steps();
+    delete bc;
+    return ok ? nout : -2;
+}
+#endif
 
 // ---- throughput of the synchronous drop-in API ---------------------------------
 // `nthreads` independent files, one SoundProcessor each (from the pool, i.e. via

@@ -84,6 +84,42 @@ class Harness:
             res.append(flat.reshape(oframes[k], nout).copy())
         return res, list(mx), list(flags)
 
+    def run_library(self, config_file, samplerate, channels, chains, gapless=True, slots=4, threads=2):
+        """chains: list of lists of [frames, channels] float32 arrays.  Product only.
+        Returns (outputs per chain per file, max values, flags, steps)."""
+        if not hasattr(self.L, "fh_run_library"):
+            raise RuntimeError("fh_run_library is only in the product harness")
+        fn = self.L.fh_run_library
+        fn.restype = C.c_int
+        files = [np.ascontiguousarray(f, np.float32) for c in chains for f in c]
+        cof = [ci for ci, c in enumerate(chains) for _ in c]
+        n = len(files)
+        fp = C.POINTER(C.c_float)
+        pin = (fp * n)(*[f.ctypes.data_as(fp) for f in files])
+        frames = (C.c_long * n)(*[f.shape[0] for f in files])
+        outs = [np.zeros((f.shape[0], 64), np.float32) for f in files]
+        pout = (fp * n)(*[o.ctypes.data_as(fp) for o in outs])
+        oframes = (C.c_long * n)()
+        mx = (C.c_float * n)()
+        flags = (C.c_int * n)()
+        steps = C.c_long(0)
+        fn.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                       C.POINTER(fp), C.POINTER(C.c_long), C.POINTER(fp), C.POINTER(C.c_long),
+                       C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_long)]
+        rc = fn(str(config_file).encode(), samplerate, channels, 1 if gapless else 0, slots, threads, n,
+                (C.c_int * n)(*cof), pin, frames, pout, oframes, mx, flags, C.byref(steps))
+        if rc < 0:
+            raise RuntimeError(f"fh_run_library failed ({rc})")
+        nout = rc
+        res, k = [], 0
+        for c in chains:
+            row = []
+            for _ in c:
+                row.append(outs[k].reshape(-1)[: oframes[k] * nout].reshape(oframes[k], nout).copy())
+                k += 1
+            res.append(row)
+        return res, list(mx), list(flags), steps.value
+
     def load_config(self, config_file, samplerate, channels):
         """-> dict(rc, created, ninp, nout, size, fragm, npar, pairs={(i,o): (state, impulse)})"""
         h = self.L.fh_config_open(str(config_file).encode(), samplerate, channels)

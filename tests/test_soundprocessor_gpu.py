@@ -193,3 +193,31 @@ def test_config_change_invalidates_pool_and_filter_cache(dirs, tmp_path):
     expect = y0.copy()
     expect[3:] += 0.5 * x[:-3]
     assert np.abs(y1 - expect).max() < 1e-5
+
+
+def test_batch_convolver_equals_per_file_path(dirs):
+    """The batched submit layer (BufferThread replacement) must give every file exactly
+    what the per-file SoundProcessor path gives it, hand-offs and quirks included,
+    with more chains than slots and chains of very different lengths."""
+    P = H.product()
+    d, rate, ch, bits = dirs["crossfeed"]
+    conf = os.path.join(d, f"filter-{rate}.conf")
+    N = _fragm(d, rate, ch)["fragm"]
+    r = np.random.default_rng(77)
+    shapes = [[N + 1, 2 * N + 5, N + N // 3], [2 * N, N + 7], [N + 100, 50, 300], [N + 100, N - 100, 333],
+              [5, 6, 7, 3 * N], [3 * N + 17], [40], [N], [N - 1, 1, 1, N + 2], [2 * N + 9, 0, N]]
+    chains = [[_noise(n, ch, 0.25, int(r.integers(1 << 30))) for n in lens] for lens in shapes]
+    for gapless in (True, False):
+        for slots, threads in ((3, 1), (16, 4)):
+            outs, mx, fl, steps = P.run_library(conf, rate, ch, chains, gapless=gapless, slots=slots, threads=threads)
+            k = 0
+            for ci, files in enumerate(chains):
+                P.drop_pool()
+                want, wmx, wfl = P.run_chain(d, rate, ch, bits, files, gapless=gapless)
+                for fi in range(len(files)):
+                    assert outs[ci][fi].shape == want[fi].shape, (gapless, slots, ci, fi)
+                    assert np.array_equal(outs[ci][fi], want[fi]), (gapless, slots, ci, fi)
+                    assert fl[k] == wfl[fi], (gapless, slots, ci, fi)
+                    if files[fi].shape[0]:
+                        assert mx[k] == pytest.approx(wmx[fi], abs=1e-7), (gapless, slots, ci, fi)
+                    k += 1
