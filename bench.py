@@ -205,11 +205,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(wl_name, streams):
+def ncu_traffic(wl_name, streams, T=1):
     """dram bytes per MAC launch from the committed ncu --set full summary, if one matches."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "mac_traffic.json")))
-        e = d.get(f"{wl_name}:{streams}")
+        e = d.get(f"{wl_name}:{streams}" if T == 1 else f"{wl_name}:{streams}:T{T}")
         return float(e["dram_bytes_per_launch"]) if e else None
     except Exception:
         return None
@@ -224,6 +224,8 @@ def main():
     ap.add_argument("--workload", default="santalucia", choices=sorted(workloads.WORKLOADS))
     ap.add_argument("--streams", type=int, default=1024, help="concurrent streams PER GPU")
     ap.add_argument("--wire", default="f32", choices=["f32", "s16"], help="PCM format of the host buffers")
+    ap.add_argument("--blocks-per-step", type=int, default=1, choices=[1, 2, 4, 8],
+                    help="consecutive blocks of every stream per step (>1: time-tiled MAC)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident loop")
     args = ap.parse_args()
@@ -259,10 +261,10 @@ def main():
 
     wl = workloads.WORKLOADS[args.workload]()
     flt = wl.load(capi.Filter(wl.ninp, wl.nout, wl.size, wl.fragm)).commit(local_rank)
-    B, N, K, W = args.streams, wl.fragm, args.steps, args.warmup
+    B, N, K, W, T = args.streams, wl.fragm, args.steps, args.warmup, args.blocks_per_step
     fmt = capi.PCM_F32 if args.wire == "f32" else capi.PCM_S16
-    batch = capi.Batch(flt, B, fmt, fmt)
-    x = workloads.synthetic_pcm(B, N, wl.ninp, 0.03, 1000 + rank)
+    batch = capi.Batch(flt, B, fmt, fmt, blocks_per_step=T)
+    x = workloads.synthetic_pcm(B, T * N, wl.ninp, 0.03, 1000 + rank)
     batch.host_in[:] = x if fmt == capi.PCM_F32 else np.rint(x * 32768.0).astype(np.int16)
     L = capi.lib()
 
@@ -295,7 +297,7 @@ def main():
     lat = None
     if not args.skip_e2e and rank == 0:
         st = capi.Stream(flt)
-        st.buffer[: N * wl.ninp] = x[0].reshape(-1)
+        st.buffer[: N * wl.ninp] = x[0, :N].reshape(-1)
         m = C.c_float(0)
         ts = []
         for k in range(1100):
@@ -327,17 +329,19 @@ def main():
     clk = clocks.stop()
     barrier()
 
-    audio_per_step = world * B * N / wl.fs
+    audio_per_step = world * B * T * N / wl.fs
     value = audio_per_step * K / (dev_ms * 1e-3)
     e2e_value = None if args.skip_e2e else audio_per_step * K / e2e_s
 
     # roofline of the complex-MAC kernel: SURVEY section 8(d) algorithmic bytes
     P, rows, I, O = flt.ring_depth, flt.active_rows, wl.ninp, wl.nout
-    bytes_mac = 8 * (N + 1) * (B * P * I + rows + B * O)
+    # block-synchronous streaming model: every one of the B*T stream-blocks of a launch
+    # reads its full partition history (a time-tiled launch moves fewer bytes: see traffic)
+    bytes_mac = 8 * (N + 1) * (B * T * P * I + rows + B * T * O)
     mac_ms = kms[1] / max(1, ksteps)
     peak, peak_src = measured_peak()
     achieved = bytes_mac / (mac_ms * 1e-3) / 1e9
-    traffic = ncu_traffic(wl.name, B)
+    traffic = ncu_traffic(wl.name, B, T)
 
     if rank == 0:
         wire_bytes = 4 if fmt == capi.PCM_F32 else 2
@@ -349,19 +353,20 @@ def main():
             "config": {
                 "workload": f"{wl.name}: {wl.ninp}x{wl.nout} fs={wl.fs} size={wl.size} fragm={N} "
                             f"partitions={flt.partitions} (non-zero ring depth {P}, {rows} filter rows)",
-                "streams_per_gpu": B, "blocks_per_step": 1, "frames_per_block": N,
+                "streams_per_gpu": B, "blocks_per_step": T, "frames_per_block": N,
                 "audio_seconds_per_step": audio_per_step, "wire_format": args.wire,
                 "l2": f"per-step working set {(bytes_mac + 0) / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2)",
                 "parallelism": f"{world} x independent stream shards, no collective",
             },
             "e2e": {"value": e2e_value, "unit": "x realtime (audio-s per wall-s)",
-                    "h2d_bytes_per_step": B * N * I * wire_bytes, "d2h_bytes_per_step": B * N * O * wire_bytes,
+                    "h2d_bytes_per_step": B * T * N * I * wire_bytes, "d2h_bytes_per_step": B * T * N * O * wire_bytes,
                     "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "kernel_ms_per_step": {"fwd_fft": kms[0] / max(1, ksteps), "mac": mac_ms,
                                    "inv_fft": kms[2] / max(1, ksteps)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "mac_kernel",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "mac_kernel" if T == 1 else f"mac_tt_kernel<T={T}>",
                          "algorithmic_bytes_per_launch": bytes_mac, "peak_source": peak_src},
             "clocks": clk,
             "block_latency_us": lat,

@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
         "fcv_stream_process": (i, [vp, i, fp]),
         "fcv_stream_filter": (vp, [vp]),
         "fcv_batch_create": (vp, [vp, i, i, i]),
+        "fcv_batch_create_tiled": (vp, [vp, i, i, i, i]),
+        "fcv_batch_blocks_per_step": (i, [vp]),
         "fcv_batch_destroy": (None, [vp]),
         "fcv_batch_nstreams": (i, [vp]),
         "fcv_batch_host_in": (vp, [vp]),
@@ -206,14 +208,15 @@ class Stream:
 
 
 class Batch:
-    def __init__(self, flt: Filter, nstreams: int, in_format=PCM_F32, out_format=PCM_F32):
+    def __init__(self, flt: Filter, nstreams: int, in_format=PCM_F32, out_format=PCM_F32, blocks_per_step=1):
         self.flt = flt
         self.n = nstreams
-        self._h = lib().fcv_batch_create(flt._h, nstreams, in_format, out_format)
+        self.blocks_per_step = blocks_per_step
+        self._h = lib().fcv_batch_create_tiled(flt._h, nstreams, in_format, out_format, blocks_per_step)
         if not self._h:
             raise FcvError(lib().fcv_last_error().decode())
         L = lib()
-        N = flt.fragm
+        N = flt.fragm * blocks_per_step
         din, dout = _PCM_DTYPE[in_format], _PCM_DTYPE[out_format]
         self.in_bytes = L.fcv_batch_host_in_bytes(self._h)
         self.out_bytes = L.fcv_batch_host_out_bytes(self._h)

@@ -65,19 +65,27 @@ static int fail(int code, const char *fmt, ...) {
 template <int LOG2N>
 __global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
-                  int ninp, int P, int pt, int in_fmt, int reset_max) {
+                  int ninp, int R, int T, int pt, int in_fmt, int reset_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     constexpr int N = 1 << LOG2N;
-    const int i = blockIdx.x, b = blockIdx.y;
+    const int i = blockIdx.x, b = blockIdx.y, bt = blockIdx.z;  // input channel, stream, block of the step
     const StreamDev s = st[b];
-    const int frames = fv ? fv[b] : N;
-    float2 *row = s.xring + (size_t)(i * P + pt) * N;
+    int frames = (fv ? fv[b] : T * N) - bt * N;
+    frames = frames < 0 ? 0 : (frames > N ? N : frames);
+    int slot = pt + bt;
+    if (slot >= R) slot -= R;
+    float2 *row = s.xring + (size_t)(i * R + slot) * N;
     // per-block maximum mode: the inverse kernel of this block starts from zero
-    if (reset_max && i == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
-    if (in_fmt == PCM_F32) fwd_body<LOG2N, PCM_F32>(sm, tb, s.din, ninp, i, frames, row);
-    else if (in_fmt == PCM_S16) fwd_body<LOG2N, PCM_S16>(sm, tb, s.din, ninp, i, frames, row);
-    else fwd_body<LOG2N, PCM_S24>(sm, tb, s.din, ninp, i, frames, row);
+    if (reset_max && i == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    if (frames == 0) {  // silence: its spectrum is zero
+        for (int e = threadIdx.x; e < N; e += fft_threads(LOG2N)) row[e] = make_float2(0.f, 0.f);
+        return;
+    }
+    const size_t boff = (size_t)bt * N * ninp;  // samples before this block in the staging area
+    if (in_fmt == PCM_F32) fwd_body<LOG2N, PCM_F32>(sm, tb, (const float *)s.din + boff, ninp, i, frames, row);
+    else if (in_fmt == PCM_S16) fwd_body<LOG2N, PCM_S16>(sm, tb, (const short *)s.din + boff, ninp, i, frames, row);
+    else fwd_body<LOG2N, PCM_S24>(sm, tb, (const int *)s.din + boff, ninp, i, frames, row);
 }
 
 // Forward transform of raw float partitions (filter preparation, K6):
@@ -131,13 +139,14 @@ __device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables 
 
 // Inverse transform of every (stream, output channel) with fused DC/Nyquist
 // products, overlap-add, tail save, re-interleave, float/int conversion and
-// running signed maximum.
+// running signed maximum.  The T blocks of a step are done one after the other
+// by the same CTA (block t+1 overlap-adds the tail block t just saved).
 template <int LOG2N>
 __global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
-                  const float2 *__restrict__ Y, const MacStep *__restrict__ steps,
-                  const int *__restrict__ group_off, const float2 *__restrict__ H, int group_no,
-                  int nout, int P, int pt, int out_fmt) {
+                  const float2 *__restrict__ Y, const TTPair *__restrict__ pairs,
+                  const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
+                  const float2 *__restrict__ H, int nout, int P, int R, int T, int pt, int out_fmt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     __shared__ float red[32];
@@ -146,43 +155,56 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     const int tid = threadIdx.x;
     const int o = blockIdx.x, b = blockIdx.y;
     const StreamDev s = st[b];
-    const int frames = fv ? fv[b] : N;
+    const int fvb = fv ? fv[b] : T * N;
+    float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
+    float lmax = 0.0f;
 
-    // DC and Nyquist are real bins sharing entry 0: redo their products as two
-    // real multiply-accumulates (the MAC kernel treated the entry as complex).
-    float dc = 0.f, ny = 0.f;
-    if (tid < 32) {
-        const int g = o / group_no, oi = o - g * group_no;
-        for (int t = group_off[g] + tid; t < group_off[g + 1]; t += 32) {
-            const int row = steps[t].row[oi];
-            if (row >= 0) {
-                int slot = pt - steps[t].part;
-                if (slot < 0) slot += P;
-                const float2 x = s.xring[(size_t)(steps[t].inp * P + slot) * M];
-                const float2 h = H[(size_t)row * M];
-                dc = fmaf(x.x, h.x, dc);
-                ny = fmaf(x.y, h.y, ny);
+    for (int bt = 0; bt < T; bt++) {
+        int frames = fvb - bt * N;
+        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+        int newest = pt + bt;
+        if (newest >= R) newest -= R;
+        // DC and Nyquist are real bins sharing entry 0: redo their products as two
+        // real multiply-accumulates (the MAC kernel treated the entry as complex).
+        float dc = 0.f, ny = 0.f;
+        if (tid < 32) {
+            for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
+                const int inp = pairs[p].inp;
+                const int *rows = tt_rows + pairs[p].rowbase;
+                for (int j = tid; j < P; j += 32) {
+                    const int row = rows[j];
+                    if (row >= 0) {
+                        int slot = newest - j;
+                        if (slot < 0) slot += R;
+                        const float2 x = s.xring[(size_t)(inp * R + slot) * M];
+                        const float2 h = H[(size_t)row * M];
+                        dc = fmaf(x.x, h.x, dc);
+                        ny = fmaf(x.y, h.y, ny);
+                    }
+                }
             }
         }
-    }
-    inv_load<LOG2N>(sm, tb, Y + ((size_t)b * nout + o) * M);
-    if (tid < 32) {
+        inv_load<LOG2N>(sm, tb, Y + (((size_t)b * nout + o) * T + bt) * M);
+        if (tid < 32) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            dc += __shfl_xor_sync(0xffffffffu, dc, d);
-            ny += __shfl_xor_sync(0xffffffffu, ny, d);
+            for (int d = 16; d > 0; d >>= 1) {
+                dc += __shfl_xor_sync(0xffffffffu, dc, d);
+                ny += __shfl_xor_sync(0xffffffffu, ny, d);
+            }
+            if (tid == 0) sm[0] = make_float2(dc + ny, dc - ny);  // Zc[0] from the two real bins
         }
-        if (tid == 0) sm[0] = make_float2(dc + ny, dc - ny);  // Zc[0] from the two real bins
+        __syncthreads();
+
+        inv_body<LOG2N>(sm, tb);
+
+        const size_t boff = (size_t)bt * N * nout;
+        float m;
+        if (out_fmt == PCM_F32) m = inv_epilogue<LOG2N, PCM_F32>(sm, tb, tail, (float *)s.dout + boff, nout, o, frames);
+        else if (out_fmt == PCM_S16) m = inv_epilogue<LOG2N, PCM_S16>(sm, tb, tail, (short *)s.dout + boff, nout, o, frames);
+        else m = inv_epilogue<LOG2N, PCM_S24>(sm, tb, tail, (int *)s.dout + boff, nout, o, frames);
+        lmax = fmaxf(lmax, m);
+        if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block
     }
-    __syncthreads();
-
-    inv_body<LOG2N>(sm, tb);
-
-    float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
-    float lmax;
-    if (out_fmt == PCM_F32) lmax = inv_epilogue<LOG2N, PCM_F32>(sm, tb, tail, s.dout, nout, o, frames);
-    else if (out_fmt == PCM_S16) lmax = inv_epilogue<LOG2N, PCM_S16>(sm, tb, tail, s.dout, nout, o, frames);
-    else lmax = inv_epilogue<LOG2N, PCM_S24>(sm, tb, tail, s.dout, nout, o, frames);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
     if ((tid & 31) == 0) red[tid >> 5] = lmax;
@@ -358,6 +380,10 @@ struct fcv_filter {
     float2 *dH = nullptr;
     MacStep *dsteps = nullptr;
     int *dgroup_off = nullptr;
+    // per-output pair lists (time-tiled MAC, DC/Nyquist products)
+    TTPair *dpairs = nullptr;
+    int *dpair_off = nullptr;
+    int *dtt_rows = nullptr;
     FftTables tb{};
     std::vector<MacStep> hsteps;
     std::vector<int> hgroup_off;
@@ -452,6 +478,12 @@ static void filter_free_device(fcv_filter *f) {
     if (f->dH) cudaFree(f->dH);
     if (f->dsteps) cudaFree(f->dsteps);
     if (f->dgroup_off) cudaFree(f->dgroup_off);
+    if (f->dpairs) cudaFree(f->dpairs);
+    if (f->dpair_off) cudaFree(f->dpair_off);
+    if (f->dtt_rows) cudaFree(f->dtt_rows);
+    f->dpairs = nullptr;
+    f->dpair_off = nullptr;
+    f->dtt_rows = nullptr;
     f->dH = nullptr;
     f->dsteps = nullptr;
     f->dgroup_off = nullptr;
@@ -523,6 +555,33 @@ extern "C" int fcv_filter_commit(fcv_filter *f, int device) {
         f->hgroup_off.push_back((int)f->hsteps.size());
     }
     f->nsteps = (int)f->hsteps.size();
+
+    // Per-output pair lists: for every output the inputs that feed it and, per
+    // partition j < ring, the filter row (or -1).
+    std::vector<TTPair> hpairs;
+    std::vector<int> hpair_off(1, 0), htt_rows;
+    for (int o = 0; o < f->nout; o++) {
+        for (int i = 0; i < f->ninp; i++) {
+            const Pair &p = f->pairs[(size_t)i * f->nout + o];
+            bool any = false;
+            for (int j = 0; j < f->ring && j < (int)p.row.size(); j++) any |= p.row[j] >= 0;
+            if (!any) continue;
+            TTPair tp;
+            tp.inp = i;
+            tp.rowbase = (int)htt_rows.size();
+            for (int j = 0; j < f->ring; j++) htt_rows.push_back(j < (int)p.row.size() ? p.row[j] : -1);
+            hpairs.push_back(tp);
+        }
+        hpair_off.push_back((int)hpairs.size());
+    }
+    CU_TRY(cudaMalloc(&f->dpairs, (hpairs.size() + 1) * sizeof(TTPair)));
+    CU_TRY(cudaMalloc(&f->dpair_off, hpair_off.size() * sizeof(int)));
+    CU_TRY(cudaMalloc(&f->dtt_rows, (htt_rows.size() + 1) * sizeof(int)));
+    if (!hpairs.empty())
+        CU_TRY(cudaMemcpy(f->dpairs, hpairs.data(), hpairs.size() * sizeof(TTPair), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(f->dpair_off, hpair_off.data(), hpair_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!htt_rows.empty())
+        CU_TRY(cudaMemcpy(f->dtt_rows, htt_rows.data(), htt_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
 
     const size_t M = (size_t)N;
     CU_TRY(cudaMalloc(&f->dH, (size_t)(nrows > 0 ? nrows : 1) * M * sizeof(float2)));
@@ -613,8 +672,10 @@ static size_t pcm_bytes(int fmt) { return fmt == FCV_PCM_S16 ? 2 : 4; }
 struct fcv_batch {
     fcv_filter *f = nullptr;
     int B = 0;
+    int T = 1;   // blocks per stream per step
+    int R = 1;   // ring depth = filter ring + T - 1
     int in_fmt = FCV_PCM_F32, out_fmt = FCV_PCM_F32;
-    size_t in_block = 0, out_block = 0;  // bytes per stream per block
+    size_t in_block = 0, out_block = 0;  // bytes per stream per STEP (T blocks)
     size_t out_pad = 0;                  // extra bytes after device_out (single-stream max mirror)
     unsigned long long step = 0;         // blocks processed so far (ring slot = step % ring)
     bool per_block_max = false;          // single-stream mode: maxv is the maximum of the last block only
@@ -672,9 +733,10 @@ static void batch_free(fcv_batch *b) {
     delete b;
 }
 
-static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_fmt, bool shared_host_buffer) {
+static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_fmt, bool shared_host_buffer, int T) {
     if (!f || !f->committed) { fail(FCV_E_STATE, "filter not committed"); return nullptr; }
     if (nstreams < 1) { fail(FCV_E_PARAM, "nstreams < 1"); return nullptr; }
+    if (T != 1 && T != 2 && T != 4 && T != 8) { fail(FCV_E_PARAM, "blocks per step must be 1, 2, 4 or 8"); return nullptr; }
     if (in_fmt < 0 || in_fmt > FCV_PCM_S24 || out_fmt < 0 || out_fmt > FCV_PCM_S24) {
         fail(FCV_E_PARAM, "bad PCM format");
         return nullptr;
@@ -688,16 +750,18 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     b->in_fmt = in_fmt;
     b->out_fmt = out_fmt;
     const size_t N = (size_t)f->fragm, B = (size_t)nstreams;
-    b->in_block = N * f->ninp * pcm_bytes(in_fmt);
-    b->out_block = N * f->nout * pcm_bytes(out_fmt);
+    b->T = T;
+    b->R = f->ring + T - 1;
+    b->in_block = (size_t)T * N * f->ninp * pcm_bytes(in_fmt);
+    b->out_block = (size_t)T * N * f->nout * pcm_bytes(out_fmt);
     b->out_pad = 256;
     b->per_block_max = shared_host_buffer;
 
-    const size_t xring_b = align_up(B * f->ninp * f->ring * N * sizeof(float2), 256);
+    const size_t xring_b = align_up(B * f->ninp * b->R * N * sizeof(float2), 256);
     const size_t tail_b = align_up(B * f->nout * N * sizeof(float), 256);
     const size_t din_b = align_up(B * b->in_block, 256);
     const size_t dout_b = align_up(B * b->out_block + b->out_pad, 256);
-    const size_t y_b = align_up(B * f->nout * N * sizeof(float2), 256);
+    const size_t y_b = align_up(B * f->nout * T * N * sizeof(float2), 256);
     const size_t max_b = align_up(B * sizeof(float), 256);
     const size_t st_b = align_up(B * sizeof(StreamDev), 256);
     const size_t fv_b = align_up(B * sizeof(int), 256);
@@ -720,12 +784,12 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     p += max_b;
     b->dst = (StreamDev *)p; p += st_b;
     b->dfv = (int *)p; p += fv_b;
-    b->state_bytes_per_stream = (size_t)f->ninp * f->ring * N * sizeof(float2);
+    b->state_bytes_per_stream = (size_t)f->ninp * b->R * N * sizeof(float2);
 
     bool ok = cudaMemset(b->dmem, 0, total) == cudaSuccess;
     std::vector<StreamDev> hs(B);
     for (size_t s = 0; s < B; s++) {
-        hs[s].xring = b->xring + s * f->ninp * f->ring * N;
+        hs[s].xring = b->xring + s * f->ninp * b->R * N;
         hs[s].tail = b->tail + s * f->nout * N;
         hs[s].din = b->din + s * b->in_block;
         hs[s].dout = b->dout + s * b->out_block;
@@ -762,35 +826,62 @@ static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * f->fragm);
     if (TPB == 128)
-        mac_kernel<NO, S, 128><<<grid, 128, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, f->ring, pt, f->nout);
+        mac_kernel<NO, S, 128><<<grid, 128, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout);
     else if (TPB == 64)
-        mac_kernel<NO, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, f->ring, pt, f->nout);
+        mac_kernel<NO, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout);
     else
-        mac_kernel<NO, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, f->ring, pt, f->nout);
+        mac_kernel<NO, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout);
+}
+
+// Time-tiled MAC: T blocks per stream per launch, one output channel per grid.z.
+template <int T>
+static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
+    const fcv_filter *f = b->f;
+    const int M4 = f->fragm / 2;
+    const int TPB = M4 >= 128 ? 128 : M4;
+    constexpr int S = 2;
+    dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->nout);
+    const float4 *H = reinterpret_cast<const float4 *>(f->dH);
+    float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
+    if (TPB == 128)
+        mac_tt_kernel<T, S, 128><<<grid, 128, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
+    else if (TPB == 64)
+        mac_tt_kernel<T, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
+    else
+        mac_tt_kernel<T, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
 }
 
 // The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
 static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaStream_t q, cudaEvent_t *ev) {
     fcv_filter *f = b->f;
-    const int pt = (int)(b->step % (unsigned long long)f->ring);
+    const int T = b->T, R = b->R;
+    // the step's first block goes to ring slot (step * T) mod R
+    const int pt = (int)((b->step * (unsigned long long)T) % (unsigned long long)R);
     const int *fv = fv_base ? fv_base + off : nullptr;
     const FftTables tb = f->tb;
     if (ev) cudaEventRecord(ev[0], q);
-    DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(f->ninp, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
-                                  b->dst + off, fv, tb, f->ninp, f->ring, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
+    DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(f->ninp, cnt, T), fft_threads(L), fft_smem_bytes(L), q>>>(
+                                  b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
     if (ev) cudaEventRecord(ev[1], q);
-    const int S = cnt >= 4 ? 4 : (cnt >= 2 ? 2 : 1);
-    switch (f->group_no) {
-        case 1: if (S == 4) launch_mac<1, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<1, 2>(b, off, cnt, pt, q); else launch_mac<1, 1>(b, off, cnt, pt, q); break;
-        case 2: if (S == 4) launch_mac<2, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<2, 2>(b, off, cnt, pt, q); else launch_mac<2, 1>(b, off, cnt, pt, q); break;
-        case 4: if (S >= 2) launch_mac<4, 2>(b, off, cnt, pt, q); else launch_mac<4, 1>(b, off, cnt, pt, q); break;
-        default: if (S >= 2) launch_mac<8, 2>(b, off, cnt, pt, q); else launch_mac<8, 1>(b, off, cnt, pt, q); break;
+    if (T == 1) {
+        const int S = cnt >= 4 ? 4 : (cnt >= 2 ? 2 : 1);
+        switch (f->group_no) {
+            case 1: if (S == 4) launch_mac<1, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<1, 2>(b, off, cnt, pt, q); else launch_mac<1, 1>(b, off, cnt, pt, q); break;
+            case 2: if (S == 4) launch_mac<2, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<2, 2>(b, off, cnt, pt, q); else launch_mac<2, 1>(b, off, cnt, pt, q); break;
+            case 4: if (S >= 2) launch_mac<4, 2>(b, off, cnt, pt, q); else launch_mac<4, 1>(b, off, cnt, pt, q); break;
+            default: if (S >= 2) launch_mac<8, 2>(b, off, cnt, pt, q); else launch_mac<8, 1>(b, off, cnt, pt, q); break;
+        }
+    } else {
+        const int newest = (pt + T - 1) % R;
+        if (T == 2) launch_mac_tt<2>(b, off, cnt, newest, q);
+        else if (T == 4) launch_mac_tt<4>(b, off, cnt, newest, q);
+        else launch_mac_tt<8>(b, off, cnt, newest, q);
     }
     if (ev) cudaEventRecord(ev[2], q);
-    const float2 *Y = b->Y + (size_t)off * f->nout * f->fragm;
+    const float2 *Y = b->Y + (size_t)off * f->nout * T * f->fragm;
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
-                                  b->dst + off, fv, tb, Y, f->dsteps, f->dgroup_off, f->dH, f->group_no, f->nout,
-                                  f->ring, pt, b->out_fmt)));
+                                  b->dst + off, fv, tb, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout,
+                                  f->ring, R, T, pt, b->out_fmt)));
     if (ev) cudaEventRecord(ev[3], q);
     g_launches += 3;
     cudaError_t e = cudaGetLastError();
@@ -814,8 +905,13 @@ static cudaEvent_t *prof_events(fcv_batch *b) {
 }
 
 extern "C" fcv_batch *fcv_batch_create(fcv_filter *f, int nstreams, int in_format, int out_format) {
-    return batch_create(f, nstreams, in_format, out_format, false);
+    return batch_create(f, nstreams, in_format, out_format, false, 1);
 }
+extern "C" fcv_batch *fcv_batch_create_tiled(fcv_filter *f, int nstreams, int in_format, int out_format,
+                                             int blocks_per_step) {
+    return batch_create(f, nstreams, in_format, out_format, false, blocks_per_step);
+}
+extern "C" int fcv_batch_blocks_per_step(const fcv_batch *b) { return b ? b->T : 0; }
 extern "C" void fcv_batch_destroy(fcv_batch *b) { batch_free(b); }
 extern "C" int fcv_batch_nstreams(const fcv_batch *b) { return b ? b->B : 0; }
 extern "C" void *fcv_batch_host_in(fcv_batch *b) { return b ? b->hin : nullptr; }
@@ -829,7 +925,7 @@ extern "C" void *fcv_batch_cuda_stream(fcv_batch *b) { return b ? (void *)b->q[0
 static int stage_fv(fcv_batch *b, const int *frames_valid, cudaStream_t q) {
     for (int s = 0; s < b->B; s++) {
         const int v = frames_valid[s];
-        if (v < 0 || v > b->f->fragm) return fail(FCV_E_PARAM, "frames_valid[%d] = %d out of range", s, v);
+        if (v < 0 || v > b->T * b->f->fragm) return fail(FCV_E_PARAM, "frames_valid[%d] = %d out of range", s, v);
         b->hfv[s] = v;
     }
     CU_TRY(cudaMemcpyAsync(b->dfv, b->hfv, (size_t)b->B * sizeof(int), cudaMemcpyHostToDevice, q));
@@ -909,7 +1005,7 @@ extern "C" int fcv_batch_submit(fcv_batch *b, int slot, const int *frames_valid)
     if (frames_valid) {
         for (int s = 0; s < b->B; s++) {
             const int v = frames_valid[s];
-            if (v < 0 || v > b->f->fragm) return fail(FCV_E_PARAM, "frames_valid[%d] = %d out of range", s, v);
+            if (v < 0 || v > b->T * b->f->fragm) return fail(FCV_E_PARAM, "frames_valid[%d] = %d out of range", s, v);
             hfv[s] = v;
         }
     }
@@ -959,7 +1055,7 @@ extern "C" int fcv_batch_reset_slot(fcv_batch *b, int slot) {
     // already enqueued and before anything enqueued later
     int rc = fcv_batch_sync(b);
     if (rc) return rc;
-    CU_TRY(cudaMemsetAsync(b->xring + (size_t)slot * f->ninp * f->ring * N, 0, b->state_bytes_per_stream, b->q[0]));
+    CU_TRY(cudaMemsetAsync(b->xring + (size_t)slot * f->ninp * b->R * N, 0, b->state_bytes_per_stream, b->q[0]));
     CU_TRY(cudaMemsetAsync(b->tail + (size_t)slot * f->nout * N, 0, (size_t)f->nout * N * sizeof(float), b->q[0]));
     CU_TRY(cudaMemsetAsync(b->maxv + slot, 0, sizeof(float), b->q[0]));
     CU_TRY(cudaStreamSynchronize(b->q[0]));
@@ -1026,7 +1122,7 @@ struct fcv_stream {
 };
 
 extern "C" fcv_stream *fcv_stream_create(fcv_filter *f) {
-    fcv_batch *b = batch_create(f, 1, FCV_PCM_F32, FCV_PCM_F32, true);
+    fcv_batch *b = batch_create(f, 1, FCV_PCM_F32, FCV_PCM_F32, true, 1);
     if (!b) return nullptr;
     fcv_stream *s = new (std::nothrow) fcv_stream();
     if (!s) { batch_free(b); fail(FCV_E_ALLOC, "out of memory"); return nullptr; }
@@ -1080,9 +1176,9 @@ extern "C" int fcv_stream_get_input_spectrum(fcv_stream *s, int inp, int age, fl
     if (inp < 0 || inp >= f->ninp || age < 0 || age >= f->ring || (unsigned long long)age >= b->step)
         return fail(FCV_E_PARAM, "bad index");
     CU_TRY(cudaSetDevice(f->device));
-    const int slot = (int)((b->step - 1 - age) % (unsigned long long)f->ring);
+    const int slot = (int)((b->step - 1 - age) % (unsigned long long)b->R);  // single streams have T == 1
     std::vector<float2> h((size_t)f->fragm);
-    CU_TRY(cudaMemcpy(h.data(), b->xring + (size_t)(inp * f->ring + slot) * f->fragm, h.size() * sizeof(float2),
+    CU_TRY(cudaMemcpy(h.data(), b->xring + (size_t)(inp * b->R + slot) * f->fragm, h.size() * sizeof(float2),
                       cudaMemcpyDeviceToHost));
     unpermute_row(f->log2n, h.data(), dst);
     return 0;

@@ -123,4 +123,79 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
     }
 }
 
+// ---- time-tiled variant ------------------------------------------------------------
+// When T consecutive blocks of a stream are available at once (prebuffered files),
+// output block t0+t needs ring slots t0+t-j, j < P: the T outputs share all but
+// T-1 of their P input rows.  This kernel walks the window of P+T-1 slots ONCE,
+// newest first, and feeds every loaded X row to all T accumulators; the filter
+// rows slide through a circular register window (one new H row per X row).
+// HBM traffic per block drops from P rows to (P+T-1)/T rows per input.
+//
+//   step d = 0 .. P+T-2 :  X row of block u = t0+T-1-d ;  output t uses H[j = t-(T-1)+d]
+//   H[j] for output t at step d lives in window register (t + d) mod T.
+struct TTPair {
+    int inp;      // input channel feeding this output
+    int rowbase;  // index into tt_rows: P consecutive filter-row numbers (absent -> the zero row)
+};
+
+template <int T, int S, int TPB>
+__global__ void __launch_bounds__(TPB)
+mac_tt_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__restrict__ pairs,
+              const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
+              const float4 *__restrict__ H, float4 *__restrict__ Y, int M4, int P, int R, int newest_slot,
+              int nout) {
+    const int e4 = blockIdx.x * TPB + threadIdx.x;
+    const int b0 = blockIdx.y * S;
+    const int o = blockIdx.z;
+
+    const float4 *xb[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int b = min(b0 + s, nstreams - 1);
+        xb[s] = reinterpret_cast<const float4 *>(st[b].xring) + e4;
+    }
+    float4 acc[T][S];
+#pragma unroll
+    for (int t = 0; t < T; t++)
+#pragma unroll
+        for (int s = 0; s < S; s++) acc[t][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int D = P + T - 1;
+    for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
+        const int inp = __ldg(&pairs[p].inp);
+        const int *rows = tt_rows + __ldg(&pairs[p].rowbase);
+        const size_t xin = (size_t)inp * R;
+        float4 hw[T];
+#pragma unroll
+        for (int t = 0; t < T; t++) hw[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int slot = newest_slot;
+        for (int d0 = 0; d0 < D; d0 += T) {
+#pragma unroll
+            for (int r = 0; r < T; r++) {
+                const int d = d0 + r;
+                if (d < D) {
+                    float4 x[S];
+#pragma unroll
+                    for (int s = 0; s < S; s++) x[s] = ld_stream(xb[s] + (xin + slot) * (size_t)M4);
+                    // the newest output (t = T-1) starts on filter partition j = d
+                    const int row = d < P ? __ldg(&rows[d]) : -1;
+                    hw[(T - 1 + r) % T] = row >= 0 ? ld_keep(H + (size_t)row * (size_t)M4 + e4)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int t = 0; t < T; t++)
+#pragma unroll
+                        for (int s = 0; s < S; s++) cmac2(acc[t][s], x[s], hw[(t + r) % T]);
+                    slot = slot == 0 ? R - 1 : slot - 1;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++)
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (b0 + s < nstreams)
+                __stcs(Y + (((size_t)(b0 + s) * nout + o) * T + t) * (size_t)M4 + e4, acc[t][s]);
+}
+
 }  // namespace fcv

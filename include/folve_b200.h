@@ -146,6 +146,15 @@ fcv_filter *fcv_stream_filter(fcv_stream *s);
 /* Creates `nstreams` fresh streams that share `f` and are advanced together.
  * in_format / out_format: FCV_PCM_*. */
 fcv_batch *fcv_batch_create(fcv_filter *f, int nstreams, int in_format, int out_format);
+/* Same, but every step carries `blocks_per_step` (1, 2, 4 or 8) consecutive
+ * blocks of every stream: staging areas are [nstreams][blocks_per_step*fragm][channels]
+ * and frames_valid counts are in [0, blocks_per_step*fragm].  With more than one
+ * block per step the complex MAC is time-tiled: each input spectrum is read from
+ * HBM once for all the output blocks of the step that need it.  Results are
+ * identical to feeding the blocks one at a time.  Blocks after a stream's
+ * frames_valid are processed as silence (follow a short step by a slot reset). */
+fcv_batch *fcv_batch_create_tiled(fcv_filter *f, int nstreams, int in_format, int out_format, int blocks_per_step);
+int fcv_batch_blocks_per_step(const fcv_batch *b);
 void fcv_batch_destroy(fcv_batch *b);
 int fcv_batch_nstreams(const fcv_batch *b);
 
