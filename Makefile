@@ -3,7 +3,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX  ?= g++
 ARCH  = -gencode arch=compute_100a,code=sm_100a
-NVFLAGS = $(ARCH) -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-Wall -Xptxas -v
+NVFLAGS = $(ARCH) -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-Wall -Xptxas -v $(EXTRA_NVFLAGS)
 CSRC = folve_b200/csrc
 LIB  = folve_b200/libfolve_b200.so
 

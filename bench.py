@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--workload", default="santalucia", choices=sorted(workloads.WORKLOADS))
     ap.add_argument("--streams", type=int, default=1024, help="concurrent streams PER GPU")
     ap.add_argument("--wire", default="f32", choices=["f32", "s16"], help="PCM format of the host buffers")
-    ap.add_argument("--blocks-per-step", type=int, default=1, choices=[1, 2, 4, 8],
+    ap.add_argument("--blocks-per-step", type=int, default=4, choices=[1, 2, 4, 8],
                     help="consecutive blocks of every stream per step (>1: time-tiled MAC)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident loop")

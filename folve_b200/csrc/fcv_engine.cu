@@ -297,7 +297,7 @@ static int get_tables(int device, int log2n, FftTables *out) {
         const int q = log2n - 1, Q = 1 << q, M = 2 * Q;
         const double PI = 3.14159265358979323846264338327950288;
         std::vector<float2> h;
-        size_t offA = 0, offU, offP[3] = {0, 0, 0};
+        size_t offA = 0, offU, offP[4] = {0, 0, 0, 0};
         h.resize(Q);
         for (int n = 0; n < Q; n++) {
             const double a = -2.0 * PI * n / M;
@@ -340,7 +340,7 @@ static int get_tables(int device, int log2n, FftTables *out) {
         tb.part = dpart;
         tb.twA = d + offA;
         tb.twU = d + offU;
-        for (int t = 0; t < 3; t++) tb.twP[t] = d + offP[t];
+        for (int t = 0; t < 4; t++) tb.twP[t] = d + offP[t];
         c->tab[log2n] = tb;
         int rc = 0;
         DISPATCH_LOG2N(log2n, rc = set_attrs<L>());

@@ -33,12 +33,15 @@ namespace fcv {
 // ---- compile-time plan ----------------------------------------------------
 // Q = 2^q is the length of each half transform.  Radix exponents per pass,
 // first pass in the low nibble.
+#ifndef FCV_PLAN12
+#define FCV_PLAN12 0x444  // 4096 = 16*16*16 (256 threads); 0x3333 = 8*8*8*8 (512 threads)
+#endif
 __host__ __device__ constexpr int plan_code(int q) {
-    return q == 12 ? 0x444 : q == 11 ? 0x344 : q == 10 ? 0x334 : q == 9 ? 0x333
+    return q == 12 ? FCV_PLAN12 : q == 11 ? 0x344 : q == 10 ? 0x334 : q == 9 ? 0x333
          : q == 8 ? 0x44 : q == 7 ? 0x34 : q == 6 ? 0x33 : q == 5 ? 0x23 : 0;
 }
 __host__ __device__ constexpr int plan_npass(int q) {
-    return (plan_code(q) >> 8) ? 3 : 2;
+    return (plan_code(q) >> 12) ? 4 : ((plan_code(q) >> 8) ? 3 : 2);
 }
 __host__ __device__ constexpr int plan_lr(int q, int t) { return (plan_code(q) >> (4 * t)) & 0xF; }
 // log2 of the block length pass t works on, and of its butterfly stride
@@ -69,6 +72,7 @@ __host__ __device__ constexpr int plan_revinv(int q, int pos) {
 }
 __host__ __device__ constexpr int fft_threads(int log2n) {
     const int n = 1 << log2n;
+    if (log2n == 13 && plan_npass(12) == 4) return 512;  // radix-8 plan: one more pass, twice the warps
     return (n / 32) > 256 ? 256 : ((n / 32) < 32 ? 32 : (n / 32));
 }
 __host__ __device__ constexpr int smem_pad(int e) { return e + (e >> 4); }
@@ -80,7 +84,7 @@ __host__ __device__ constexpr size_t fft_smem_bytes(int log2n) {
 struct FftTables {
     const float2 *twA;     // [Q]   w_M^n = exp(-2 pi i n / M)
     const float2 *twU;     // [M]   exp(-i pi k / M) for the bin stored at entry e
-    const float2 *twP[3];  // per pass t with stride S_t > 1: [(k1-1)*S_t + u] = exp(-2 pi i u k1 / Q_t)
+    const float2 *twP[4];  // per pass t with stride S_t > 1: [(k1-1)*S_t + u] = exp(-2 pi i u k1 / Q_t)
     const unsigned short *part;  // [M] entry holding the conjugate-partner bin (M - k) of entry e
 };
 
@@ -181,24 +185,37 @@ template <> struct Bfly<16> {
 };
 
 // ---- passes over both half transforms ----------------------------------------
+// When the butterfly stride S divides the thread count, every butterfly a thread
+// handles in a pass has the same u = b mod S, i.e. the same R-1 twiddles: they are
+// loaded once per pass (TW_INVARIANT), otherwise once per butterfly.
 template <int Q_LOG2, int T, int NT>
 __device__ __forceinline__ void fwd_pass(float2 *sm, const float2 *__restrict__ tw, int tid) {
     constexpr int LR = plan_lr(Q_LOG2, T), R = 1 << LR;
     constexpr int LS = plan_ls(Q_LOG2, T), S = 1 << LS;
     constexpr int LQT = plan_lqt(Q_LOG2, T);
     constexpr int NB = (2 << Q_LOG2) >> LR;
+    constexpr bool TW_INVARIANT = S > 1 && (NT % S) == 0;
+    float2 w[R];
+    if (TW_INVARIANT) {
+#pragma unroll
+        for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + (tid & (S - 1))]);
+    }
     for (int b = tid; b < NB; b += NT) {
         const int u = b & (S - 1);
         const int base = ((b >> LS) << LQT) + u;
         float2 v[R];
 #pragma unroll
         for (int j = 0; j < R; j++) v[j] = sm[smem_pad(base + (j << LS))];
+        if (S > 1 && !TW_INVARIANT) {
+#pragma unroll
+            for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
+        }
         Bfly<R>::template run<-1>(v);
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int k1 = Bfly<R>::out(r);
             float2 x = v[r];
-            if (S > 1 && k1 > 0) x = cmul(x, __ldg(&tw[(k1 - 1) * S + u]));
+            if (S > 1 && k1 > 0) x = cmul(x, w[k1]);
             sm[smem_pad(base + (k1 << LS))] = x;
         }
     }
@@ -211,14 +228,24 @@ __device__ __forceinline__ void inv_pass(float2 *sm, const float2 *__restrict__ 
     constexpr int LS = plan_ls(Q_LOG2, T), S = 1 << LS;
     constexpr int LQT = plan_lqt(Q_LOG2, T);
     constexpr int NB = (2 << Q_LOG2) >> LR;
+    constexpr bool TW_INVARIANT = S > 1 && (NT % S) == 0;
+    float2 w[R];
+    if (TW_INVARIANT) {
+#pragma unroll
+        for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + (tid & (S - 1))]);
+    }
     for (int b = tid; b < NB; b += NT) {
         const int u = b & (S - 1);
         const int base = ((b >> LS) << LQT) + u;
         float2 v[R];
+        if (S > 1 && !TW_INVARIANT) {
+#pragma unroll
+            for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
+        }
 #pragma unroll
         for (int k1 = 0; k1 < R; k1++) {
             float2 x = sm[smem_pad(base + (k1 << LS))];
-            if (S > 1 && k1 > 0) x = cmulconj(x, __ldg(&tw[(k1 - 1) * S + u]));
+            if (S > 1 && k1 > 0) x = cmulconj(x, w[k1]);
             v[k1] = x;
         }
         Bfly<R>::template run<+1>(v);
@@ -232,11 +259,13 @@ template <int Q_LOG2, int NT>
 __device__ __forceinline__ void fwd_passes(float2 *sm, const FftTables &tb, int tid) {
     fwd_pass<Q_LOG2, 0, NT>(sm, tb.twP[0], tid);
     fwd_pass<Q_LOG2, 1, NT>(sm, tb.twP[1], tid);
-    if constexpr (plan_npass(Q_LOG2) == 3) fwd_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 3) fwd_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 4) fwd_pass<Q_LOG2, 3, NT>(sm, tb.twP[3], tid);
 }
 template <int Q_LOG2, int NT>
 __device__ __forceinline__ void inv_passes(float2 *sm, const FftTables &tb, int tid) {
-    if constexpr (plan_npass(Q_LOG2) == 3) inv_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 4) inv_pass<Q_LOG2, 3, NT>(sm, tb.twP[3], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 3) inv_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
     inv_pass<Q_LOG2, 1, NT>(sm, tb.twP[1], tid);
     inv_pass<Q_LOG2, 0, NT>(sm, tb.twP[0], tid);
 }
@@ -251,6 +280,26 @@ __device__ __forceinline__ int partner_entry(int e, int &kp_out, int &kpp_out) {
     kp_out = kp;
     kpp_out = kpp;
     return (half << Q_LOG2) + plan_rev(Q_LOG2, kpp);
+}
+
+// Entry holding the conjugate partner (bin M - k) of the bin stored at entry e,
+// computed in position space: half 1 is a mirror (k'' = Q-1-k' complements every
+// digit); half 0 negates k' digit by digit with the carry running from the
+// lowest bin digit (the highest position digit) upwards.
+template <int Q_LOG2>
+__device__ __forceinline__ int partner_of(int e) {
+    constexpr int Q = 1 << Q_LOG2;
+    const int pos = e & (Q - 1);
+    if (e >> Q_LOG2) return Q + (Q - 1 - pos);
+    int carry = 1, pos2 = 0;
+#pragma unroll
+    for (int t = 0; t < plan_npass(Q_LOG2); t++) {
+        const int lr = plan_lr(Q_LOG2, t), ls = plan_ls(Q_LOG2, t), mask = (1 << lr) - 1;
+        int nd = (mask - ((pos >> ls) & mask)) + carry;
+        carry = nd >> lr;
+        pos2 |= (nd & mask) << ls;
+    }
+    return pos2;
 }
 
 // ---- PCM wire formats ---------------------------------------------------------
@@ -394,16 +443,13 @@ __device__ __forceinline__ void inv_load(float2 *sm, const FftTables &tb, const 
 #pragma unroll 1
     for (int c = 0; c < M / NT; c += CH) {
         float2 y[CH], yp[CH], w[CH];
-        int e2[CH];
-#pragma unroll
-        for (int i = 0; i < CH; i++) e2[i] = __ldg(&tb.part[tid + (c + i) * NT]);
 #pragma unroll
         for (int i = 0; i < CH; i++) {
-            y[i] = __ldg(&yrow[tid + (c + i) * NT]);
-            w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
+            const int e = tid + (c + i) * NT;
+            y[i] = __ldg(&yrow[e]);
+            yp[i] = __ldg(&yrow[partner_of<LOG2N - 1>(e)]);
+            w[i] = __ldg(&tb.twU[e]);
         }
-#pragma unroll
-        for (int i = 0; i < CH; i++) yp[i] = __ldg(&yrow[e2[i]]);
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             const int e = tid + (c + i) * NT;

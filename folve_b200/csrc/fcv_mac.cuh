@@ -138,6 +138,14 @@ struct TTPair {
     int rowbase;  // index into tt_rows: P consecutive filter-row numbers (absent -> the zero row)
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+#ifndef FCV_TT_PREFETCH
+#define FCV_TT_PREFETCH 6  // X rows requested into L2 this many steps ahead of their use
+#endif
+
 template <int T, int S, int TPB>
 __global__ void __launch_bounds__(TPB)
 mac_tt_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__restrict__ pairs,
@@ -168,7 +176,27 @@ mac_tt_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__re
         float4 hw[T];
 #pragma unroll
         for (int t = 0; t < T; t++) hw[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // software pipeline, one step deep: the X rows and the filter row of step
+        // d+1 are requested before the multiply-accumulates of step d
         int slot = newest_slot;
+        // L2 prefetch runs FCV_TT_PREFETCH rows ahead of the register pipeline, so that
+        // the loads below mostly hit L2 and few bytes need to be in flight per thread
+        int pslot = newest_slot;
+#pragma unroll
+        for (int k = 0; k < FCV_TT_PREFETCH; k++) {
+            if (k > 0 && k < D) {
+#pragma unroll
+                for (int s = 0; s < S; s++) prefetch_l2(xb[s] + (xin + pslot) * (size_t)M4);
+            }
+            pslot = pslot == 0 ? R - 1 : pslot - 1;
+        }
+        float4 xn[S], hn;
+#pragma unroll
+        for (int s = 0; s < S; s++) xn[s] = ld_stream(xb[s] + (xin + slot) * (size_t)M4);
+        {
+            const int row = __ldg(&rows[0]);
+            hn = row >= 0 ? ld_keep(H + (size_t)row * (size_t)M4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int d0 = 0; d0 < D; d0 += T) {
 #pragma unroll
             for (int r = 0; r < T; r++) {
@@ -176,16 +204,24 @@ mac_tt_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__re
                 if (d < D) {
                     float4 x[S];
 #pragma unroll
-                    for (int s = 0; s < S; s++) x[s] = ld_stream(xb[s] + (xin + slot) * (size_t)M4);
-                    // the newest output (t = T-1) starts on filter partition j = d
-                    const int row = d < P ? __ldg(&rows[d]) : -1;
-                    hw[(T - 1 + r) % T] = row >= 0 ? ld_keep(H + (size_t)row * (size_t)M4 + e4)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int s = 0; s < S; s++) x[s] = xn[s];
+                    hw[(T - 1 + r) % T] = hn;  // the newest output (t = T-1) starts on partition j = d
+                    slot = slot == 0 ? R - 1 : slot - 1;
+                    if (d + FCV_TT_PREFETCH < D) {
+#pragma unroll
+                        for (int s = 0; s < S; s++) prefetch_l2(xb[s] + (xin + pslot) * (size_t)M4);
+                    }
+                    pslot = pslot == 0 ? R - 1 : pslot - 1;
+                    if (d + 1 < D) {
+#pragma unroll
+                        for (int s = 0; s < S; s++) xn[s] = ld_stream(xb[s] + (xin + slot) * (size_t)M4);
+                        const int row = d + 1 < P ? __ldg(&rows[d + 1]) : -1;
+                        hn = row >= 0 ? ld_keep(H + (size_t)row * (size_t)M4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
                     for (int t = 0; t < T; t++)
 #pragma unroll
                         for (int s = 0; s < S; s++) cmac2(acc[t][s], x[s], hw[(t + r) % T]);
-                    slot = slot == 0 ? R - 1 : slot - 1;
                 }
             }
         }
