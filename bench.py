@@ -367,7 +367,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "mac_kernel" if T == 1 else f"mac_tt_kernel<T={T}>",
-                         "algorithmic_bytes_per_launch": bytes_mac, "peak_source": peak_src},
+                         "algorithmic_bytes_per_launch": bytes_mac, "peak_source": peak_src,
+                         # what the kernel really moved (ncu dram bytes) over the same measured time:
+                         # for a time-tiled launch this, not `frac`, is the fraction of the HBM peak in use
+                         "traffic_gbs": (traffic / (mac_ms * 1e-3) / 1e9) if traffic else None,
+                         "traffic_frac_of_peak": (traffic / (mac_ms * 1e-3) / 1e9 / peak) if traffic else None},
             "clocks": clk,
             "block_latency_us": lat,
         }

@@ -43,7 +43,10 @@ def to_bytes(v, unit):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     # ---- launch list
-    rows = [r for r in csv.reader(open(os.path.join(G, f"{tag}_launches.csv"))) if len(r) > 10 and r[0].isdigit()]
+    src = os.path.join(G, f"{tag}_launches.csv")
+    if not os.path.exists(src):
+        src = os.path.join(P, f"{tag}_launches.csv")
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
     agg = collections.OrderedDict()
     for r in rows:
         key = (r[4].split("(")[0].replace("void ", ""), r[8])
@@ -51,7 +54,8 @@ def main():
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`)\n\n"
-                "Command: `python bench.py --steps 20 --warmup 3 --no-cpu-baseline --skip-e2e` (santalucia, 1024 streams).\n"
+                "Command: `python bench.py --steps 20 --warmup 3 --no-cpu-baseline --skip-e2e` (santalucia, 1024 streams;\n"
+                "r01: `--blocks-per-step 1`, r01tt: 4 blocks per step).\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's\n"
                 "`kernel_ms_per_step`, not absolutes.\n\n| kernel | grid | launches | mean us | share of listed time |\n|---|---|---|---|---|\n")
         for (k, grid), v in agg.items():
@@ -61,7 +65,8 @@ def main():
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     with open(os.path.join(P, f"{tag}_kernels.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` captures\n")
-        for rep in (f"{tag}_mac.ncu-rep", f"{tag}_fft.ncu-rep"):
+        keys = dict(a.split("=", 1) for a in sys.argv[2:] if "=" in a)   # e.g. r01_mactt4.ncu-rep=santalucia:1024:T4
+        for rep in [f"{tag}_mac.ncu-rep", f"{tag}_fft.ncu-rep"] + [k for k in keys if k not in (f"{tag}_mac.ncu-rep",)]:
             path = os.path.join(G, rep)
             if not os.path.exists(path):
                 continue
@@ -72,12 +77,12 @@ def main():
                 for w in WANT:
                     if w in hdr:
                         f.write(f"| {w} | {r[hdr.index(w)]} | {units[hdr.index(w)]} |\n")
-                if name.startswith("mac_kernel"):
+                if name.startswith("mac_"):
                     i, j = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
                     b = to_bytes(r[i], units[i]) + to_bytes(r[j], units[j])
                     grid = int(r[hdr.index("launch__grid_size")].replace(",", ""))
                     streams = grid // 32 * 4  # grid = 32 bin tiles x ceil(streams/4) for fragm 8192
-                    traffic[f"santalucia:{streams}"] = {
+                    traffic[keys.get(rep, f"santalucia:{streams}")] = {
                         "dram_bytes_per_launch": b, "source": f"profiles/{tag}_kernels.md ({rep})",
                         "duration_us_under_ncu": float(r[hdr.index('gpu__time_duration.sum')].replace(',', ''))}
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
