@@ -700,6 +700,7 @@ struct fcv_batch {
     // streams
     static const int NQ = 4;
     cudaStream_t q[NQ] = {};
+    cudaEvent_t fj[5] = {};  // fork/join events of the chunked device path
     // stopwatch
     cudaEvent_t sw[16] = {};
     // profiling
@@ -716,6 +717,7 @@ static void batch_free(fcv_batch *b) {
     if (b->f && b->f->device >= 0) cudaSetDevice(b->f->device);
     for (auto e : b->ev) cudaEventDestroy(e);
     for (int i = 0; i < 16; i++) if (b->sw[i]) cudaEventDestroy(b->sw[i]);
+    for (int i = 0; i < 5; i++) if (b->fj[i]) cudaEventDestroy(b->fj[i]);
     for (int i = 0; i < fcv_batch::NQ; i++)
         if (b->q[i]) { cudaStreamSynchronize(b->q[i]); cudaStreamDestroy(b->q[i]); }
     if (b->dmem) cudaFree(b->dmem);
@@ -941,8 +943,32 @@ extern "C" int fcv_batch_process_device(fcv_batch *b, const int *frames_valid) {
         int rc = stage_fv(b, frames_valid, b->q[0]);
         if (rc) return rc;
     }
-    int rc = run_kernels(b, 0, b->B, frames_valid ? b->dfv : nullptr, b->q[0], prof_events(b));
-    if (rc) return rc;
+    // Optional fork/join over the batch's CUDA streams: the FFT kernels (issue and
+    // shared-memory bound) of one part of the batch can then overlap the MAC kernel
+    // (HBM bound) of another.  q[0] stays the stream everything is ordered on.
+    static const int env_chunks = getenv("FCV_DEVICE_CHUNKS") ? atoi(getenv("FCV_DEVICE_CHUNKS")) : 0;
+    int nchunk = (b->profiling || env_chunks < 2) ? 1 : env_chunks;
+    if (nchunk > b->B / 8) nchunk = b->B / 8 > 0 ? b->B / 8 : 1;
+    if (nchunk == 1) {
+        int rc = run_kernels(b, 0, b->B, frames_valid ? b->dfv : nullptr, b->q[0], prof_events(b));
+        if (rc) return rc;
+        b->step++;
+        return 0;
+    }
+    for (int i = 0; i < fcv_batch::NQ + 1; i++)
+        if (!b->fj[i]) CU_TRY(cudaEventCreateWithFlags(&b->fj[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(b->fj[fcv_batch::NQ], b->q[0]));
+    for (int i = 1; i < fcv_batch::NQ; i++) CU_TRY(cudaStreamWaitEvent(b->q[i], b->fj[fcv_batch::NQ], 0));
+    const int per = ((b->B + nchunk - 1) / nchunk + 1) & ~1;
+    for (int c = 0, off = 0; off < b->B; c++, off += per) {
+        const int cnt = (b->B - off) < per ? (b->B - off) : per;
+        int rc = run_kernels(b, off, cnt, frames_valid ? b->dfv : nullptr, b->q[c % fcv_batch::NQ], nullptr);
+        if (rc) return rc;
+    }
+    for (int i = 1; i < fcv_batch::NQ; i++) {
+        CU_TRY(cudaEventRecord(b->fj[i], b->q[i]));
+        CU_TRY(cudaStreamWaitEvent(b->q[0], b->fj[i], 0));
+    }
     b->step++;
     return 0;
 }
