@@ -836,12 +836,11 @@ static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_
 }
 
 // Time-tiled MAC: T blocks per stream per launch, one output channel per grid.z.
-template <int T>
-static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
+template <int T, int S>
+static void launch_mac_tt_s(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
     const fcv_filter *f = b->f;
     const int M4 = f->fragm / 2;
     const int TPB = M4 >= 128 ? 128 : M4;
-    constexpr int S = 2;
     dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->nout);
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
@@ -851,6 +850,19 @@ static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cuda
         mac_tt_kernel<T, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
     else
         mac_tt_kernel<T, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
+}
+
+template <int T>
+static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
+    // Streams per thread, sharing each filter value from registers.  Measured on B200
+    // (SantaLucia, 1024 streams): T=4: S=4 0.150 ms/block (HBM floor 0.148), S=2 0.166;
+    // T=8: S=2 0.134, S=4 0.143 (228 registers).  FCV_TT_S overrides for experiments.
+    static const int env_s = getenv("FCV_TT_S") ? atoi(getenv("FCV_TT_S")) : 0;
+    int S = env_s ? env_s : (T >= 8 ? 2 : 4);
+    if (cnt < S) S = cnt >= 2 ? 2 : 1;
+    if (S >= 4) launch_mac_tt_s<T, 4>(b, off, cnt, newest, q);
+    else if (S >= 2) launch_mac_tt_s<T, 2>(b, off, cnt, newest, q);
+    else launch_mac_tt_s<T, 1>(b, off, cnt, newest, q);
 }
 
 // The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
