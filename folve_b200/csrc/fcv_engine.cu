@@ -30,6 +30,9 @@ using namespace fcv;
 #ifndef FFT_MIN_CTAS
 #define FFT_MIN_CTAS 2
 #endif
+#ifndef FWD_MIN_CTAS
+#define FWD_MIN_CTAS 4
+#endif
 
 // ---------------------------------------------------------------------------
 // errors
@@ -63,29 +66,40 @@ static int fail(int code, const char *fmt, ...) {
 // fused int/float conversion + de-interleave + zero padding + real FFT, written
 // into ring slot `pt` of the stream's input-spectra ring.
 template <int LOG2N>
-__global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
+__global__ void __launch_bounds__(fft_threads(LOG2N, 1), FWD_MIN_CTAS)
 fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
-                  int ninp, int R, int T, int pt, int in_fmt, int reset_max) {
+                  int ninp, int R, int T, int pt, int in_fmt, int reset_max, int ahead) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
-    constexpr int N = 1 << LOG2N;
-    const int i = blockIdx.x, b = blockIdx.y, bt = blockIdx.z;  // input channel, stream, block of the step
+    constexpr int N = 1 << LOG2N, NT = fft_threads(LOG2N, 1);
+    // grid: x = 2 * input channel + half, y = stream, z = block of the step
+    const int i = blockIdx.x >> 1, h = blockIdx.x & 1, b = blockIdx.y, bt = blockIdx.z;
     const StreamDev s = st[b];
+    // optional L2 prefetch of the PCM block of the CTA `ahead` places behind in launch order
+    if (ahead > 0 && blockIdx.x == 0) {
+        const long long la = (long long)b + (long long)gridDim.y * bt + ahead / (2 * ninp);
+        if (la < (long long)gridDim.y * gridDim.z) {
+            const int b2 = (int)(la % gridDim.y), bt2 = (int)(la / gridDim.y);
+            const size_t blk = (size_t)N * ninp * (in_fmt == PCM_S16 ? 2 : 4);
+            const char *src = reinterpret_cast<const char *>(st[b2].din) + (size_t)bt2 * blk;
+            for (size_t off = (size_t)threadIdx.x * 128; off < blk; off += (size_t)NT * 128) prefetch_l2(src + off);
+        }
+    }
     int frames = (fv ? fv[b] : T * N) - bt * N;
     frames = frames < 0 ? 0 : (frames > N ? N : frames);
     int slot = pt + bt;
     if (slot >= R) slot -= R;
     float2 *row = s.xring + (size_t)(i * R + slot) * N;
     // per-block maximum mode: the inverse kernel of this block starts from zero
-    if (reset_max && i == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    if (reset_max && blockIdx.x == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
     if (frames == 0) {  // silence: its spectrum is zero
-        for (int e = threadIdx.x; e < N; e += fft_threads(LOG2N)) row[e] = make_float2(0.f, 0.f);
+        for (int e = threadIdx.x; e < N / 2; e += NT) row[h * (N / 2) + e] = make_float2(0.f, 0.f);
         return;
     }
     const size_t boff = (size_t)bt * N * ninp;  // samples before this block in the staging area
-    if (in_fmt == PCM_F32) fwd_body<LOG2N, PCM_F32>(sm, tb, (const float *)s.din + boff, ninp, i, frames, row);
-    else if (in_fmt == PCM_S16) fwd_body<LOG2N, PCM_S16>(sm, tb, (const short *)s.din + boff, ninp, i, frames, row);
-    else fwd_body<LOG2N, PCM_S24>(sm, tb, (const int *)s.din + boff, ninp, i, frames, row);
+    if (in_fmt == PCM_F32) fwd_body<LOG2N, PCM_F32, 1>(sm, tb, (const float *)s.din + boff, ninp, i, frames, row, h);
+    else if (in_fmt == PCM_S16) fwd_body<LOG2N, PCM_S16, 1>(sm, tb, (const short *)s.din + boff, ninp, i, frames, row, h);
+    else fwd_body<LOG2N, PCM_S24, 1>(sm, tb, (const int *)s.din + boff, ninp, i, frames, row, h);
 }
 
 // Forward transform of raw float partitions (filter preparation, K6):
@@ -97,7 +111,7 @@ fwd_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, FftTable
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     constexpr int N = 1 << LOG2N;
     const size_t r = blockIdx.x;
-    fwd_body<LOG2N, PCM_F32>(sm, tb, src + r * N, 1, 0, N, dst + r * N);
+    fwd_body<LOG2N, PCM_F32, 2>(sm, tb, src + r * N, 1, 0, N, dst + r * N);
 }
 
 // Overlap-add, tail save, re-interleave, float/int conversion and signed maximum
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
                   const float2 *__restrict__ Y, const TTPair *__restrict__ pairs,
                   const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
-                  const float2 *__restrict__ H, int nout, int P, int R, int T, int pt, int out_fmt) {
+                  const float2 *__restrict__ H, int nout, int P, int R, int T, int pt, int out_fmt, int ahead) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     __shared__ float red[32];
@@ -159,7 +173,24 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
     float lmax = 0.0f;
 
+    // L2 prefetch (see fwd_stream_kernel): first spectrum and overlap tail of the CTA
+    // `ahead` places behind this one; this CTA's own next spectrum at each block.
+    if (ahead > 0) {
+        const long long la = (long long)o + (long long)nout * b + ahead;
+        if (la < (long long)nout * gridDim.y) {
+            const int o2 = (int)(la % nout), b2 = (int)(la / nout);
+            const char *y2 = reinterpret_cast<const char *>(Y + (((size_t)b2 * nout + o2) * T) * M);
+            for (size_t off = (size_t)tid * 128; off < (size_t)M * 8; off += (size_t)NT * 128) prefetch_l2(y2 + off);
+            const char *t2 = reinterpret_cast<const char *>(st[b2].tail + (size_t)o2 * N);
+            for (size_t off = (size_t)tid * 128; off < (size_t)N * 4; off += (size_t)NT * 128) prefetch_l2(t2 + off);
+        }
+    }
+
     for (int bt = 0; bt < T; bt++) {
+        if (ahead > 0 && bt + 1 < T) {
+            const char *y2 = reinterpret_cast<const char *>(Y + (((size_t)b * nout + o) * T + bt + 1) * M);
+            for (size_t off = (size_t)tid * 128; off < (size_t)M * 8; off += (size_t)NT * 128) prefetch_l2(y2 + off);
+        }
         int frames = fvb - bt * N;
         frames = frames < 0 ? 0 : (frames > N ? N : frames);
         int newest = pt + bt;
@@ -270,7 +301,8 @@ static int check_device(int device) {
 template <int LOG2N>
 static int set_attrs() {
     const int bytes = (int)fft_smem_bytes(LOG2N);
-    CU_TRY(cudaFuncSetAttribute(fwd_stream_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CU_TRY(cudaFuncSetAttribute(fwd_stream_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fft_smem_bytes(LOG2N, 1)));
     CU_TRY(cudaFuncSetAttribute(fwd_raw_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CU_TRY(cudaFuncSetAttribute(inv_stream_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return 0;
@@ -844,12 +876,16 @@ static void launch_mac_tt_s(const fcv_batch *b, int off, int cnt, int newest, cu
     dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->nout);
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
-    if (TPB == 128)
-        mac_tt_kernel<T, S, 128><<<grid, 128, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
-    else if (TPB == 64)
-        mac_tt_kernel<T, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
+    static const bool v1 = getenv("FCV_MAC_V2") == nullptr;  // FCV_MAC_V2=1: experimental pointer-walking variant
+#define FCV_TT_ARGS b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout
+    if (TPB == 128) {
+        if (v1) mac_tt_kernel<T, S, 128><<<grid, 128, 0, q>>>(FCV_TT_ARGS);
+        else mac_tt2_kernel<T, S, 128><<<grid, 128, 0, q>>>(FCV_TT_ARGS);
+    } else if (TPB == 64)
+        mac_tt2_kernel<T, S, 64><<<grid, 64, 0, q>>>(FCV_TT_ARGS);
     else
-        mac_tt_kernel<T, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout);
+        mac_tt2_kernel<T, S, 32><<<grid, 32, 0, q>>>(FCV_TT_ARGS);
+#undef FCV_TT_ARGS
 }
 
 template <int T>
@@ -865,6 +901,13 @@ static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cuda
     else launch_mac_tt_s<T, 1>(b, off, cnt, newest, q);
 }
 
+// How many CTAs ahead (in launch order) the FFT kernels prefetch into L2: about the number
+// of CTAs resident on the device at once (2 per SM).  FCV_FFT_AHEAD overrides; 0 disables.
+static int fft_ahead() {
+    static const int v = getenv("FCV_FFT_AHEAD") ? atoi(getenv("FCV_FFT_AHEAD")) : 296;
+    return v;
+}
+
 // The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
 static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaStream_t q, cudaEvent_t *ev) {
     fcv_filter *f = b->f;
@@ -873,11 +916,15 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     const int pt = (int)((b->step * (unsigned long long)T) % (unsigned long long)R);
     const int *fv = fv_base ? fv_base + off : nullptr;
     const FftTables tb = f->tb;
+    // diagnostic: FCV_ONLY=1|2|4 (bit mask fwd|mac|inv) launches only those kernels
+    static const int only = getenv("FCV_ONLY") ? atoi(getenv("FCV_ONLY")) : 7;
     if (ev) cudaEventRecord(ev[0], q);
-    DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(f->ninp, cnt, T), fft_threads(L), fft_smem_bytes(L), q>>>(
-                                  b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
+    if (only & 1)
+    DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(2 * f->ninp, cnt, T), fft_threads(L, 1), fft_smem_bytes(L, 1), q>>>(
+                                  b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0, fft_ahead())));
     if (ev) cudaEventRecord(ev[1], q);
-    if (T == 1) {
+    if (!(only & 2)) {
+    } else if (T == 1) {
         const int S = cnt >= 4 ? 4 : (cnt >= 2 ? 2 : 1);
         switch (f->group_no) {
             case 1: if (S == 4) launch_mac<1, 4>(b, off, cnt, pt, q); else if (S == 2) launch_mac<1, 2>(b, off, cnt, pt, q); else launch_mac<1, 1>(b, off, cnt, pt, q); break;
@@ -893,9 +940,10 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     }
     if (ev) cudaEventRecord(ev[2], q);
     const float2 *Y = b->Y + (size_t)off * f->nout * T * f->fragm;
+    if (only & 4)
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
                                   b->dst + off, fv, tb, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout,
-                                  f->ring, R, T, pt, b->out_fmt)));
+                                  f->ring, R, T, pt, b->out_fmt, fft_ahead())));
     if (ev) cudaEventRecord(ev[3], q);
     g_launches += 3;
     cudaError_t e = cudaGetLastError();

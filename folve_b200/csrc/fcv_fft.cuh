@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fcv_c2.cuh"
+
 namespace fcv {
 
 // ---- compile-time plan ----------------------------------------------------
@@ -70,14 +72,19 @@ __host__ __device__ constexpr int plan_revinv(int q, int pos) {
     }
     return k;
 }
-__host__ __device__ constexpr int fft_threads(int log2n) {
-    const int n = 1 << log2n;
-    if (log2n == 13 && plan_npass(12) == 4) return 512;  // radix-8 plan: one more pass, twice the warps
+// NH = number of half transforms one CTA works on: 2 = the whole spectrum, 1 = one half
+// (the halves are independent from the zero-padded load up to and including the unpack
+// of the forward transform, so the forward kernels run one half per CTA: half the
+// threads and shared memory per CTA, twice as many CTAs per SM, and their load, compute
+// and store phases overlap instead of alternating).
+__host__ __device__ constexpr int fft_threads(int log2n, int nh = 2) {
+    const int n = (1 << log2n) * nh / 2;
+    if (log2n == 13 && plan_npass(12) == 4) return 256 * nh;  // radix-8 plan: one more pass, twice the warps
     return (n / 32) > 256 ? 256 : ((n / 32) < 32 ? 32 : (n / 32));
 }
 __host__ __device__ constexpr int smem_pad(int e) { return e + (e >> 4); }
-__host__ __device__ constexpr size_t fft_smem_bytes(int log2n) {
-    return (size_t)smem_pad(1 << log2n) * sizeof(float2) + 64;
+__host__ __device__ constexpr size_t fft_smem_bytes(int log2n, int nh = 2) {
+    return (size_t)smem_pad((1 << log2n) * nh / 2) * sizeof(float2) + 64;
 }
 
 // Twiddle tables for one partition size, resident in device memory.
@@ -113,29 +120,39 @@ __device__ __forceinline__ float2 mul_w(float2 a, float c, float s) {
 // run<DIR>(v): v <- DFT_R(v) with kernel exp(DIR * 2 pi i j k / R).
 // The result for bin k is left in register out(r) == k, i.e. register r holds
 // bin out(r).
+// All complex values are packed pairs (fcv_c2.cuh): a complex add/sub is ONE FADD2,
+// multiplications by +-i fold into the operand modifiers of the add that consumes
+// them, a twiddle multiplication is FMUL2 + FFMA2.
 template <int R> struct Bfly;
+
+// a * (DIR * i)
+template <int DIR>
+__device__ __forceinline__ c2 c2_mul_i(c2 a) { return DIR < 0 ? c2_mul_ni(a) : c2_mul_pi(a); }
+// a * (c + DIR*i*s), c and s compile-time constants
+template <int DIR>
+__device__ __forceinline__ c2 c2_mul_w(c2 a, float c, float s) { return c2_cmul(a, c2_pack(c, DIR < 0 ? -s : s)); }
 
 template <> struct Bfly<2> {
     __host__ __device__ static constexpr int out(int r) { return r; }
-    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[2]) {
-        const float2 a = v[0], b = v[1];
-        v[0] = cadd(a, b);
-        v[1] = csub(a, b);
+    template <int DIR> __device__ __forceinline__ static void run(c2 (&v)[2]) {
+        const c2 a = v[0], b = v[1];
+        v[0] = c2_add(a, b);
+        v[1] = c2_sub(a, b);
     }
 };
 
 template <int DIR>
-__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
-    const float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = mul_i<DIR>(csub(b, d));
-    a = cadd(s0, s1);
-    c = csub(s0, s1);
-    b = cadd(d0, d1);
-    d = csub(d0, d1);
+__device__ __forceinline__ void dft4(c2 &a, c2 &b, c2 &c, c2 &d) {
+    const c2 s0 = c2_add(a, c), d0 = c2_sub(a, c), s1 = c2_add(b, d), t = c2_sub(b, d);
+    a = c2_add(s0, s1);
+    c = c2_sub(s0, s1);
+    b = c2_add(d0, c2_mul_i<DIR>(t));
+    d = c2_sub(d0, c2_mul_i<DIR>(t));
 }
 
 template <> struct Bfly<4> {
     __host__ __device__ static constexpr int out(int r) { return r; }
-    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[4]) {
+    template <int DIR> __device__ __forceinline__ static void run(c2 (&v)[4]) {
         dft4<DIR>(v[0], v[1], v[2], v[3]);
     }
 };
@@ -143,18 +160,18 @@ template <> struct Bfly<4> {
 // j = j0 + 4 j1 (j1 in {0,1}), k = k1 + 2 k0: register k0 + 4 k1 holds bin k1 + 2 k0
 template <> struct Bfly<8> {
     __host__ __device__ static constexpr int out(int r) { return (r >> 2) + 2 * (r & 3); }
-    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[8]) {
+    template <int DIR> __device__ __forceinline__ static void run(c2 (&v)[8]) {
         constexpr float C2 = 0.70710678118654752440f;
 #pragma unroll
         for (int j0 = 0; j0 < 4; j0++) {
-            const float2 a = v[j0], b = v[j0 + 4];
-            v[j0] = cadd(a, b);
-            v[j0 + 4] = csub(a, b);
+            const c2 a = v[j0], b = v[j0 + 4];
+            v[j0] = c2_add(a, b);
+            v[j0 + 4] = c2_sub(a, b);
         }
         // twiddle w_8^(j0*k1), k1 = 1 row only
-        v[5] = mul_w<DIR>(v[5], C2, C2);
-        v[6] = mul_i<DIR>(v[6]);
-        v[7] = mul_w<DIR>(v[7], -C2, C2);
+        v[5] = c2_mul_w<DIR>(v[5], C2, C2);
+        v[6] = c2_mul_i<DIR>(v[6]);
+        v[7] = c2_mul_w<DIR>(v[7], -C2, C2);
         dft4<DIR>(v[0], v[1], v[2], v[3]);
         dft4<DIR>(v[4], v[5], v[6], v[7]);
     }
@@ -163,22 +180,22 @@ template <> struct Bfly<8> {
 // j = j0 + 4 j1, k = k1 + 4 k0: register k0 + 4 k1 holds bin k1 + 4 k0
 template <> struct Bfly<16> {
     __host__ __device__ static constexpr int out(int r) { return (r >> 2) + 4 * (r & 3); }
-    template <int DIR> __device__ __forceinline__ static void run(float2 (&v)[16]) {
+    template <int DIR> __device__ __forceinline__ static void run(c2 (&v)[16]) {
         constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
         constexpr float S1 = 0.38268343236508977173f;  // sin(pi/8)
         constexpr float C2 = 0.70710678118654752440f;
 #pragma unroll
         for (int j0 = 0; j0 < 4; j0++) dft4<DIR>(v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12]);
         // v[j0 + 4 k1] *= w_16^(j0 k1)
-        v[5] = mul_w<DIR>(v[5], C1, S1);     // 1
-        v[6] = mul_w<DIR>(v[6], C2, C2);     // 2
-        v[7] = mul_w<DIR>(v[7], S1, C1);     // 3
-        v[9] = mul_w<DIR>(v[9], C2, C2);     // 2
-        v[10] = mul_i<DIR>(v[10]);           // 4
-        v[11] = mul_w<DIR>(v[11], -C2, C2);  // 6
-        v[13] = mul_w<DIR>(v[13], S1, C1);   // 3
-        v[14] = mul_w<DIR>(v[14], -C2, C2);  // 6
-        v[15] = mul_w<DIR>(v[15], -C1, -S1); // 9
+        v[5] = c2_mul_w<DIR>(v[5], C1, S1);     // 1
+        v[6] = c2_mul_w<DIR>(v[6], C2, C2);     // 2
+        v[7] = c2_mul_w<DIR>(v[7], S1, C1);     // 3
+        v[9] = c2_mul_w<DIR>(v[9], C2, C2);     // 2
+        v[10] = c2_mul_i<DIR>(v[10]);           // 4
+        v[11] = c2_mul_w<DIR>(v[11], -C2, C2);  // 6
+        v[13] = c2_mul_w<DIR>(v[13], S1, C1);   // 3
+        v[14] = c2_mul_w<DIR>(v[14], -C2, C2);  // 6
+        v[15] = c2_mul_w<DIR>(v[15], -C1, -S1); // 9
 #pragma unroll
         for (int k1 = 0; k1 < 4; k1++) dft4<DIR>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
     }
@@ -188,86 +205,137 @@ template <> struct Bfly<16> {
 // When the butterfly stride S divides the thread count, every butterfly a thread
 // handles in a pass has the same u = b mod S, i.e. the same R-1 twiddles: they are
 // loaded once per pass (TW_INVARIANT), otherwise once per butterfly.
-template <int Q_LOG2, int T, int NT>
-__device__ __forceinline__ void fwd_pass(float2 *sm, const float2 *__restrict__ tw, int tid) {
+//
+// Shared-memory addressing: element base + j*S of a butterfly sits at
+// smem_pad(base) + smem_pad(j*S) whenever the pass's block length is >= 16 (the low
+// four bits of base are then u < S and never carry), i.e. one register plus
+// compile-time offsets.
+template <int LS, int LQT>
+__device__ __forceinline__ int bfly_pos(int pbase, int base, int j) {
+    if (LQT >= 4) return pbase + smem_pad(j << LS);
+    return smem_pad(base + (j << LS));
+}
+
+template <int Q_LOG2, int T, int NT, int NH>
+__device__ __forceinline__ void fwd_pass(float2 *smf, const float2 *__restrict__ twf, int tid) {
     constexpr int LR = plan_lr(Q_LOG2, T), R = 1 << LR;
     constexpr int LS = plan_ls(Q_LOG2, T), S = 1 << LS;
     constexpr int LQT = plan_lqt(Q_LOG2, T);
-    constexpr int NB = (2 << Q_LOG2) >> LR;
+    constexpr int NB = (NH << Q_LOG2) >> LR;
     constexpr bool TW_INVARIANT = S > 1 && (NT % S) == 0;
-    float2 w[R];
+    constexpr int NI = (NB + NT - 1) / NT;       // butterflies per thread
+    constexpr int UN = (NI % 2 == 0 && R <= 16) ? 2 : 1;  // two independent butterflies in flight
+    c2 *sm = reinterpret_cast<c2 *>(smf);
+    const c2 *tw = reinterpret_cast<const c2 *>(twf);
+    c2 w[R];
     if (TW_INVARIANT) {
 #pragma unroll
         for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + (tid & (S - 1))]);
     }
-    for (int b = tid; b < NB; b += NT) {
-        const int u = b & (S - 1);
-        const int base = ((b >> LS) << LQT) + u;
-        float2 v[R];
+#ifdef FCV_EXP_NOTW
 #pragma unroll
-        for (int j = 0; j < R; j++) v[j] = sm[smem_pad(base + (j << LS))];
-        if (S > 1 && !TW_INVARIANT) {
+    for (int k1 = 1; k1 < R; k1++) w[k1] = c2_pack(1.0f - 1e-3f * k1 * tid, 1e-3f * tid);
+#endif
+#pragma unroll 1
+    for (int b0 = tid; b0 < NB; b0 += NT * UN) {
+        c2 v[UN][R];
+        int pb[UN], bs[UN];
 #pragma unroll
-            for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
+        for (int q = 0; q < UN; q++) {
+            const int b = b0 + q * NT;
+            const int u = b & (S - 1);
+            bs[q] = ((b >> LS) << LQT) + u;
+            pb[q] = smem_pad(bs[q]);
+#pragma unroll
+            for (int j = 0; j < R; j++) v[q][j] = sm[bfly_pos<LS, LQT>(pb[q], bs[q], j)];
         }
-        Bfly<R>::template run<-1>(v);
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int k1 = Bfly<R>::out(r);
-            float2 x = v[r];
-            if (S > 1 && k1 > 0) x = cmul(x, w[k1]);
-            sm[smem_pad(base + (k1 << LS))] = x;
+        for (int q = 0; q < UN; q++) {
+            const int b = b0 + q * NT;
+            if (b < NB || UN == 1) {
+#ifndef FCV_EXP_NOTW
+                if (S > 1 && !TW_INVARIANT) {
+                    const int u = b & (S - 1);
+#pragma unroll
+                    for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
+                }
+#endif
+                Bfly<R>::template run<-1>(v[q]);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int k1 = Bfly<R>::out(r);
+                    c2 x = v[q][r];
+                    if (S > 1 && k1 > 0) x = c2_cmul(x, w[k1]);
+                    sm[bfly_pos<LS, LQT>(pb[q], bs[q], k1)] = x;
+                }
+            }
         }
     }
     __syncthreads();
 }
 
-template <int Q_LOG2, int T, int NT>
-__device__ __forceinline__ void inv_pass(float2 *sm, const float2 *__restrict__ tw, int tid) {
+template <int Q_LOG2, int T, int NT, int NH>
+__device__ __forceinline__ void inv_pass(float2 *smf, const float2 *__restrict__ twf, int tid) {
     constexpr int LR = plan_lr(Q_LOG2, T), R = 1 << LR;
     constexpr int LS = plan_ls(Q_LOG2, T), S = 1 << LS;
     constexpr int LQT = plan_lqt(Q_LOG2, T);
-    constexpr int NB = (2 << Q_LOG2) >> LR;
+    constexpr int NB = (NH << Q_LOG2) >> LR;
     constexpr bool TW_INVARIANT = S > 1 && (NT % S) == 0;
-    float2 w[R];
+    constexpr int NI = (NB + NT - 1) / NT;
+    constexpr int UN = (NI % 2 == 0 && R <= 16) ? 2 : 1;
+    c2 *sm = reinterpret_cast<c2 *>(smf);
+    const c2 *tw = reinterpret_cast<const c2 *>(twf);
+    c2 w[R];
     if (TW_INVARIANT) {
 #pragma unroll
         for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + (tid & (S - 1))]);
     }
-    for (int b = tid; b < NB; b += NT) {
-        const int u = b & (S - 1);
-        const int base = ((b >> LS) << LQT) + u;
-        float2 v[R];
-        if (S > 1 && !TW_INVARIANT) {
+#pragma unroll 1
+    for (int b0 = tid; b0 < NB; b0 += NT * UN) {
+        c2 v[UN][R];
+        int pb[UN], bs[UN];
 #pragma unroll
-            for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
+        for (int q = 0; q < UN; q++) {
+            const int b = b0 + q * NT;
+            const int u = b & (S - 1);
+            bs[q] = ((b >> LS) << LQT) + u;
+            pb[q] = smem_pad(bs[q]);
+#pragma unroll
+            for (int k1 = 0; k1 < R; k1++) v[q][k1] = sm[bfly_pos<LS, LQT>(pb[q], bs[q], k1)];
         }
 #pragma unroll
-        for (int k1 = 0; k1 < R; k1++) {
-            float2 x = sm[smem_pad(base + (k1 << LS))];
-            if (S > 1 && k1 > 0) x = cmulconj(x, w[k1]);
-            v[k1] = x;
-        }
-        Bfly<R>::template run<+1>(v);
+        for (int q = 0; q < UN; q++) {
+            const int b = b0 + q * NT;
+            if (S > 1 && !TW_INVARIANT) {
+                const int u = b & (S - 1);
 #pragma unroll
-        for (int r = 0; r < R; r++) sm[smem_pad(base + (Bfly<R>::out(r) << LS))] = v[r];
+                for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
+            }
+            if (S > 1) {
+#pragma unroll
+                for (int k1 = 1; k1 < R; k1++) v[q][k1] = c2_cmulconj(v[q][k1], w[k1]);
+            }
+            Bfly<R>::template run<+1>(v[q]);
+#pragma unroll
+            for (int r = 0; r < R; r++) sm[bfly_pos<LS, LQT>(pb[q], bs[q], Bfly<R>::out(r))] = v[q][r];
+        }
     }
     __syncthreads();
 }
 
-template <int Q_LOG2, int NT>
+template <int Q_LOG2, int NT, int NH>
 __device__ __forceinline__ void fwd_passes(float2 *sm, const FftTables &tb, int tid) {
-    fwd_pass<Q_LOG2, 0, NT>(sm, tb.twP[0], tid);
-    fwd_pass<Q_LOG2, 1, NT>(sm, tb.twP[1], tid);
-    if constexpr (plan_npass(Q_LOG2) >= 3) fwd_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
-    if constexpr (plan_npass(Q_LOG2) >= 4) fwd_pass<Q_LOG2, 3, NT>(sm, tb.twP[3], tid);
+    fwd_pass<Q_LOG2, 0, NT, NH>(sm, tb.twP[0], tid);
+    fwd_pass<Q_LOG2, 1, NT, NH>(sm, tb.twP[1], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 3) fwd_pass<Q_LOG2, 2, NT, NH>(sm, tb.twP[2], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 4) fwd_pass<Q_LOG2, 3, NT, NH>(sm, tb.twP[3], tid);
 }
-template <int Q_LOG2, int NT>
+template <int Q_LOG2, int NT, int NH>
 __device__ __forceinline__ void inv_passes(float2 *sm, const FftTables &tb, int tid) {
-    if constexpr (plan_npass(Q_LOG2) >= 4) inv_pass<Q_LOG2, 3, NT>(sm, tb.twP[3], tid);
-    if constexpr (plan_npass(Q_LOG2) >= 3) inv_pass<Q_LOG2, 2, NT>(sm, tb.twP[2], tid);
-    inv_pass<Q_LOG2, 1, NT>(sm, tb.twP[1], tid);
-    inv_pass<Q_LOG2, 0, NT>(sm, tb.twP[0], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 4) inv_pass<Q_LOG2, 3, NT, NH>(sm, tb.twP[3], tid);
+    if constexpr (plan_npass(Q_LOG2) >= 3) inv_pass<Q_LOG2, 2, NT, NH>(sm, tb.twP[2], tid);
+    inv_pass<Q_LOG2, 1, NT, NH>(sm, tb.twP[1], tid);
+    inv_pass<Q_LOG2, 0, NT, NH>(sm, tb.twP[0], tid);
 }
 
 // entry e of the packed-permuted layout <-> its conjugate-partner entry
@@ -361,11 +429,11 @@ __device__ __forceinline__ void pcm_store(void *p, size_t idx, float v) {
 // in: interleaved PCM, `nchan` channels, channel `chan`; frames >= frames_valid read as 0.
 // All global loads of a stage are issued before their first use (the stages are
 // latency bound otherwise: one CTA only has 8 warps).
-template <int LOG2N, int FMT, int NCH>
+template <int LOG2N, int FMT, int NCH, int NH>
 __device__ __forceinline__ void fwd_load(float2 *sm, const FftTables &tb, const void *in, int nchan,
-                                         int chan, int frames_valid) {
+                                         int chan, int frames_valid, int h0) {
     constexpr int QL = LOG2N - 1, Q = 1 << QL;
-    constexpr int NT = fft_threads(LOG2N);
+    constexpr int NT = fft_threads(LOG2N, NH);
     constexpr int IT = Q / NT;
     constexpr int CH = IT < 8 ? IT : 8;
     const int tid = threadIdx.x;
@@ -374,55 +442,72 @@ __device__ __forceinline__ void fwd_load(float2 *sm, const FftTables &tb, const 
         float2 z[CH], w[CH];
 #pragma unroll
         for (int i = 0; i < CH; i++) z[i] = pcm_load2<FMT, NCH>(in, nchan, chan, tid + (c + i) * NT);
+        if (NH == 2 || h0) {
 #pragma unroll
-        for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twA[tid + (c + i) * NT]);
+            for (int i = 0; i < CH; i++) w[i] = __ldg(&tb.twA[tid + (c + i) * NT]);
+        }
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             const int n = tid + (c + i) * NT;
             float2 v = z[i];
             if (2 * n >= frames_valid) v.x = 0.0f;
             if (2 * n + 1 >= frames_valid) v.y = 0.0f;
-            sm[smem_pad(n)] = v;
-            sm[smem_pad(Q + n)] = cmul(v, w[i]);
+            if (NH == 2) {
+                sm[smem_pad(n)] = v;
+                sm[smem_pad(Q + n)] = cmul(v, w[i]);
+            } else {
+                sm[smem_pad(n)] = h0 ? cmul(v, w[i]) : v;
+            }
         }
     }
 }
 
-template <int LOG2N, int FMT>
+// NH == 2: the whole spectrum; NH == 1: half h0 of it (entries [h0*Q, (h0+1)*Q) of out_row).
+template <int LOG2N, int FMT, int NH>
 __device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const void *in, int nchan,
-                                         int chan, int frames_valid, float2 *__restrict__ out_row) {
-    constexpr int QL = LOG2N - 1, Q = 1 << QL, M = 2 * Q;
-    constexpr int NT = fft_threads(LOG2N);
+                                         int chan, int frames_valid, float2 *__restrict__ out_row, int h0 = 0) {
+    constexpr int QL = LOG2N - 1, Q = 1 << QL, ME = NH * Q;
+    constexpr int NT = fft_threads(LOG2N, NH);
     const int tid = threadIdx.x;
-    if (nchan == 2) fwd_load<LOG2N, FMT, 2>(sm, tb, in, nchan, chan, frames_valid);
-    else if (nchan == 1) fwd_load<LOG2N, FMT, 1>(sm, tb, in, nchan, chan, frames_valid);
-    else fwd_load<LOG2N, FMT, 0>(sm, tb, in, nchan, chan, frames_valid);
+    if (nchan == 2) fwd_load<LOG2N, FMT, 2, NH>(sm, tb, in, nchan, chan, frames_valid, h0);
+    else if (nchan == 1) fwd_load<LOG2N, FMT, 1, NH>(sm, tb, in, nchan, chan, frames_valid, h0);
+    else fwd_load<LOG2N, FMT, 0, NH>(sm, tb, in, nchan, chan, frames_valid, h0);
     __syncthreads();
-    fwd_passes<QL, NT>(sm, tb, tid);
-    // unpack: X[k] = E - i w D from the bin and its conjugate partner
-    constexpr int CH = (M / NT) < 8 ? (M / NT) : 8;
+    fwd_passes<QL, NT, NH>(sm, tb, tid);
+    // unpack: X[k] = E - i w D from the bin and its conjugate partner (same half)
+    const int e0 = NH == 2 ? 0 : h0 * Q;  // first global entry this CTA holds
+    constexpr int CH = (ME / NT) < 8 ? (ME / NT) : 8;
 #pragma unroll 1
-    for (int c = 0; c < M / NT; c += CH) {
+    for (int c = 0; c < ME / NT; c += CH) {
         float2 w[CH], x[CH];
         int e2[CH];
 #pragma unroll
         for (int i = 0; i < CH; i++) {
-            w[i] = __ldg(&tb.twU[tid + (c + i) * NT]);
-            e2[i] = __ldg(&tb.part[tid + (c + i) * NT]);
+#ifdef FCV_EXP_NOPART
+            w[i] = make_float2(1.0f - 1e-4f * tid, 1e-4f * (c + i));
+            e2[i] = 0;
+#else
+            w[i] = __ldg(&tb.twU[e0 + tid + (c + i) * NT]);
+            e2[i] = (int)__ldg(&tb.part[e0 + tid + (c + i) * NT]) - e0;
+#endif
         }
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             const int e = tid + (c + i) * NT;
             const float2 zk = sm[smem_pad(e)];
+#ifdef FCV_EXP_NOPART
+            const float2 zp = make_float2(zk.y, zk.x);
+#else
             const float2 zp = sm[smem_pad(e2[i])];
+#endif
             const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
             const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
             const float2 t = cmul(w[i], dv);
             x[i] = make_float2(ev.x + t.y, ev.y - t.x);              // E - i w D
-            if (e == 0) x[i] = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
+            if (e0 + e == 0) x[i] = make_float2(zk.x + zk.y, zk.x - zk.y);  // DC, Nyquist
         }
 #pragma unroll
-        for (int i = 0; i < CH; i++) out_row[tid + (c + i) * NT] = x[i];
+        for (int i = 0; i < CH; i++) out_row[e0 + tid + (c + i) * NT] = x[i];
     }
 }
 
@@ -465,7 +550,7 @@ template <int LOG2N>
 __device__ __forceinline__ void inv_body(float2 *sm, const FftTables &tb) {
     constexpr int QL = LOG2N - 1;
     constexpr int NT = fft_threads(LOG2N);
-    inv_passes<QL, NT>(sm, tb, threadIdx.x);
+    inv_passes<QL, NT, 2>(sm, tb, threadIdx.x);
 }
 
 }  // namespace fcv
