@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "fcv_fft.cuh"
+#include "fcv_fft13.cuh"
 #include "fcv_mac.cuh"
 
 using namespace fcv;
@@ -247,6 +248,133 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// fragm = 8192: the wavefront-lean transforms of fcv_fft13.cuh
+// ---------------------------------------------------------------------------
+#ifndef F13_INV_NT
+#define F13_INV_NT 256   // threads of the inverse kernel: 256 (2 CTAs/SM, <= 128 registers) or 128 (3 CTAs/SM)
+#endif
+constexpr int f13_min_ctas(int nt) { return nt >= 256 ? 2 : 3; }
+
+// Forward transform of the current block: one CTA = one half (blockIdx.x & 1) of the
+// spectra of C consecutive input channels (blockIdx.x >> 1 = channel group) of one
+// (stream, block): PCM and twiddles are fetched once for C transforms.
+template <int FMT, int NCH, int C>
+__global__ void __launch_bounds__(128 * C, f13_min_ctas(128 * C))
+fwd13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, f13::Tables tb,
+                    int ninp, int R, int T, int pt, int reset_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    constexpr int N = f13::N;
+    const int h = blockIdx.x & 1, ch0 = (blockIdx.x >> 1) * C, b = blockIdx.y, bt = blockIdx.z;
+    const StreamDev s = st[b];
+    int frames = (fv ? fv[b] : T * N) - bt * N;
+    frames = frames < 0 ? 0 : (frames > N ? N : frames);
+    int slot = pt + bt;
+    if (slot >= R) slot -= R;
+    float2 *rows[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) rows[c] = s.xring + (size_t)((ch0 + c) * R + slot) * N;
+    // per-block maximum mode: the inverse kernel of this block starts from zero
+    if (reset_max && blockIdx.x == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    if (frames == 0) {  // silence: its spectrum is zero
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            for (int e = threadIdx.x; e < f13::Q; e += 128 * C) rows[c][h * f13::Q + e] = make_float2(0.f, 0.f);
+        return;
+    }
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    const void *in = reinterpret_cast<const char *>(s.din) + (size_t)bt * N * ninp * wire;
+    if (h == 0) f13::fwd_half<0, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
+    else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
+}
+
+// Filter preparation (K6): src[row][N] floats -> dst[row][N] spectra, one half per CTA.
+__global__ void __launch_bounds__(128, f13_min_ctas(128))
+fwd13_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, f13::Tables tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    const size_t r = blockIdx.y;
+    float2 *rows[1] = {dst + r * f13::N};
+    if (blockIdx.x == 0) f13::fwd_half<0, PCM_F32, 1, 1, 128>(sm, tb, src + r * f13::N, 1, 0, f13::N, rows);
+    else f13::fwd_half<1, PCM_F32, 1, 1, 128>(sm, tb, src + r * f13::N, 1, 0, f13::N, rows);
+}
+
+// Inverse transform of every (stream, output channel), T blocks one after the other.
+template <int FMT>
+__global__ void __launch_bounds__(F13_INV_NT, f13_min_ctas(F13_INV_NT))
+inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, f13::Tables tb,
+                    const float2 *__restrict__ Y, const TTPair *__restrict__ pairs,
+                    const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
+                    const float2 *__restrict__ H, int nout, int P, int R, int T, int pt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    constexpr int NT = F13_INV_NT;
+    __shared__ float red[NT / 32];
+    constexpr int N = f13::N, M = N;
+    const int tid = threadIdx.x;
+    const int o = blockIdx.x, b = blockIdx.y;
+    const StreamDev s = st[b];
+    const int fvb = fv ? fv[b] : T * N;
+    float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    float lmax = 0.0f;
+
+    for (int bt = 0; bt < T; bt++) {
+        int frames = fvb - bt * N;
+        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+        int newest = pt + bt;
+        if (newest >= R) newest -= R;
+        // DC and Nyquist are real bins sharing entry 0: redo their products as two
+        // real multiply-accumulates (the MAC kernel treated the entry as complex).
+        float dc = 0.f, ny = 0.f;
+        if (tid < 32) {
+            for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
+                const int inp = pairs[p].inp;
+                const int *rows = tt_rows + pairs[p].rowbase;
+                for (int j = tid; j < P; j += 32) {
+                    const int row = rows[j];
+                    if (row >= 0) {
+                        int slot = newest - j;
+                        if (slot < 0) slot += R;
+                        const float2 x = s.xring[(size_t)(inp * R + slot) * M];
+                        const float2 hh = H[(size_t)row * M];
+                        dc = fmaf(x.x, hh.x, dc);
+                        ny = fmaf(x.y, hh.y, ny);
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                dc += __shfl_xor_sync(0xffffffffu, dc, d);
+                ny += __shfl_xor_sync(0xffffffffu, ny, d);
+            }
+        }
+        const float2 *yrow = Y + (((size_t)b * nout + o) * T + bt) * M;
+#pragma unroll 1
+        for (int j = tid; j < 256; j += NT) {
+            if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(dc + ny, dc - ny), j);  // Zc[0] from the two real bins
+            else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, j - 128);
+        }
+        __syncthreads();
+        f13::pass_b<+1, 2, NT>(sm, tb);
+        __syncthreads();
+        void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * nout * wire;
+        lmax = fmaxf(lmax, f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames));
+        if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+    if ((tid & 31) == 0) red[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; w++) lmax = fmaxf(lmax, red[w]);
+        // running maximum is >= 0, positive floats order like their bit patterns
+        if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // per-device context: twiddle tables per partition size
 // ---------------------------------------------------------------------------
@@ -258,6 +386,8 @@ struct DeviceCtx {
     bool have[16] = {};
     FftTables tab[16];
     bool attr_set[16] = {};
+    bool have13 = false;
+    f13::Tables tab13{};
 };
 static std::mutex g_ctx_mu;
 static std::map<int, DeviceCtx *> g_ctx;
@@ -383,6 +513,68 @@ static int get_tables(int device, int log2n, FftTables *out) {
     return 0;
 }
 
+
+// fragm = 8192 runs the transforms of fcv_fft13.cuh (their spectrum layout differs from the
+// generic kernels', so the choice is process-wide); FCV_GENERIC_FFT=1 keeps the generic ones.
+static bool use_f13(int log2n) {
+    static const bool generic = [] {
+        const char *v = getenv("FCV_GENERIC_FFT");
+        return v && *v && *v != '0';
+    }();
+    return log2n == f13::LOG2N && !generic;
+}
+
+template <int FMT>
+static int set_attrs13() {
+    const int one = (int)f13::HALF_BYTES, two = 2 * (int)f13::HALF_BYTES;
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<FMT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<FMT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<FMT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
+    CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    return 0;
+}
+
+// Twiddle tables of the fragm = 8192 transforms (fcv_fft13.cuh), double precision on the host.
+static int get_tables13(int device, f13::Tables *out) {
+    DeviceCtx *c = get_ctx(device);
+    std::lock_guard<std::mutex> l(c->mu);
+    if (!c->have13) {
+        const int M = f13::N, Q = f13::Q;
+        const double PI = 3.14159265358979323846264338327950288;
+        std::vector<float2> h((size_t)15 * 256 + 16 * 256 + 256 + 2 * Q);
+        auto unit = [&](double turns) {  // exp(-2 pi i turns)
+            const double a = -2.0 * PI * turns;
+            return make_float2((float)cos(a), (float)sin(a));
+        };
+        size_t o0 = 0, o1 = o0 + 15 * 256, oB = o1 + 16 * 256, oU = oB + 256;
+        for (int k0 = 1; k0 < 16; k0++)
+            for (int u = 0; u < 256; u++) h[o0 + (size_t)(k0 - 1) * 256 + u] = unit((double)(2 * u * k0 % M) / M);
+        for (int k0 = 0; k0 < 16; k0++)
+            for (int u = 0; u < 256; u++) h[o1 + (size_t)k0 * 256 + u] = unit((double)(u * (2 * k0 + 1) % M) / M);
+        for (int n0 = 0; n0 < 16; n0++)
+            for (int k1 = 0; k1 < 16; k1++) h[oB + (size_t)n0 * 16 + k1] = unit((double)(n0 * k1) / 256.0);
+        for (int e = 0; e < 2 * Q; e++) {
+            const int k = 2 * (e & (Q - 1)) + (e >> (f13::LOG2N - 1));
+            h[oU + e] = unit((double)k / (2.0 * M));
+        }
+        float2 *d = nullptr;
+        CU_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
+        CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        c->tab13.twA0 = d + o0;
+        c->tab13.twA1 = d + o1;
+        c->tab13.twB = d + oB;
+        c->tab13.twU = d + oU;
+        int rc = set_attrs13<PCM_F32>();
+        if (!rc) rc = set_attrs13<PCM_S16>();
+        if (!rc) rc = set_attrs13<PCM_S24>();
+        if (rc) return rc;
+        CU_TRY(cudaFuncSetAttribute(fwd13_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f13::HALF_BYTES));
+        c->have13 = true;
+    }
+    *out = c->tab13;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // filter
 // ---------------------------------------------------------------------------
@@ -417,6 +609,7 @@ struct fcv_filter {
     int *dpair_off = nullptr;
     int *dtt_rows = nullptr;
     FftTables tb{};
+    f13::Tables tb13{};   // fragm = 8192 only
     std::vector<MacStep> hsteps;
     std::vector<int> hgroup_off;
 };
@@ -529,6 +722,10 @@ extern "C" int fcv_filter_commit(fcv_filter *f, int device) {
     CU_TRY(cudaSetDevice(device));
     rc = get_tables(device, f->log2n, &f->tb);
     if (rc) return rc;
+    if (use_f13(f->log2n)) {
+        rc = get_tables13(device, &f->tb13);
+        if (rc) return rc;
+    }
     f->device = device;
     const int N = f->fragm;
 
@@ -627,7 +824,11 @@ extern "C" int fcv_filter_commit(fcv_filter *f, int device) {
         CU_TRY(cudaMalloc(&dsrc, rows.size() * sizeof(float)));
         CU_TRY(cudaMemcpy(dsrc, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
         const FftTables tb = f->tb;
-        DISPATCH_LOG2N(f->log2n, (fwd_raw_kernel<L><<<nrows, fft_threads(L), fft_smem_bytes(L)>>>(dsrc, f->dH, tb)));
+        if (use_f13(f->log2n)) {
+            fwd13_raw_kernel<<<dim3(2, nrows), 128, f13::HALF_BYTES>>>(dsrc, f->dH, f->tb13);
+        } else {
+            DISPATCH_LOG2N(f->log2n, (fwd_raw_kernel<L><<<nrows, fft_threads(L), fft_smem_bytes(L)>>>(dsrc, f->dH, tb)));
+        }
         g_launches++;
         cudaError_t e = cudaDeviceSynchronize();
         cudaFree(dsrc);
@@ -662,7 +863,8 @@ static void unpermute_row(int log2n, const float2 *row, float *dst) {
     dst[0] = row[0].x; dst[1] = 0.f;
     dst[2 * M] = row[0].y; dst[2 * M + 1] = 0.f;
     for (int k = 1; k < M; k++) {
-        const int e = ((k & 1) << q) + plan_rev(q, k >> 1);
+        // fragm = 8192: split-parity natural layout (fcv_fft13.cuh); else digit-reversed halves
+        const int e = ((k & 1) << q) + (use_f13(log2n) ? (k >> 1) : plan_rev(q, k >> 1));
         dst[2 * k] = row[e].x;
         dst[2 * k + 1] = row[e].y;
     }
@@ -901,6 +1103,28 @@ static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cuda
     else launch_mac_tt_s<T, 1>(b, off, cnt, newest, q);
 }
 
+// fragm = 8192 forward launch: stereo and mono blocks take the vector-load kernels (stereo:
+// both channels per CTA), any other channel count one channel per CTA with scalar loads.
+template <int FMT>
+static void launch_fwd13_fmt(const fcv_batch *b, int off, int cnt, const int *fv, int pt, cudaStream_t q) {
+    const fcv_filter *f = b->f;
+    const int rm = b->per_block_max ? 1 : 0;
+    if (f->ninp == 2)
+        fwd13_stream_kernel<FMT, 2, 2><<<dim3(2, cnt, b->T), 256, 2 * f13::HALF_BYTES, q>>>(
+            b->dst + off, fv, f->tb13, f->ninp, b->R, b->T, pt, rm);
+    else if (f->ninp == 1)
+        fwd13_stream_kernel<FMT, 1, 1><<<dim3(2, cnt, b->T), 128, f13::HALF_BYTES, q>>>(
+            b->dst + off, fv, f->tb13, f->ninp, b->R, b->T, pt, rm);
+    else
+        fwd13_stream_kernel<FMT, 0, 1><<<dim3(2 * f->ninp, cnt, b->T), 128, f13::HALF_BYTES, q>>>(
+            b->dst + off, fv, f->tb13, f->ninp, b->R, b->T, pt, rm);
+}
+static void launch_fwd13(const fcv_batch *b, int off, int cnt, const int *fv, int pt, cudaStream_t q) {
+    if (b->in_fmt == PCM_F32) launch_fwd13_fmt<PCM_F32>(b, off, cnt, fv, pt, q);
+    else if (b->in_fmt == PCM_S16) launch_fwd13_fmt<PCM_S16>(b, off, cnt, fv, pt, q);
+    else launch_fwd13_fmt<PCM_S24>(b, off, cnt, fv, pt, q);
+}
+
 // How many CTAs ahead (in launch order) the FFT kernels prefetch into L2: about the number
 // of CTAs resident on the device at once (2 per SM).  FCV_FFT_AHEAD overrides; 0 disables.
 static int fft_ahead() {
@@ -919,7 +1143,11 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     // diagnostic: FCV_ONLY=1|2|4 (bit mask fwd|mac|inv) launches only those kernels
     static const int only = getenv("FCV_ONLY") ? atoi(getenv("FCV_ONLY")) : 7;
     if (ev) cudaEventRecord(ev[0], q);
-    if (only & 1)
+    const bool k13 = use_f13(f->log2n);
+    if (!(only & 1)) {
+    } else if (k13) {
+        launch_fwd13(b, off, cnt, fv, pt, q);
+    } else
     DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(2 * f->ninp, cnt, T), fft_threads(L, 1), fft_smem_bytes(L, 1), q>>>(
                                   b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0, fft_ahead())));
     if (ev) cudaEventRecord(ev[1], q);
@@ -940,7 +1168,16 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     }
     if (ev) cudaEventRecord(ev[2], q);
     const float2 *Y = b->Y + (size_t)off * f->nout * T * f->fragm;
-    if (only & 4)
+    if (!(only & 4)) {
+    } else if (k13) {
+#define FCV_INV13_ARGS b->dst + off, fv, f->tb13, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout, f->ring, R, T, pt
+        const dim3 grid(f->nout, cnt);
+        const size_t smem = 2 * f13::HALF_BYTES;
+        if (b->out_fmt == PCM_F32) inv13_stream_kernel<PCM_F32><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS);
+        else if (b->out_fmt == PCM_S16) inv13_stream_kernel<PCM_S16><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS);
+        else inv13_stream_kernel<PCM_S24><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS);
+#undef FCV_INV13_ARGS
+    } else
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
                                   b->dst + off, fv, tb, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout,
                                   f->ring, R, T, pt, b->out_fmt, fft_ahead())));

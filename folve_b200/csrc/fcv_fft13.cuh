@@ -1,0 +1,381 @@
+// fcv_fft13.cuh -- the real FFT / inverse real FFT of one zero-padded partition for
+// fragm = 8192 (every filter longer than 4096 taps, /root/reference/zita-fconfig.cc:74-77),
+// built around what the profile says bounds these kernels on B200: the L1/LSU data pipe
+// (one 128-byte wavefront per clock per SM, shared and global accesses together), not
+// instruction issue, not DRAM latency, not occupancy (profiles/r02_fft_findings.md).
+//
+// Role in the reference path: same as fcv_fft.cuh -- FFTW's r2c / c2r inside
+// zita-convolver's Convlevel::process(), reached from SoundProcessor::Process()
+// (/root/reference/sound-processor.cc:98-127), with the (de)interleave, zero padding,
+// overlap-add, int/float conversion and running maximum fused in.
+//
+// Method.  z[n] = x[2n] + i x[2n+1]; the block is zero padded, so the M = 8192 point
+// transform of z splits into two independent Q = 4096 point transforms ("halves"):
+// half h holds the bins k = 2k' + h.  Each half is 16 x 16 x 16:
+//   pass A  over n2 (n = n0 + 16 n1 + 256 n2), straight from global memory into registers
+//           (half 1: inputs times w_32^n2, constants; w_M^u folded into the output twiddles);
+//           out  A[k0][u] * w,  u = n0 + 16 n1                         -> shared, row k0
+//   pass B  over n1, in place in shared memory:  B[k0][n0 + 16 k1]
+//   pass C  over n0, shared -> registers; one thread takes the run (k0,k1) AND the run of
+//           its conjugate partners, so the real-spectrum unpack X = E - i w D happens in
+//           registers and both results go straight to global memory.
+// Shared memory is touched 4 times per element instead of 9, every table is read in
+// lane order, and one CTA transforms both channels of a stereo block so that PCM and
+// twiddles are fetched once for two transforms.
+// The inverse runs the same passes backwards (C^-1 from global with the Hermitian
+// repack in registers, B^-1 in place, A^-1 + overlap-add + PCM store from registers).
+//
+// Spectrum layout ("split-parity natural"): entry e = h*Q + k' holds bin k = 2k' + h;
+// DC and Nyquist (both real) share entry 0.  The conjugate partner of bin k (bin M - k)
+// is entry (Q - k') mod Q of the same half for h = 0 and Q - 1 - k' for h = 1.  The MAC
+// kernels are element-wise and never look at the order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fcv_c2.cuh"
+#include "fcv_fft.cuh"
+
+namespace fcv {
+namespace f13 {
+
+constexpr int LOG2N = 13;
+constexpr int N = 1 << LOG2N;      // frames per block = complex entries per spectrum
+constexpr int Q = N / 2;           // entries per half
+constexpr int ROW = 257;           // shared-memory row stride (elements): odd -> stride-ROW accesses are conflict free
+constexpr int HALF_ELEMS = 16 * ROW;
+constexpr size_t HALF_BYTES = (size_t)HALF_ELEMS * sizeof(float2);
+
+struct Tables {
+    const float2 *twA0;  // [15][256]  w_M^(2 u k0),      k0 = 1..15   (half 0, pass A)
+    const float2 *twA1;  // [16][256]  w_M^(u (2 k0 + 1)), k0 = 0..15   (half 1, pass A, premultiply folded in)
+    const float2 *twB;   // [16][16]   w_256^(n0 k1)
+    const float2 *twU;   // [2 Q]      exp(-i pi k / M) for the bin at entry e
+};
+
+__host__ __device__ constexpr int out16(int r) { return (r >> 2) + 4 * (r & 3); }   // Bfly<16>::out
+__host__ __device__ constexpr int reg16(int k) { return ((k & 3) << 2) | (k >> 2); }  // its inverse
+
+// w_32^j = exp(-2 pi i j / 32), j = 0..15 (compile-time j after unrolling)
+__device__ __forceinline__ float2 w32(int j) {
+    constexpr float C[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                             0.19509032201612826785f, 0.0f, -0.19509032201612826785f, -0.38268343236508977173f,
+                             -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                             -0.92387953251128675613f, -0.98078528040323044913f};
+    constexpr float S[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                             0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                             0.98078528040323044913f, 1.0f, 0.98078528040323044913f, 0.92387953251128675613f,
+                             0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                             0.38268343236508977173f, 0.19509032201612826785f};
+    return make_float2(C[j], -S[j]);
+}
+
+__device__ __forceinline__ c2 ldg_c2(const float2 *p) {
+    const float2 v = __ldg(p);
+    return c2_pack(v.x, v.y);
+}
+
+// z[n] = (x[2n], x[2n+1]) of C consecutive channels starting at ch0, frames >= fv read as 0.
+// NCH = 2: stereo block and both channels wanted (one vector load); NCH = 1: mono block;
+// NCH = 0: any layout, scalar loads.
+template <int FMT, int NCH, int C>
+__device__ __forceinline__ void load_z(const void *in, int nchan, int ch0, int n, int fv, c2 (&z)[C]) {
+    float2 v[C];
+    if (NCH == 2 && C == 2) {
+        if (FMT == PCM_F32) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(in) + n);
+            v[0] = make_float2(t.x, t.z);
+            v[1] = make_float2(t.y, t.w);
+        } else if (FMT == PCM_S16) {
+            constexpr float K = 1.0f / 32768.0f;
+            const short4 t = __ldg(reinterpret_cast<const short4 *>(in) + n);
+            v[0] = make_float2(t.x * K, t.z * K);
+            v[1] = make_float2(t.y * K, t.w * K);
+        } else {
+            constexpr float K = 1.0f / 8388608.0f;
+            const int4 t = __ldg(reinterpret_cast<const int4 *>(in) + n);
+            v[0] = make_float2(t.x * K, t.z * K);
+            v[1] = make_float2(t.y * K, t.w * K);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] = pcm_load2<FMT, (NCH == 1 ? 1 : 0)>(in, nchan, ch0 + c, n);
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (2 * n >= fv) v[c].x = 0.0f;
+        if (2 * n + 1 >= fv) v[c].y = 0.0f;
+        z[c] = c2_pack(v[c].x, v[c].y);
+    }
+}
+
+// ---- forward ---------------------------------------------------------------------------
+// Pass A of half H for C channels: global PCM -> registers -> shared row k0.
+template <int H, int FMT, int NCH, int C, int NT>
+__device__ __forceinline__ void fwd_pass_a(c2 *sm, const Tables &tb, const void *in, int nchan, int ch0, int fv) {
+#pragma unroll 1
+    for (int u = threadIdx.x; u < 256; u += NT) {
+        c2 v[C][16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            c2 z[C];
+            load_z<FMT, NCH, C>(in, nchan, ch0, u + 256 * j, fv, z);
+#pragma unroll
+            for (int c = 0; c < C; c++) v[c][j] = z[c];
+        }
+        c2 w[16];
+        if (H == 0) {
+#pragma unroll
+            for (int k0 = 1; k0 < 16; k0++) w[k0] = ldg_c2(tb.twA0 + (k0 - 1) * 256 + u);
+        } else {
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0++) w[k0] = ldg_c2(tb.twA1 + k0 * 256 + u);
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (H == 1) {
+#pragma unroll
+                for (int j = 1; j < 16; j++) v[c][j] = c2_cmul(v[c][j], c2_pack(w32(j)));
+            }
+            Bfly<16>::template run<-1>(v[c]);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k0 = out16(r);
+                c2 x = v[c][r];
+                if (H == 1 || k0 > 0) x = c2_cmul(x, w[k0]);
+                sm[c * HALF_ELEMS + k0 * ROW + u] = x;
+            }
+        }
+    }
+}
+
+// Pass B, in place: thread (k0, n0) transforms over n1 / k1 at row k0, columns n0 + 16 j.
+// NA arrays of HALF_ELEMS (channels in the forward kernel, halves in the inverse one).
+template <int DIR, int NA, int NT>
+__device__ __forceinline__ void pass_b(c2 *sm, const Tables &tb) {
+    const int k0 = threadIdx.x & 15;
+#pragma unroll 1
+    for (int n0 = threadIdx.x >> 4; n0 < 16; n0 += NT / 16) {
+        c2 w[16];
+#pragma unroll
+        for (int k1 = 1; k1 < 16; k1++) w[k1] = ldg_c2(tb.twB + n0 * 16 + k1);
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+            c2 *p = sm + a * HALF_ELEMS + k0 * ROW + n0;
+            c2 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = p[16 * j];
+            if (DIR > 0) {
+#pragma unroll
+                for (int k1 = 1; k1 < 16; k1++) v[k1] = c2_cmulconj(v[k1], w[k1]);
+            }
+            Bfly<16>::template run<DIR>(v);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k = out16(r);
+                c2 x = v[r];
+                if (DIR < 0 && k > 0) x = c2_cmul(x, w[k]);
+                p[16 * k] = x;
+            }
+        }
+    }
+}
+
+// X[k] = E - i w D and X[M-k] = conj(E + i w D) from Z[k] (zk) and Z[M-k] (zp)
+__device__ __forceinline__ void unpack_pair(c2 zk, c2 zp, c2 w, c2 &xk, c2 &xp) {
+    const c2 e = c2_scale(c2_add(zk, c2_conj(zp)), 0.5f);
+    const c2 d = c2_scale(c2_sub(zk, c2_conj(zp)), 0.5f);
+    const c2 t = c2_cmul(d, w);
+    xk = c2_add(e, c2_mul_ni(t));           // E - i t
+    xp = c2_conj(c2_add(e, c2_mul_pi(t)));  // conj(E + i t)
+}
+
+// Pass C of half H + unpack, one channel: shared -> registers -> global row (entries [H*Q, (H+1)*Q)).
+template <int H>
+__device__ __forceinline__ void fwd_pass_c(const c2 *sm, const Tables &tb, float2 *__restrict__ row, int t) {
+    c2 *out = reinterpret_cast<c2 *>(row) + H * Q;
+    const float2 *twu = tb.twU + H * Q;
+    if (H == 0 && t == 0) {
+        // runs c = 0 and c = 128 hold their own partners: k2 <-> 16 - k2 and k2 <-> 15 - k2
+        c2 v1[16], v2[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            v1[j] = sm[j];                  // (k0, k1) = (0, 0): row 0, columns n0
+            v2[j] = sm[16 * 8 + j];         // (k0, k1) = (0, 8): row 0, columns 128 + n0
+        }
+        Bfly<16>::template run<-1>(v1);
+        Bfly<16>::template run<-1>(v2);
+        {
+            const float2 z0 = c2_unpack(v1[reg16(0)]);
+            out[0] = c2_pack(z0.x + z0.y, z0.x - z0.y);  // DC, Nyquist
+        }
+#pragma unroll
+        for (int k2 = 1; k2 <= 8; k2++) {
+            c2 xk, xp;
+            unpack_pair(v1[reg16(k2)], v1[reg16(16 - k2)], ldg_c2(twu + 256 * k2), xk, xp);
+            out[256 * k2] = xk;
+            if (k2 != 8) out[256 * (16 - k2)] = xp;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            c2 xk, xp;
+            unpack_pair(v2[reg16(k2)], v2[reg16(15 - k2)], ldg_c2(twu + 256 * k2 + 128), xk, xp);
+            out[256 * k2 + 128] = xk;
+            out[256 * (15 - k2) + 128] = xp;
+        }
+        return;
+    }
+    const int c = t, cc = H == 0 ? 256 - t : 255 - t;
+    c2 v1[16], v2[16];
+    {
+        const c2 *p1 = sm + (c & 15) * ROW + (c >> 4) * 16;
+        const c2 *p2 = sm + (cc & 15) * ROW + (cc >> 4) * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            v1[j] = p1[j];
+            v2[j] = p2[j];
+        }
+    }
+    Bfly<16>::template run<-1>(v1);
+    Bfly<16>::template run<-1>(v2);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) {
+        c2 xk, xp;
+        unpack_pair(v1[reg16(k2)], v2[reg16(15 - k2)], ldg_c2(twu + 256 * k2 + c), xk, xp);
+        out[256 * k2 + c] = xk;
+        out[256 * (15 - k2) + cc] = xp;
+    }
+}
+
+// One half (H) of the transforms of C channels of one block.  rows[c] = spectrum row of channel ch0 + c.
+// NT = 128 * C threads: pass A one u per thread (C = 2) or two (C = 1), pass C one job per thread.
+template <int H, int FMT, int NCH, int C, int NT>
+__device__ __forceinline__ void fwd_half(c2 *sm, const Tables &tb, const void *in, int nchan, int ch0, int fv,
+                                         float2 *const (&rows)[C]) {
+    fwd_pass_a<H, FMT, NCH, C, NT>(sm, tb, in, nchan, ch0, fv);
+    __syncthreads();
+    pass_b<-1, C, NT>(sm, tb);
+    __syncthreads();
+#pragma unroll 1
+    for (int j = threadIdx.x; j < 128 * C; j += NT) {
+        const int c = j >> 7;
+        fwd_pass_c<H>(sm + c * HALF_ELEMS, tb, C == 1 ? rows[0] : (c ? rows[C - 1] : rows[0]), j & 127);
+    }
+}
+
+// ---- inverse ---------------------------------------------------------------------------
+// Zc[k] = (Y[k] + conj Y[M-k]) + i conj(w) (Y[k] - conj Y[M-k]),  Zc[M-k] = conj(E - i conj(w) D)
+__device__ __forceinline__ void repack_pair(c2 yk, c2 yp, c2 w, c2 &zk, c2 &zp) {
+    const c2 e = c2_add(yk, c2_conj(yp));
+    const c2 d = c2_sub(yk, c2_conj(yp));
+    const c2 t = c2_cmulconj(d, w);
+    zk = c2_add(e, c2_mul_pi(t));           // E + i t
+    zp = c2_conj(c2_add(e, c2_mul_ni(t)));  // conj(E - i t)
+}
+
+// Pass C^-1 of half H: global spectrum row -> registers (Hermitian repack) -> shared.
+// zc0 = the value of entry 0 (from the two real bins), used by thread 0 of half 0 only.
+template <int H>
+__device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float2 *__restrict__ yrow, c2 zc0, int t) {
+    const float2 *y = yrow + H * Q;
+    const float2 *twu = tb.twU + H * Q;
+    if (H == 0 && t == 0) {
+        c2 y1[16], y2[16], v1[16], v2[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) {
+            y1[k2] = ldg_c2(y + 256 * k2);
+            y2[k2] = ldg_c2(y + 256 * k2 + 128);
+        }
+        v1[0] = zc0;
+#pragma unroll
+        for (int k2 = 1; k2 <= 8; k2++) {
+            c2 zk, zp;
+            repack_pair(y1[k2], y1[16 - k2], ldg_c2(twu + 256 * k2), zk, zp);
+            v1[k2] = zk;
+            if (k2 != 8) v1[16 - k2] = zp;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            c2 zk, zp;
+            repack_pair(y2[k2], y2[15 - k2], ldg_c2(twu + 256 * k2 + 128), zk, zp);
+            v2[k2] = zk;
+            v2[15 - k2] = zp;
+        }
+        Bfly<16>::template run<+1>(v1);
+        Bfly<16>::template run<+1>(v2);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            sm[out16(r)] = v1[r];
+            sm[16 * 8 + out16(r)] = v2[r];
+        }
+        return;
+    }
+    const int c = t, cc = H == 0 ? 256 - t : 255 - t;
+    c2 v1[16], v2[16];
+    {
+        c2 y1[16], y2[16], w[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) {
+            y1[k2] = ldg_c2(y + 256 * k2 + c);
+            y2[k2] = ldg_c2(y + 256 * k2 + cc);
+            w[k2] = ldg_c2(twu + 256 * k2 + c);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) repack_pair(y1[k2], y2[15 - k2], w[k2], v1[k2], v2[15 - k2]);
+    }
+    Bfly<16>::template run<+1>(v1);
+    Bfly<16>::template run<+1>(v2);
+    c2 *p1 = sm + (c & 15) * ROW + (c >> 4) * 16;
+    c2 *p2 = sm + (cc & 15) * ROW + (cc >> 4) * 16;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        p1[out16(r)] = v1[r];
+        p2[out16(r)] = v2[r];
+    }
+}
+
+// Pass A^-1 of both halves + overlap-add, tail save, re-interleave, float -> PCM and the
+// signed maximum of the valid frames (sound-processor.cc:115-125), all from registers.
+// sm: [2][HALF_ELEMS] (half 0, half 1).  Returns this thread's maximum.
+template <int FMT, int NT>
+__device__ __forceinline__ float inv_pass_a(const c2 *sm, const Tables &tb, float2 *__restrict__ tail, void *dout,
+                                            int nout, int o, int frames) {
+    float lmax = 0.0f;
+#pragma unroll 1
+    for (int u = threadIdx.x; u < 256; u += NT) {
+        c2 va[16], vb[16];
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++) {
+            va[k0] = sm[k0 * ROW + u];
+            vb[k0] = sm[HALF_ELEMS + k0 * ROW + u];
+        }
+#pragma unroll
+        for (int k0 = 1; k0 < 16; k0++) va[k0] = c2_cmulconj(va[k0], ldg_c2(tb.twA0 + (k0 - 1) * 256 + u));
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++) vb[k0] = c2_cmulconj(vb[k0], ldg_c2(tb.twA1 + k0 * 256 + u));
+        Bfly<16>::template run<+1>(va);
+        Bfly<16>::template run<+1>(vb);
+        float2 tl[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) tl[r] = tail[u + 256 * out16(r)];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int n2 = out16(r), n = u + 256 * n2;
+            const c2 b = n2 == 0 ? vb[r] : c2_cmulconj(vb[r], c2_pack(w32(n2)));
+            const float2 s = c2_unpack(c2_add(va[r], b));
+            const float2 d = c2_unpack(c2_sub(va[r], b));
+            const float y0 = s.x + tl[r].x, y1 = s.y + tl[r].y;
+            tail[n] = d;
+            const int f0 = 2 * n;
+            pcm_store<FMT>(dout, (size_t)f0 * nout + o, y0);
+            pcm_store<FMT>(dout, (size_t)(f0 + 1) * nout + o, y1);
+            if (f0 < frames) lmax = fmaxf(lmax, y0);
+            if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
+        }
+    }
+    return lmax;
+}
+
+}  // namespace f13
+}  // namespace fcv
