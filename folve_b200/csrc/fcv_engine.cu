@@ -321,30 +321,42 @@ inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
     const size_t wire = FMT == PCM_S16 ? 2 : 4;
     float lmax = 0.0f;
 
-    for (int bt = 0; bt < T; bt++) {
-        int frames = fvb - bt * N;
-        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+    // DC and Nyquist are real bins sharing entry 0: redo their products as two real
+    // multiply-accumulates (the MAC kernel treated the entry as complex).  Lanes of warp 0
+    // split the partitions.  The scattered X entries of block bt+1 are requested into L2
+    // while block bt is being transformed, so only a CTA's first block waits on HBM for them.
+    auto dcny = [&](int bt, bool prefetch_only, float &dc, float &ny) {
         int newest = pt + bt;
         if (newest >= R) newest -= R;
-        // DC and Nyquist are real bins sharing entry 0: redo their products as two
-        // real multiply-accumulates (the MAC kernel treated the entry as complex).
-        float dc = 0.f, ny = 0.f;
-        if (tid < 32) {
-            for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
-                const int inp = pairs[p].inp;
-                const int *rows = tt_rows + pairs[p].rowbase;
-                for (int j = tid; j < P; j += 32) {
-                    const int row = rows[j];
-                    if (row >= 0) {
-                        int slot = newest - j;
-                        if (slot < 0) slot += R;
-                        const float2 x = s.xring[(size_t)(inp * R + slot) * M];
+        for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
+            const int inp = pairs[p].inp;
+            const int *rows = tt_rows + pairs[p].rowbase;
+            for (int j = tid; j < P; j += 32) {
+                const int row = rows[j];
+                if (row >= 0) {
+                    int slot = newest - j;
+                    if (slot < 0) slot += R;
+                    const float2 *xp = s.xring + (size_t)(inp * R + slot) * M;
+                    if (prefetch_only) {
+                        prefetch_l2(xp);
+                    } else {
+                        const float2 x = *xp;
                         const float2 hh = H[(size_t)row * M];
                         dc = fmaf(x.x, hh.x, dc);
                         ny = fmaf(x.y, hh.y, ny);
                     }
                 }
             }
+        }
+    };
+
+    for (int bt = 0; bt < T; bt++) {
+        int frames = fvb - bt * N;
+        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+        float dc = 0.f, ny = 0.f;
+        if (tid < 32) {
+            if (bt + 1 < T) dcny(bt + 1, true, dc, ny);
+            dcny(bt, false, dc, ny);
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
                 dc += __shfl_xor_sync(0xffffffffu, dc, d);

@@ -2,7 +2,7 @@
 // fragm = 8192 (every filter longer than 4096 taps, /root/reference/zita-fconfig.cc:74-77),
 // built around what the profile says bounds these kernels on B200: the L1/LSU data pipe
 // (one 128-byte wavefront per clock per SM, shared and global accesses together), not
-// instruction issue, not DRAM latency, not occupancy (profiles/r02_fft_findings.md).
+// instruction issue, not DRAM latency, not occupancy (profiles/r01_fft_findings.md).
 //
 // Role in the reference path: same as fcv_fft.cuh -- FFTW's r2c / c2r inside
 // zita-convolver's Convlevel::process(), reached from SoundProcessor::Process()
