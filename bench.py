@@ -223,8 +223,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="santalucia", choices=sorted(workloads.WORKLOADS))
     ap.add_argument("--streams", type=int, default=1024, help="concurrent streams PER GPU")
-    ap.add_argument("--wire", default="f32", choices=["f32", "s16"], help="PCM format of the host buffers")
-    ap.add_argument("--blocks-per-step", type=int, default=4, choices=[1, 2, 4, 8],
+    ap.add_argument("--wire", default="s16", choices=["f32", "s16"],
+                    help="PCM format of the host and device staging buffers (the workload is 16-bit audio; "
+                         "the conversions are fused into the FFT kernels)")
+    ap.add_argument("--blocks-per-step", type=int, default=8, choices=[1, 2, 4, 8],
                     help="consecutive blocks of every stream per step (>1: time-tiled MAC)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident loop")
@@ -274,24 +276,29 @@ def main():
     # Two host staging slots: block k+1 is submitted before block k is awaited, the
     # way a prebuffering server keeps the copy engines busy; every step still moves
     # its own input host->device and its own output device->host.
-    in1, out1 = batch.slot_views(1)
-    in1[:] = batch.host_in
-    for _ in range(1 if args.skip_e2e else W):
-        batch.process()
-    barrier()
+    def measure_e2e(bt, steps):
+        """-> (seconds for `steps` steps, max over ranks; kernel launches)"""
+        in1, _ = bt.slot_views(1)
+        in1[:] = bt.host_in
+        for _ in range(1 if args.skip_e2e else W):
+            bt.process()
+        barrier()
+        n_0 = L.fcv_kernel_launches()
+        t_0 = time.perf_counter()
+        if not args.skip_e2e:
+            bt.submit(0)
+            for k in range(1, steps):
+                bt.submit(k & 1)
+                bt.wait((k - 1) & 1)      # block k-1 is complete in its host_out slot
+            bt.wait((steps - 1) & 1)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(time.perf_counter() - t_0)
+        nl = L.fcv_kernel_launches() - n_0
+        barrier()
+        return sec, nl
+
     clocks.start()
-    n0 = L.fcv_kernel_launches()
-    t0 = time.perf_counter()
-    if not args.skip_e2e:
-        batch.submit(0)
-        for k in range(1, K):
-            batch.submit(k & 1)
-            batch.wait((k - 1) & 1)      # block k-1 is complete in its host_out slot
-        batch.wait((K - 1) & 1)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    launches_e2e = L.fcv_kernel_launches() - n0
-    barrier()
+    e2e_s, launches_e2e = measure_e2e(batch, K)
 
     # ---- single-stream block latency through the synchronous drop-in call
     lat = None
@@ -331,6 +338,17 @@ def main():
 
     audio_per_step = world * B * T * N / wl.fs
     value = audio_per_step * K / (dev_ms * 1e-3)
+    # the same end-to-end loop with float32 on the wire (what SoundProcessor's float buffer
+    # would ship unconverted): twice the PCIe bytes
+    e2e_f32 = None
+    if not args.skip_e2e and fmt != capi.PCM_F32:
+        K2 = max(10, K // 4)
+        b32 = capi.Batch(flt, B, capi.PCM_F32, capi.PCM_F32, blocks_per_step=T)
+        b32.host_in[:] = x
+        sec, _ = measure_e2e(b32, K2)
+        e2e_f32 = {"value": audio_per_step * K2 / sec, "ms_per_step": 1e3 * sec / K2, "steps": K2,
+                   "h2d_bytes_per_step": B * T * N * wl.ninp * 4, "d2h_bytes_per_step": B * T * N * wl.nout * 4}
+        b32.close()
     e2e_value = None if args.skip_e2e else audio_per_step * K / e2e_s
 
     # roofline of the complex-MAC kernel: SURVEY section 8(d) algorithmic bytes
@@ -360,13 +378,14 @@ def main():
             },
             "e2e": {"value": e2e_value, "unit": "x realtime (audio-s per wall-s)",
                     "h2d_bytes_per_step": B * T * N * I * wire_bytes, "d2h_bytes_per_step": B * T * N * O * wire_bytes,
-                    "ms_per_step": 1e3 * e2e_s / K},
+                    "ms_per_step": 1e3 * e2e_s / K, "wire_format": args.wire, "f32_wire": e2e_f32},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "kernel_ms_per_step": {"fwd_fft": kms[0] / max(1, ksteps), "mac": mac_ms,
                                    "inv_fft": kms[2] / max(1, ksteps)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "mac_kernel" if T == 1 else f"mac_tt_kernel<T={T}>",
+                         "kernel": "mac_kernel" if T == 1 else (f"mac_tma_kernel<T={T}>" if T >= 4 and not
+                                                                os.environ.get("FCV_MAC_TMA") == "0" else f"mac_tt_kernel<T={T}>"),
                          "algorithmic_bytes_per_launch": bytes_mac, "peak_source": peak_src,
                          # what the kernel really moved (ncu dram bytes) over the same measured time:
                          # for a time-tiled launch this, not `frac`, is the fraction of the HBM peak in use

@@ -25,6 +25,7 @@
 #include "fcv_fft.cuh"
 #include "fcv_fft13.cuh"
 #include "fcv_mac.cuh"
+#include "fcv_mac_tma.cuh"
 
 using namespace fcv;
 
@@ -69,23 +70,13 @@ static int fail(int code, const char *fmt, ...) {
 template <int LOG2N>
 __global__ void __launch_bounds__(fft_threads(LOG2N, 1), FWD_MIN_CTAS)
 fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
-                  int ninp, int R, int T, int pt, int in_fmt, int reset_max, int ahead) {
+                  int ninp, int R, int T, int pt, int in_fmt, int reset_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     constexpr int N = 1 << LOG2N, NT = fft_threads(LOG2N, 1);
     // grid: x = 2 * input channel + half, y = stream, z = block of the step
     const int i = blockIdx.x >> 1, h = blockIdx.x & 1, b = blockIdx.y, bt = blockIdx.z;
     const StreamDev s = st[b];
-    // optional L2 prefetch of the PCM block of the CTA `ahead` places behind in launch order
-    if (ahead > 0 && blockIdx.x == 0) {
-        const long long la = (long long)b + (long long)gridDim.y * bt + ahead / (2 * ninp);
-        if (la < (long long)gridDim.y * gridDim.z) {
-            const int b2 = (int)(la % gridDim.y), bt2 = (int)(la / gridDim.y);
-            const size_t blk = (size_t)N * ninp * (in_fmt == PCM_S16 ? 2 : 4);
-            const char *src = reinterpret_cast<const char *>(st[b2].din) + (size_t)bt2 * blk;
-            for (size_t off = (size_t)threadIdx.x * 128; off < blk; off += (size_t)NT * 128) prefetch_l2(src + off);
-        }
-    }
     int frames = (fv ? fv[b] : T * N) - bt * N;
     frames = frames < 0 ? 0 : (frames > N ? N : frames);
     int slot = pt + bt;
@@ -161,7 +152,7 @@ __global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
                   const float2 *__restrict__ Y, const TTPair *__restrict__ pairs,
                   const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
-                  const float2 *__restrict__ H, int nout, int P, int R, int T, int pt, int out_fmt, int ahead) {
+                  const float2 *__restrict__ H, int nout, int P, int R, int T, int pt, int out_fmt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     __shared__ float red[32];
@@ -174,24 +165,7 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
     float lmax = 0.0f;
 
-    // L2 prefetch (see fwd_stream_kernel): first spectrum and overlap tail of the CTA
-    // `ahead` places behind this one; this CTA's own next spectrum at each block.
-    if (ahead > 0) {
-        const long long la = (long long)o + (long long)nout * b + ahead;
-        if (la < (long long)nout * gridDim.y) {
-            const int o2 = (int)(la % nout), b2 = (int)(la / nout);
-            const char *y2 = reinterpret_cast<const char *>(Y + (((size_t)b2 * nout + o2) * T) * M);
-            for (size_t off = (size_t)tid * 128; off < (size_t)M * 8; off += (size_t)NT * 128) prefetch_l2(y2 + off);
-            const char *t2 = reinterpret_cast<const char *>(st[b2].tail + (size_t)o2 * N);
-            for (size_t off = (size_t)tid * 128; off < (size_t)N * 4; off += (size_t)NT * 128) prefetch_l2(t2 + off);
-        }
-    }
-
     for (int bt = 0; bt < T; bt++) {
-        if (ahead > 0 && bt + 1 < T) {
-            const char *y2 = reinterpret_cast<const char *>(Y + (((size_t)b * nout + o) * T + bt + 1) * M);
-            for (size_t off = (size_t)tid * 128; off < (size_t)M * 8; off += (size_t)NT * 128) prefetch_l2(y2 + off);
-        }
         int frames = fvb - bt * N;
         frames = frames < 0 ? 0 : (frames > N ? N : frames);
         int newest = pt + bt;
@@ -825,7 +799,10 @@ extern "C" int fcv_filter_commit(fcv_filter *f, int device) {
         CU_TRY(cudaMemcpy(f->dtt_rows, htt_rows.data(), htt_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
 
     const size_t M = (size_t)N;
-    CU_TRY(cudaMalloc(&f->dH, (size_t)(nrows > 0 ? nrows : 1) * M * sizeof(float2)));
+    // one extra, all-zero row after the filter rows: what the TMA-staged MAC loads for a
+    // partition in which a pair has no data
+    CU_TRY(cudaMalloc(&f->dH, (size_t)(nrows + 1) * M * sizeof(float2)));
+    CU_TRY(cudaMemset(f->dH + (size_t)nrows * M, 0, M * sizeof(float2)));
     CU_TRY(cudaMalloc(&f->dsteps, (size_t)(f->nsteps > 0 ? f->nsteps : 1) * sizeof(MacStep)));
     CU_TRY(cudaMalloc(&f->dgroup_off, f->hgroup_off.size() * sizeof(int)));
     if (f->nsteps)
@@ -1090,20 +1067,46 @@ static void launch_mac_tt_s(const fcv_batch *b, int off, int cnt, int newest, cu
     dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->nout);
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
-    static const bool v1 = getenv("FCV_MAC_V2") == nullptr;  // FCV_MAC_V2=1: experimental pointer-walking variant
 #define FCV_TT_ARGS b->dst + off, cnt, f->dpairs, f->dpair_off, f->dtt_rows, H, Y, M4, f->ring, b->R, newest, f->nout
-    if (TPB == 128) {
-        if (v1) mac_tt_kernel<T, S, 128><<<grid, 128, 0, q>>>(FCV_TT_ARGS);
-        else mac_tt2_kernel<T, S, 128><<<grid, 128, 0, q>>>(FCV_TT_ARGS);
-    } else if (TPB == 64)
-        mac_tt2_kernel<T, S, 64><<<grid, 64, 0, q>>>(FCV_TT_ARGS);
-    else
-        mac_tt2_kernel<T, S, 32><<<grid, 32, 0, q>>>(FCV_TT_ARGS);
+    if (TPB == 128) mac_tt_kernel<T, S, 128><<<grid, 128, 0, q>>>(FCV_TT_ARGS);
+    else if (TPB == 64) mac_tt_kernel<T, S, 64><<<grid, 64, 0, q>>>(FCV_TT_ARGS);
+    else mac_tt_kernel<T, S, 32><<<grid, 32, 0, q>>>(FCV_TT_ARGS);
 #undef FCV_TT_ARGS
+}
+
+// TMA-staged variant (fcv_mac_tma.cuh).  Returns false when the shape is not covered.
+template <int T, int S, int NS>
+static bool launch_mac_tma(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
+    const fcv_filter *f = b->f;
+    const int M4 = f->fragm / 2;
+    if (M4 % tma::TPB != 0 || cnt < S) return false;
+    const size_t smem = tma::smem_bytes(S, NS);
+    // dynamic + static shared memory exceeds the 48 KB default; the attribute is per device
+    if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return false;
+    dim3 grid(M4 / tma::TPB, (cnt + S - 1) / S, f->nout);
+    const float4 *H = reinterpret_cast<const float4 *>(f->dH);
+    float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
+    tma::mac_tma_kernel<T, S, NS><<<grid, tma::THREADS, smem, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off,
+                                                                     f->dtt_rows, H, Y, M4, f->ring, b->R, newest,
+                                                                     f->nout, f->nrows);
+    return true;
 }
 
 template <int T>
 static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
+    // T = 4 and T = 8 stream their rows through TMA-staged tiles (fcv_mac_tma.cuh) whenever the
+    // shape allows (spectrum tiles of 2 KB, at least two streams); measured equal to the
+    // register-pipelined kernel below at T = 8 and 2 % faster at T = 4.  FCV_MAC_TMA=0 turns
+    // it off, 2 / 3 select other stream tilings (experiments).
+    static const int use_tma = getenv("FCV_MAC_TMA") ? atoi(getenv("FCV_MAC_TMA")) : 1;
+    if (use_tma) {
+        if (T == 8 && use_tma == 3 && launch_mac_tma<8, 1, 12>(b, off, cnt, newest, q)) return;
+        if (T == 8 && launch_mac_tma<8, 2, 8>(b, off, cnt, newest, q)) return;
+        if (T == 4 && use_tma == 2 && launch_mac_tma<4, 4, 6>(b, off, cnt, newest, q)) return;
+        if (T == 4 && launch_mac_tma<4, 2, 8>(b, off, cnt, newest, q)) return;
+    }
     // Streams per thread, sharing each filter value from registers.  Measured on B200
     // (SantaLucia, 1024 streams): T=4: S=4 0.150 ms/block (HBM floor 0.148), S=2 0.166;
     // T=8: S=2 0.134, S=4 0.143 (228 registers).  FCV_TT_S overrides for experiments.
@@ -1137,13 +1140,6 @@ static void launch_fwd13(const fcv_batch *b, int off, int cnt, const int *fv, in
     else launch_fwd13_fmt<PCM_S24>(b, off, cnt, fv, pt, q);
 }
 
-// How many CTAs ahead (in launch order) the FFT kernels prefetch into L2: about the number
-// of CTAs resident on the device at once (2 per SM).  FCV_FFT_AHEAD overrides; 0 disables.
-static int fft_ahead() {
-    static const int v = getenv("FCV_FFT_AHEAD") ? atoi(getenv("FCV_FFT_AHEAD")) : 296;
-    return v;
-}
-
 // The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
 static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaStream_t q, cudaEvent_t *ev) {
     fcv_filter *f = b->f;
@@ -1161,7 +1157,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
         launch_fwd13(b, off, cnt, fv, pt, q);
     } else
     DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(2 * f->ninp, cnt, T), fft_threads(L, 1), fft_smem_bytes(L, 1), q>>>(
-                                  b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0, fft_ahead())));
+                                  b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
     if (ev) cudaEventRecord(ev[1], q);
     if (!(only & 2)) {
     } else if (T == 1) {
@@ -1192,7 +1188,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     } else
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
                                   b->dst + off, fv, tb, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout,
-                                  f->ring, R, T, pt, b->out_fmt, fft_ahead())));
+                                  f->ring, R, T, pt, b->out_fmt)));
     if (ev) cudaEventRecord(ev[3], q);
     g_launches += 3;
     cudaError_t e = cudaGetLastError();

@@ -232,10 +232,6 @@ __device__ __forceinline__ void fwd_pass(float2 *smf, const float2 *__restrict__
 #pragma unroll
         for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + (tid & (S - 1))]);
     }
-#ifdef FCV_EXP_NOTW
-#pragma unroll
-    for (int k1 = 1; k1 < R; k1++) w[k1] = c2_pack(1.0f - 1e-3f * k1 * tid, 1e-3f * tid);
-#endif
 #pragma unroll 1
     for (int b0 = tid; b0 < NB; b0 += NT * UN) {
         c2 v[UN][R];
@@ -253,13 +249,11 @@ __device__ __forceinline__ void fwd_pass(float2 *smf, const float2 *__restrict__
         for (int q = 0; q < UN; q++) {
             const int b = b0 + q * NT;
             if (b < NB || UN == 1) {
-#ifndef FCV_EXP_NOTW
                 if (S > 1 && !TW_INVARIANT) {
                     const int u = b & (S - 1);
 #pragma unroll
                     for (int k1 = 1; k1 < R; k1++) w[k1] = __ldg(&tw[(k1 - 1) * S + u]);
                 }
-#endif
                 Bfly<R>::template run<-1>(v[q]);
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -483,23 +477,14 @@ __device__ __forceinline__ void fwd_body(float2 *sm, const FftTables &tb, const 
         int e2[CH];
 #pragma unroll
         for (int i = 0; i < CH; i++) {
-#ifdef FCV_EXP_NOPART
-            w[i] = make_float2(1.0f - 1e-4f * tid, 1e-4f * (c + i));
-            e2[i] = 0;
-#else
             w[i] = __ldg(&tb.twU[e0 + tid + (c + i) * NT]);
             e2[i] = (int)__ldg(&tb.part[e0 + tid + (c + i) * NT]) - e0;
-#endif
         }
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             const int e = tid + (c + i) * NT;
             const float2 zk = sm[smem_pad(e)];
-#ifdef FCV_EXP_NOPART
-            const float2 zp = make_float2(zk.y, zk.x);
-#else
             const float2 zp = sm[smem_pad(e2[i])];
-#endif
             const float2 ev = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
             const float2 dv = make_float2(0.5f * (zk.x - zp.x), 0.5f * (zk.y + zp.y));
             const float2 t = cmul(w[i], dv);

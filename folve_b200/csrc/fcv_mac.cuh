@@ -234,162 +234,4 @@ mac_tt_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__re
 }
 
 
-// ---- time-tiled MAC, packed-complex version (the one the engine launches) ----------
-// Same walk as mac_tt_kernel (window of P+T-1 ring slots, newest first; every X row
-// feeds all T accumulators; the filter rows slide through a register window), with
-//   * the arithmetic in packed fp32x2 (fcv_c2.cuh): one complex MAC = 2 FFMA2, half
-//     the issue slots of the scalar form, bit-identical results;
-//   * running row pointers (one 64-bit add per stream per row) instead of a 64-bit
-//     multiply per load; the ring wrap is a uniform select;
-//   * X rows double-buffered in registers by unrolling T rows (T is even), the filter
-//     row of step d+1 loaded straight into the window register that output 0 has just
-//     released (no staging copy);
-//   * the steps at both ends of the window, where some outputs have no partition
-//     (j < 0 or j >= P), skip those multiply-accumulates (uniform branches).
-__device__ __forceinline__ c2x2 ld_stream_c2(const char *p) {
-    c2x2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(v.a), "=l"(v.b) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ c2x2 ld_keep_c2(const char *p) {
-    c2x2 v;
-    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(v.a), "=l"(v.b) : "l"(p));
-    return v;
-}
-
-template <int T, int S, int TPB, bool GUARD>
-struct TTChunk {
-    // T consecutive steps d0 .. d0+T-1 (those < D).  State carried between steps:
-    //   xb[2][S]  X rows of step d (buffer d & 1) and d+1
-    //   hw[T]     filter window: H[j] for output t at step d is hw[(t + d) % T]
-    template <typename F>
-    static __device__ __forceinline__ void run(int d0, int D, int P, c2 (&acc)[T][S][2], c2x2 (&xb)[2][S],
-                                               c2x2 (&hw)[T], F &&advance) {
-#pragma unroll
-        for (int r = 0; r < T; r++) {
-            const int d = d0 + r;
-            if (d < D) {
-                // requests for step d+1 (X rows into the other buffer) and the L2 prefetch
-                advance(d, r, /*phase=*/0);
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    const int j = d - (T - 1) + t;
-                    if (!GUARD || (j >= 0 && j < P)) {
-                        const c2x2 h = hw[(t + r) % T];
-#pragma unroll
-                        for (int s = 0; s < S; s++) {
-                            acc[t][s][0] = c2_cmac(acc[t][s][0], xb[r & 1][s].a, h.a);
-                            acc[t][s][1] = c2_cmac(acc[t][s][1], xb[r & 1][s].b, h.b);
-                        }
-                    }
-                    // output 0 is done with hw[r % T]: that register takes H[d+1] for output T-1
-                    if (t == 0) advance(d, r, /*phase=*/1);
-                }
-            }
-        }
-    }
-};
-
-template <int T, int S, int TPB>
-__global__ void __launch_bounds__(TPB)
-mac_tt2_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__restrict__ pairs,
-               const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
-               const float4 *__restrict__ H, float4 *__restrict__ Y, int M4, int P, int R, int newest_slot,
-               int nout) {
-    static_assert(T % 2 == 0, "X rows are double buffered over an even unroll");
-    const int e4 = blockIdx.x * TPB + threadIdx.x;
-    const int b0 = blockIdx.y * S;
-    const int o = blockIdx.z;
-    const long long rowb = (long long)M4 * 16;  // bytes per spectrum row
-
-    const char *xbase[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        const int b = min(b0 + s, nstreams - 1);
-        xbase[s] = reinterpret_cast<const char *>(st[b].xring) + (size_t)e4 * 16;
-    }
-    const char *hbase = reinterpret_cast<const char *>(H) + (size_t)e4 * 16;
-
-    c2 acc[T][S][2];
-#pragma unroll
-    for (int t = 0; t < T; t++)
-#pragma unroll
-        for (int s = 0; s < S; s++) acc[t][s][0] = acc[t][s][1] = 0ull;
-
-    const int D = P + T - 1;
-    for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
-        const int inp = __ldg(&pairs[p].inp);
-        const int *rows = tt_rows + __ldg(&pairs[p].rowbase);
-        const long long xin = (long long)inp * R * rowb;
-
-        c2x2 hw[T], xb[2][S];
-#pragma unroll
-        for (int t = 0; t < T; t++) hw[t].a = hw[t].b = 0ull;
-
-        // running pointers: xp = row of the step being requested, xq = row being prefetched
-        const char *xp[S], *xq[S];
-        int slot = newest_slot, qslot = newest_slot;
-#pragma unroll
-        for (int s = 0; s < S; s++) xp[s] = xq[s] = xbase[s] + xin + (long long)newest_slot * rowb;
-        auto step_back = [&](const char *(&ptr)[S], int &sl) {
-            const long long delta = sl == 0 ? (long long)(R - 1) * rowb : -rowb;
-            sl = sl == 0 ? R - 1 : sl - 1;
-#pragma unroll
-            for (int s = 0; s < S; s++) ptr[s] += delta;
-        };
-        // L2 prefetch runs FCV_TT_PREFETCH rows ahead of the register pipeline
-#pragma unroll
-        for (int k = 1; k <= FCV_TT_PREFETCH; k++) {
-            step_back(xq, qslot);
-            if (k < D) {
-#pragma unroll
-                for (int s = 0; s < S; s++) prefetch_l2(xq[s]);
-            }
-        }
-        // step 0: X row of the newest block, H[0] into the window register of output T-1
-#pragma unroll
-        for (int s = 0; s < S; s++) xb[0][s] = ld_stream_c2(xp[s]);
-        int rown = __ldg(&rows[0]);
-        if (rown >= 0) hw[T - 1] = ld_keep_c2(hbase + (long long)rown * rowb);
-        rown = P > 1 ? __ldg(&rows[1]) : -1;
-
-        auto advance = [&](int d, int r, int phase) {
-            if (phase == 0) {
-                if (d + 1 < D) {
-                    step_back(xp, slot);
-#pragma unroll
-                    for (int s = 0; s < S; s++) xb[(r + 1) & 1][s] = ld_stream_c2(xp[s]);
-                }
-                step_back(xq, qslot);
-                if (d + 1 + FCV_TT_PREFETCH < D) {
-#pragma unroll
-                    for (int s = 0; s < S; s++) prefetch_l2(xq[s]);
-                }
-            } else {
-                // H[d+1] (zero beyond the last partition or where the pair has none)
-                c2x2 h;
-                h.a = h.b = 0ull;
-                if (rown >= 0) h = ld_keep_c2(hbase + (long long)rown * rowb);
-                hw[r % T] = h;
-                rown = d + 2 < P ? __ldg(&rows[d + 2]) : -1;
-            }
-        };
-
-        int d0 = 0;
-        TTChunk<T, S, TPB, true>::run(d0, D, P, acc, xb, hw, advance);  // head: outputs t < T-1-d have j < 0
-        for (d0 = T; d0 + T <= P; d0 += T) TTChunk<T, S, TPB, false>::run(d0, D, P, acc, xb, hw, advance);
-        for (; d0 < D; d0 += T) TTChunk<T, S, TPB, true>::run(d0, D, P, acc, xb, hw, advance);  // tail: j >= P
-    }
-#pragma unroll
-    for (int t = 0; t < T; t++)
-#pragma unroll
-        for (int s = 0; s < S; s++)
-            if (b0 + s < nstreams) {
-                c2x2 v;
-                v.a = acc[t][s][0];
-                v.b = acc[t][s][1];
-                __stcs(Y + (((size_t)(b0 + s) * nout + o) * T + t) * (size_t)M4 + e4, c2x2_to(v));
-            }
-}
-
 }  // namespace fcv

@@ -292,6 +292,44 @@ def test_time_tiled_batch_equals_block_by_block(T):
     f.close()
 
 
+@pytest.mark.parametrize("nin,nout,T", [(1, 1, 4), (3, 2, 4), (1, 2, 8), (6, 6, 2)])
+def test_time_tiled_other_channel_counts_and_s24(nin, nout, T):
+    """fragm = 8192 with mono, odd and 5.1 channel counts: the forward kernel's mono and
+    scalar-load paths, several blocks per step, 24-bit wire format; tiled == block by block
+    and both == oracle."""
+    r = _rng(90 + 10 * nin + nout + T)
+    spec = FilterSpec(nin, nout, 30000)
+    for i in range(nin):
+        for o in range(nout):
+            if (i + o) % 2 == 0 or nin == 1:
+                spec.add(i, o, r.standard_normal(8000 + 4000 * ((i + o) % 3)) * 0.004, 3000 * ((i * nout + o) % 5))
+    f = _engine(spec)
+    N, B = spec.fragm, 3
+    assert N == 8192
+    total = 2 * T * N
+    xi = r.integers(-(1 << 21), 1 << 21, (B, total, nin)).astype(np.int32)       # 24-bit samples
+    one = capi.Batch(f, B, capi.PCM_S24, capi.PCM_F32)
+    want = np.zeros((B, total, nout), np.float32)
+    for k in range(2 * T):
+        one.host_in[:] = xi[:, k * N:(k + 1) * N]
+        one.process()
+        want[:, k * N:(k + 1) * N] = one.host_out
+    one.close()
+    tt = capi.Batch(f, B, capi.PCM_S24, capi.PCM_F32, blocks_per_step=T)
+    got = np.zeros_like(want)
+    for k in range(2):
+        tt.host_in[:] = xi[:, k * T * N:(k + 1) * T * N]
+        tt.process()
+        got[:, k * T * N:(k + 1) * T * N] = tt.host_out
+    tt.close()
+    assert np.abs(got - want).max() < 2e-6
+    o = _oracle(spec)
+    x0 = (xi[0].astype(np.float64) / 8388608.0).astype(np.float32)
+    ref = run_blocks(o, x0, N)
+    assert np.abs(got[0] - ref).max() < TOL_FS
+    f.close()
+
+
 def test_async_submit_wait_two_slots():
     r = _rng(20)
     spec = FilterSpec(2, 2, 20000)
