@@ -148,6 +148,39 @@ def cpu_arm(wl, filter_dir):
     return ("port", lambda nt, nb: cpu_run(wl, nt, nb), "restated Convproc (oracle/zita_oracle.c)")
 
 
+def fft_calibration(n=16384, reps=300):
+    """The CPU arm's FFT is the oracle's own (FFTW is not installed): time it next to
+    pocketfft (scipy, float32) on one core so that the GPU/CPU ratio cannot be silently
+    flattered by a slow CPU transform."""
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libzita_oracle.so"))
+    L.offt_plan_create.restype = C.c_void_p
+    L.offt_plan_create.argtypes = [C.c_int]
+    L.offt_r2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.offt_plan_destroy.argtypes = [C.c_void_p]
+    x = np.random.default_rng(0).standard_normal(n).astype(np.float32)
+    out = np.zeros(n + 2, np.float32)
+    plan = L.offt_plan_create(n)
+    for _ in range(20):
+        L.offt_r2c(plan, x.ctypes.data, out.ctypes.data)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        L.offt_r2c(plan, x.ctypes.data, out.ctypes.data)
+    t_oracle = (time.perf_counter() - t0) / reps
+    L.offt_plan_destroy(plan)
+    res = {"n": n, "oracle_r2c_us": round(1e6 * t_oracle, 1)}
+    try:
+        import scipy.fft as sfft
+        for _ in range(20):
+            sfft.rfft(x)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sfft.rfft(x)
+        res["pocketfft_rfft_us"] = round(1e6 * (time.perf_counter() - t0) / reps, 1)
+    except Exception:
+        pass
+    return res
+
+
 def cpu_baseline(wl, filter_dir, target_s=12.0):
     cores = len(os.sched_getaffinity(0))
     kind, run, what = cpu_arm(wl, filter_dir)
@@ -158,6 +191,7 @@ def cpu_baseline(wl, filter_dir, target_s=12.0):
         "value": audio / wall, "unit": "x realtime (audio-s per wall-s)", "cores": cores, "kind": kind,
         "sample": f"{cores} files x {nb} blocks of {wl.fragm} frames ({wl.name}), one SoundProcessor/Convproc per "
                   f"file, one file per thread, {wall:.1f} s wall; {what}",
+        "fft_calibration_one_core": fft_calibration(),
     }
 
 

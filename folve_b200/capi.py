@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         "fcv_batch_sync": (i, [vp]),
         "fcv_batch_reset_slot": (i, [vp, i]),
         "fcv_batch_get_max": (i, [vp, fp]),
+        "fcv_batch_get_block_max": (i, [vp, fp]),
         "fcv_batch_cuda_stream": (vp, [vp]),
         "fcv_batch_event_record": (i, [vp, i]),
         "fcv_batch_event_elapsed_ms": (i, [vp, i, i, fp]),
@@ -264,6 +265,12 @@ class Batch:
     def get_max(self):
         m = np.zeros(self.n, np.float32)
         _check(lib().fcv_batch_get_max(self._h, _fp(m)))
+        return m
+
+    def get_block_max(self):
+        """[nstreams, blocks_per_step]: signed maximum of every block of the last step"""
+        m = np.zeros((self.n, self.blocks_per_step), np.float32)
+        _check(lib().fcv_batch_get_block_max(self._h, _fp(m)))
         return m
 
     @property

@@ -64,6 +64,14 @@ static int fail(int code, const char *fmt, ...) {
 // kernels
 // ---------------------------------------------------------------------------
 
+// Signed maximum (>= 0) of one block over all output channels: warp reduction, then one
+// atomic per warp (positive floats order like their bit patterns).
+__device__ __forceinline__ void block_max_update(float *dst, float m) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(m));
+}
+
 // Forward transform of the current block of every (stream, input channel):
 // fused int/float conversion + de-interleave + zero padding + real FFT, written
 // into ring slot `pt` of the stream's input-spectra ring.
@@ -84,6 +92,7 @@ fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     float2 *row = s.xring + (size_t)(i * R + slot) * N;
     // per-block maximum mode: the inverse kernel of this block starts from zero
     if (reset_max && blockIdx.x == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) s.bmax[bt] = 0.0f;  // this block's maximum starts from zero
     if (frames == 0) {  // silence: its spectrum is zero
         for (int e = threadIdx.x; e < N / 2; e += NT) row[h * (N / 2) + e] = make_float2(0.f, 0.f);
         return;
@@ -209,6 +218,7 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
         else if (out_fmt == PCM_S16) m = inv_epilogue<LOG2N, PCM_S16>(sm, tb, tail, (short *)s.dout + boff, nout, o, frames);
         else m = inv_epilogue<LOG2N, PCM_S24>(sm, tb, tail, (int *)s.dout + boff, nout, o, frames);
         lmax = fmaxf(lmax, m);
+        block_max_update(s.bmax + bt, m);
         if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block
     }
 #pragma unroll
@@ -252,6 +262,7 @@ fwd13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
     for (int c = 0; c < C; c++) rows[c] = s.xring + (size_t)((ch0 + c) * R + slot) * N;
     // per-block maximum mode: the inverse kernel of this block starts from zero
     if (reset_max && blockIdx.x == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) s.bmax[bt] = 0.0f;  // this block's maximum starts from zero
     if (frames == 0) {  // silence: its spectrum is zero
 #pragma unroll
         for (int c = 0; c < C; c++)
@@ -347,7 +358,9 @@ inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
         f13::pass_b<+1, 2, NT>(sm, tb);
         __syncthreads();
         void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * nout * wire;
-        lmax = fmaxf(lmax, f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames));
+        const float m = f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames);
+        lmax = fmaxf(lmax, m);
+        block_max_update(s.bmax + bt, m);
         if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block
     }
 #pragma unroll
@@ -909,6 +922,7 @@ struct fcv_batch {
     unsigned char *din = nullptr, *dout = nullptr;
     float2 *Y = nullptr;
     float *maxv = nullptr;
+    float *bmax = nullptr;               // [B][T] per-block maxima of the last step
     StreamDev *dst = nullptr;
     int *dfv = nullptr;
     size_t state_bytes_per_stream = 0;
@@ -988,9 +1002,10 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     const size_t dout_b = align_up(B * b->out_block + b->out_pad, 256);
     const size_t y_b = align_up(B * f->nout * T * N * sizeof(float2), 256);
     const size_t max_b = align_up(B * sizeof(float), 256);
+    const size_t bmax_b = align_up(B * (size_t)T * sizeof(float), 256);
     const size_t st_b = align_up(B * sizeof(StreamDev), 256);
     const size_t fv_b = align_up(B * sizeof(int), 256);
-    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + st_b + fv_b;
+    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + bmax_b + st_b + fv_b;
     cudaError_t e = cudaMalloc(&b->dmem, total);
     if (e != cudaSuccess) {
         fail(FCV_E_ALLOC, "cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
@@ -1007,6 +1022,7 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     // so that one device->host copy brings back both
     b->maxv = shared_host_buffer ? (float *)(b->dout + B * b->out_block) : (float *)p;
     p += max_b;
+    b->bmax = (float *)p; p += bmax_b;
     b->dst = (StreamDev *)p; p += st_b;
     b->dfv = (int *)p; p += fv_b;
     b->state_bytes_per_stream = (size_t)f->ninp * b->R * N * sizeof(float2);
@@ -1019,6 +1035,7 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
         hs[s].din = b->din + s * b->in_block;
         hs[s].dout = b->dout + s * b->out_block;
         hs[s].maxv = b->maxv + s;
+        hs[s].bmax = b->bmax + s * (size_t)T;
     }
     ok = ok && cudaMemcpy(b->dst, hs.data(), B * sizeof(StreamDev), cudaMemcpyHostToDevice) == cudaSuccess;
     if (shared_host_buffer) {
@@ -1399,6 +1416,15 @@ extern "C" int fcv_batch_get_max(fcv_batch *b, float *max_out) {
     int rc = fcv_batch_sync(b);
     if (rc) return rc;
     CU_TRY(cudaMemcpy(max_out, b->maxv, (size_t)b->B * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int fcv_batch_get_block_max(fcv_batch *b, float *max_out) {
+    if (!b || !max_out) return fail(FCV_E_PARAM, "null argument");
+    CU_TRY(cudaSetDevice(b->f->device));
+    int rc = fcv_batch_sync(b);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(max_out, b->bmax, (size_t)b->B * b->T * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

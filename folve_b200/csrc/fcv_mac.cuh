@@ -34,6 +34,7 @@ struct StreamDev {
     const void *din;  // interleaved PCM in,  [N][ninp] wire format
     void *dout;       // interleaved PCM out, [N][nout] wire format
     float *maxv;    // running signed maximum
+    float *bmax;    // [T] signed maximum of each block of the last step (valid frames only)
 };
 
 constexpr int MAC_NO_MAX = 8;

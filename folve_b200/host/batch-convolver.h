@@ -8,6 +8,11 @@
 // convolve-file-handler.cc:370-424) -- here every active chain contributes one
 // block per step and all blocks go through ONE fcv_batch launch sequence.
 //
+// With blocks_per_step = T > 1 every chain contributes up to T consecutive blocks per step
+// (the time-tiled MAC then reads each input spectrum once for all T outputs that need it);
+// a step of a chain ends early wherever the per-file path would continue from a reset
+// processor.
+//
 // Results are those of the per-file SoundProcessor path, including the gapless
 // hand-off rules of PassoverProcessor (convolve-file-handler.cc:328-351) and
 // their corner cases:
@@ -45,8 +50,9 @@ typedef std::vector<ChainFile> Chain;  // files of one directory, alphabetical o
 class BatchConvolver {
 public:
     // `slots` chains are in flight at once.  NULL on configuration or GPU failure.
+    // blocks_per_step: 1, 2, 4 or 8 consecutive blocks of every chain per GPU step.
     static BatchConvolver *Create(const std::string &config_file, int samplerate, int channels, int slots,
-                                  bool gapless, int device);
+                                  bool gapless, int device, int blocks_per_step = 1);
     ~BatchConvolver();
 
     int fragment_size() const { return fragm_; }
@@ -63,12 +69,14 @@ public:
 private:
     BatchConvolver() {}
     struct Slot;
-    void FillSlot(Slot &s, float *in_block);
-    void DrainSlot(Slot &s, const float *out_block, float running_max);
+    struct BlockPlan;
+    void FillBlock(Slot &s, BlockPlan &b, float *in_block);
+    void FillSlot(Slot &s, float *in_step);
+    void DrainSlot(Slot &s, const float *out_step, const float *block_max);
 
     fcv_filter *filter_ = nullptr;
     fcv_batch *batch_ = nullptr;
-    int fragm_ = 0, ninp_ = 0, nout_ = 0, slots_ = 0;
+    int fragm_ = 0, ninp_ = 0, nout_ = 0, slots_ = 0, tblocks_ = 1;
     bool gapless_ = true;
     long blocks_ = 0, steps_ = 0;
 };

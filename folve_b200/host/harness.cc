@@ -237,11 +237,12 @@ int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits,
 // files of a chain in alphabetical order -- through folve_b200::BatchConvolver with
 // `slots` chains in flight.  PCM in/out is float, [frames][channels].
 // Returns the number of output channels, <0 on failure.
-int fh_run_library(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
-                   int nfiles, const int *chain_of_file, const float *const *pcm, const long *frames,
-                   float *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags, long *steps_out) {
+int fh_run_library_tiled(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
+                         int nfiles, const int *chain_of_file, const float *const *pcm, const long *frames,
+                         float *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
+                         long *steps_out, int blocks_per_step) {
     folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, slots, gapless != 0, SoundProcessor::Device());
+        config_file, samplerate, channels, slots, gapless != 0, SoundProcessor::Device(), blocks_per_step);
     if (!bc) return -1;
     const int nout = bc->output_channels();
     std::vector<folve_b200::Chain> chains;
@@ -271,6 +272,13 @@ int fh_run_library(const char *config_file, int samplerate, int channels, int ga
     if (steps_out) *steps_out = bc->steps();
     delete bc;
     return ok ? nout : -2;
+}
+
+int fh_run_library(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
+                   int nfiles, const int *chain_of_file, const float *const *pcm, const long *frames,
+                   float *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags, long *steps_out) {
+    return fh_run_library_tiled(config_file, samplerate, channels, gapless, slots, threads, nfiles, chain_of_file, pcm,
+                                frames, out_pcm, out_frames, max_values, gapless_flags, steps_out, 1);
 }
 #endif
 

@@ -193,6 +193,11 @@ int fcv_batch_sync(fcv_batch *b);
  * gapless album chain), read its running signed maximum. */
 int fcv_batch_reset_slot(fcv_batch *b, int slot);
 int fcv_batch_get_max(fcv_batch *b, float *max_out /* [nstreams] */);
+/* Signed maximum (>= 0, over all output channels, valid frames only) of every block of
+ * the last step: what SoundProcessor::Process() adds to max_out_value_observed_ block by
+ * block (sound-processor.cc:120-123), so that a caller stepping several blocks at once
+ * can still tell the running maximum at the block where a file ended. */
+int fcv_batch_get_block_max(fcv_batch *b, float *max_out /* [nstreams][blocks_per_step] */);
 
 /* cudaStream_t the batch launches on (as void*), for CUDA-event timing by the caller. */
 void *fcv_batch_cuda_stream(fcv_batch *b);

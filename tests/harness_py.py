@@ -84,12 +84,13 @@ class Harness:
             res.append(flat.reshape(oframes[k], nout).copy())
         return res, list(mx), list(flags)
 
-    def run_library(self, config_file, samplerate, channels, chains, gapless=True, slots=4, threads=2):
+    def run_library(self, config_file, samplerate, channels, chains, gapless=True, slots=4, threads=2,
+                    blocks_per_step=1):
         """chains: list of lists of [frames, channels] float32 arrays.  Product only.
         Returns (outputs per chain per file, max values, flags, steps)."""
         if not hasattr(self.L, "fh_run_library"):
             raise RuntimeError("fh_run_library is only in the product harness")
-        fn = self.L.fh_run_library
+        fn = self.L.fh_run_library_tiled
         fn.restype = C.c_int
         files = [np.ascontiguousarray(f, np.float32) for c in chains for f in c]
         cof = [ci for ci, c in enumerate(chains) for _ in c]
@@ -105,9 +106,9 @@ class Harness:
         steps = C.c_long(0)
         fn.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                        C.POINTER(fp), C.POINTER(C.c_long), C.POINTER(fp), C.POINTER(C.c_long),
-                       C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_long)]
+                       C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_long), C.c_int]
         rc = fn(str(config_file).encode(), samplerate, channels, 1 if gapless else 0, slots, threads, n,
-                (C.c_int * n)(*cof), pin, frames, pout, oframes, mx, flags, C.byref(steps))
+                (C.c_int * n)(*cof), pin, frames, pout, oframes, mx, flags, C.byref(steps), blocks_per_step)
         if rc < 0:
             raise RuntimeError(f"fh_run_library failed ({rc})")
         nout = rc
