@@ -227,7 +227,7 @@ def run_reference(args, rank, world):
                                    f"thread; {what}"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -249,7 +249,21 @@ def ncu_traffic(wl_name, streams, T=1):
         return None
 
 
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything libraries print on
+    file descriptor 1 meanwhile (NCCL's version banner at N > 1) was redirected to stderr."""
+    _STDOUT.write(json.dumps(line) + "\n")
+    _STDOUT.flush()
+
+
+_STDOUT = sys.stdout
+
+
 def main():
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -442,7 +456,7 @@ def main():
                         "value": a / w, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
                         "what": "SoundProcessor::FillBuffer/WriteProcessed block loop, one file per host thread, "
                                 "one synchronous fcv_stream_process per block"}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     batch.close()
     flt.close()

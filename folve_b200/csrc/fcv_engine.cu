@@ -152,6 +152,46 @@ __device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables 
     return lmax;
 }
 
+// DC and Nyquist are real bins sharing entry 0 of a spectrum: their products are two real
+// multiply-accumulates over the partition history (the MAC kernels treat entry 0 as one
+// complex value, which the inverse transform ignores).  One warp per (stream, output,
+// block of the step), lanes split the partitions; the result is stored as entry 0 of the
+// complex N-point sequence the inverse transform starts from: (dc + ny, dc - ny).
+// Runs between the forward transform and the inverse one, off their critical paths.
+__global__ void __launch_bounds__(256)
+dcny_kernel(const StreamDev *__restrict__ st, const TTPair *__restrict__ pairs, const int *__restrict__ pair_off,
+            const int *__restrict__ tt_rows, const float2 *__restrict__ H, float2 *__restrict__ zc0, int nwarps,
+            int nout, int P, int R, int T, int pt, int M) {
+    const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    const int bt = w % T, o = (w / T) % nout, b = w / (T * nout);
+    const float2 *xring = st[b].xring;
+    int newest = pt + bt;
+    if (newest >= R) newest -= R;
+    float dc = 0.f, ny = 0.f;
+    for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
+        const int inp = pairs[p].inp;
+        const int *rows = tt_rows + pairs[p].rowbase;
+        for (int j = lane; j < P; j += 32) {
+            const int row = rows[j];
+            if (row >= 0) {
+                int slot = newest - j;
+                if (slot < 0) slot += R;
+                const float2 x = xring[(size_t)(inp * R + slot) * M];
+                const float2 h = H[(size_t)row * M];
+                dc = fmaf(x.x, h.x, dc);
+                ny = fmaf(x.y, h.y, ny);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        dc += __shfl_xor_sync(0xffffffffu, dc, d);
+        ny += __shfl_xor_sync(0xffffffffu, ny, d);
+    }
+    if (lane == 0) zc0[w] = make_float2(dc + ny, dc - ny);
+}
+
 // Inverse transform of every (stream, output channel) with fused DC/Nyquist
 // products, overlap-add, tail save, re-interleave, float/int conversion and
 // running signed maximum.  The T blocks of a step are done one after the other
@@ -159,9 +199,7 @@ __device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables 
 template <int LOG2N>
 __global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
 inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
-                  const float2 *__restrict__ Y, const TTPair *__restrict__ pairs,
-                  const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
-                  const float2 *__restrict__ H, int nout, int P, int R, int T, int pt, int out_fmt) {
+                  const float2 *__restrict__ Y, const float2 *__restrict__ zc0, int nout, int T, int out_fmt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
     __shared__ float red[32];
@@ -177,37 +215,8 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     for (int bt = 0; bt < T; bt++) {
         int frames = fvb - bt * N;
         frames = frames < 0 ? 0 : (frames > N ? N : frames);
-        int newest = pt + bt;
-        if (newest >= R) newest -= R;
-        // DC and Nyquist are real bins sharing entry 0: redo their products as two
-        // real multiply-accumulates (the MAC kernel treated the entry as complex).
-        float dc = 0.f, ny = 0.f;
-        if (tid < 32) {
-            for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
-                const int inp = pairs[p].inp;
-                const int *rows = tt_rows + pairs[p].rowbase;
-                for (int j = tid; j < P; j += 32) {
-                    const int row = rows[j];
-                    if (row >= 0) {
-                        int slot = newest - j;
-                        if (slot < 0) slot += R;
-                        const float2 x = s.xring[(size_t)(inp * R + slot) * M];
-                        const float2 h = H[(size_t)row * M];
-                        dc = fmaf(x.x, h.x, dc);
-                        ny = fmaf(x.y, h.y, ny);
-                    }
-                }
-            }
-        }
         inv_load<LOG2N>(sm, tb, Y + (((size_t)b * nout + o) * T + bt) * M);
-        if (tid < 32) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                dc += __shfl_xor_sync(0xffffffffu, dc, d);
-                ny += __shfl_xor_sync(0xffffffffu, ny, d);
-            }
-            if (tid == 0) sm[0] = make_float2(dc + ny, dc - ny);  // Zc[0] from the two real bins
-        }
+        if (tid == 0) sm[0] = zc0[((size_t)b * nout + o) * T + bt];  // Zc[0] from the two real bins (dcny_kernel)
         __syncthreads();
 
         inv_body<LOG2N>(sm, tb);
@@ -287,12 +296,10 @@ fwd13_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, f13::T
 }
 
 // Inverse transform of every (stream, output channel), T blocks one after the other.
-template <int FMT>
+template <int FMT, bool PF>
 __global__ void __launch_bounds__(F13_INV_NT, f13_min_ctas(F13_INV_NT))
 inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, f13::Tables tb,
-                    const float2 *__restrict__ Y, const TTPair *__restrict__ pairs,
-                    const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
-                    const float2 *__restrict__ H, int nout, int P, int R, int T, int pt) {
+                    const float2 *__restrict__ Y, const float2 *__restrict__ zc0, int nout, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c2 *sm = reinterpret_cast<c2 *>(smem_raw);
     constexpr int NT = F13_INV_NT;
@@ -306,52 +313,19 @@ inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
     const size_t wire = FMT == PCM_S16 ? 2 : 4;
     float lmax = 0.0f;
 
-    // DC and Nyquist are real bins sharing entry 0: redo their products as two real
-    // multiply-accumulates (the MAC kernel treated the entry as complex).  Lanes of warp 0
-    // split the partitions.  The scattered X entries of block bt+1 are requested into L2
-    // while block bt is being transformed, so only a CTA's first block waits on HBM for them.
-    auto dcny = [&](int bt, bool prefetch_only, float &dc, float &ny) {
-        int newest = pt + bt;
-        if (newest >= R) newest -= R;
-        for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
-            const int inp = pairs[p].inp;
-            const int *rows = tt_rows + pairs[p].rowbase;
-            for (int j = tid; j < P; j += 32) {
-                const int row = rows[j];
-                if (row >= 0) {
-                    int slot = newest - j;
-                    if (slot < 0) slot += R;
-                    const float2 *xp = s.xring + (size_t)(inp * R + slot) * M;
-                    if (prefetch_only) {
-                        prefetch_l2(xp);
-                    } else {
-                        const float2 x = *xp;
-                        const float2 hh = H[(size_t)row * M];
-                        dc = fmaf(x.x, hh.x, dc);
-                        ny = fmaf(x.y, hh.y, ny);
-                    }
-                }
-            }
-        }
-    };
-
     for (int bt = 0; bt < T; bt++) {
         int frames = fvb - bt * N;
         frames = frames < 0 ? 0 : (frames > N ? N : frames);
-        float dc = 0.f, ny = 0.f;
-        if (tid < 32) {
-            if (bt + 1 < T) dcny(bt + 1, true, dc, ny);
-            dcny(bt, false, dc, ny);
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                dc += __shfl_xor_sync(0xffffffffu, dc, d);
-                ny += __shfl_xor_sync(0xffffffffu, ny, d);
-            }
-        }
+        // entry 0 of the sequence to transform comes from the two real bins (dcny_kernel)
+        const float2 z0 = tid == 0 ? zc0[((size_t)b * nout + o) * T + bt] : make_float2(0.f, 0.f);
         const float2 *yrow = Y + (((size_t)b * nout + o) * T + bt) * M;
+        if (PF && bt + 1 < T) {  // the next block's spectrum row (64 KB) is requested into L2 now
+#pragma unroll
+            for (int i = 0; i < (M * 8 / 128) / NT; i++) prefetch_l2(yrow + M + (size_t)(tid + i * NT) * 16);
+        }
 #pragma unroll 1
         for (int j = tid; j < 256; j += NT) {
-            if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(dc + ny, dc - ny), j);  // Zc[0] from the two real bins
+            if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), j);
             else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, j - 128);
         }
         __syncthreads();
@@ -529,7 +503,8 @@ static int set_attrs13() {
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<FMT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<FMT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<FMT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
-    CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     return 0;
 }
 
@@ -915,6 +890,7 @@ struct fcv_batch {
     size_t out_pad = 0;                  // extra bytes after device_out (single-stream max mirror)
     unsigned long long step = 0;         // blocks processed so far (ring slot = step % ring)
     bool per_block_max = false;          // single-stream mode: maxv is the maximum of the last block only
+    int num_sms = 148;                   // SMs of the device (persistent grids)
     // device
     unsigned char *dmem = nullptr;       // one slab
     float2 *xring = nullptr;
@@ -923,6 +899,7 @@ struct fcv_batch {
     float2 *Y = nullptr;
     float *maxv = nullptr;
     float *bmax = nullptr;               // [B][T] per-block maxima of the last step
+    float2 *zc0 = nullptr;               // [B][nout][T] entry 0 of the sequences to inverse-transform (dcny_kernel)
     StreamDev *dst = nullptr;
     int *dfv = nullptr;
     size_t state_bytes_per_stream = 0;
@@ -995,6 +972,8 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     b->out_block = (size_t)T * N * f->nout * pcm_bytes(out_fmt);
     b->out_pad = 256;
     b->per_block_max = shared_host_buffer;
+    if (cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, f->device) != cudaSuccess || b->num_sms < 1)
+        b->num_sms = 148;
 
     const size_t xring_b = align_up(B * f->ninp * b->R * N * sizeof(float2), 256);
     const size_t tail_b = align_up(B * f->nout * N * sizeof(float), 256);
@@ -1005,7 +984,8 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     const size_t bmax_b = align_up(B * (size_t)T * sizeof(float), 256);
     const size_t st_b = align_up(B * sizeof(StreamDev), 256);
     const size_t fv_b = align_up(B * sizeof(int), 256);
-    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + bmax_b + st_b + fv_b;
+    const size_t zc_b = align_up(B * f->nout * (size_t)T * sizeof(float2), 256);
+    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + bmax_b + st_b + fv_b + zc_b;
     cudaError_t e = cudaMalloc(&b->dmem, total);
     if (e != cudaSuccess) {
         fail(FCV_E_ALLOC, "cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
@@ -1025,6 +1005,7 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     b->bmax = (float *)p; p += bmax_b;
     b->dst = (StreamDev *)p; p += st_b;
     b->dfv = (int *)p; p += fv_b;
+    b->zc0 = (float2 *)p; p += zc_b;
     b->state_bytes_per_stream = (size_t)f->ninp * b->R * N * sizeof(float2);
 
     bool ok = cudaMemset(b->dmem, 0, total) == cudaSuccess;
@@ -1102,12 +1083,17 @@ static bool launch_mac_tma(const fcv_batch *b, int off, int cnt, int newest, cud
     if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return false;
-    dim3 grid(M4 / tma::TPB, (cnt + S - 1) / S, f->nout);
+    // one CTA per work item; FCV_MAC_PERSIST=n runs a persistent grid of n CTAs per SM instead
+    // (measured 5 % slower on SantaLucia x 1024 streams: 1.05 vs 1.00 ms, profiles/r01_experiments.md)
+    static const int persist = getenv("FCV_MAC_PERSIST") ? atoi(getenv("FCV_MAC_PERSIST")) : 0;
+    const int ntiles = M4 / tma::TPB, ngroups = (cnt + S - 1) / S, nitems = ntiles * ngroups * f->nout;
+    int grid = nitems;
+    if (persist > 0 && b->num_sms * persist < nitems) grid = b->num_sms * persist;
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
     tma::mac_tma_kernel<T, S, NS><<<grid, tma::THREADS, smem, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off,
                                                                      f->dtt_rows, H, Y, M4, f->ring, b->R, newest,
-                                                                     f->nout, f->nrows);
+                                                                     f->nout, f->nrows, ntiles, ngroups, nitems);
     return true;
 }
 
@@ -1193,21 +1179,31 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     }
     if (ev) cudaEventRecord(ev[2], q);
     const float2 *Y = b->Y + (size_t)off * f->nout * T * f->fragm;
+    float2 *zc0 = b->zc0 + (size_t)off * f->nout * T;
+    if (only & 4) {
+        const int nwarps = cnt * f->nout * T;
+        dcny_kernel<<<(nwarps + 7) / 8, 256, 0, q>>>(b->dst + off, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, zc0,
+                                                     nwarps, f->nout, f->ring, R, T, pt, f->fragm);
+    }
     if (!(only & 4)) {
     } else if (k13) {
-#define FCV_INV13_ARGS b->dst + off, fv, f->tb13, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout, f->ring, R, T, pt
+#define FCV_INV13_ARGS b->dst + off, fv, f->tb13, Y, zc0, f->nout, T
         const dim3 grid(f->nout, cnt);
         const size_t smem = 2 * f13::HALF_BYTES;
-        if (b->out_fmt == PCM_F32) inv13_stream_kernel<PCM_F32><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS);
-        else if (b->out_fmt == PCM_S16) inv13_stream_kernel<PCM_S16><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS);
-        else inv13_stream_kernel<PCM_S24><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS);
+        static const bool pf = !(getenv("FCV_INV_PF") && atoi(getenv("FCV_INV_PF")) == 0);
+#define FCV_INV13_LAUNCH(F) \
+        do { if (pf && T > 1) inv13_stream_kernel<F, true><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS); \
+             else inv13_stream_kernel<F, false><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS); } while (0)
+        if (b->out_fmt == PCM_F32) FCV_INV13_LAUNCH(PCM_F32);
+        else if (b->out_fmt == PCM_S16) FCV_INV13_LAUNCH(PCM_S16);
+        else FCV_INV13_LAUNCH(PCM_S24);
+#undef FCV_INV13_LAUNCH
 #undef FCV_INV13_ARGS
     } else
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
-                                  b->dst + off, fv, tb, Y, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, f->nout,
-                                  f->ring, R, T, pt, b->out_fmt)));
+                                  b->dst + off, fv, tb, Y, zc0, f->nout, T, b->out_fmt)));
     if (ev) cudaEventRecord(ev[3], q);
-    g_launches += 3;
+    g_launches += 4;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(FCV_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
@@ -1514,9 +1510,9 @@ extern "C" int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_in
         CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)frames_valid * f->ninp * sizeof(float), cudaMemcpyHostToDevice, q));
     int rc = run_kernels(b, 0, 1, b->dfv, q, nullptr);
     if (rc) return rc;
-    b->step++;
     // one copy brings back the whole output block and the running maximum behind it
     CU_TRY(cudaMemcpyAsync(b->hin, b->dout, b->out_block + sizeof(float), cudaMemcpyDeviceToHost, q));
+    b->step++;
     CU_TRY(cudaStreamSynchronize(q));
     if (max_inout) {
         float m;

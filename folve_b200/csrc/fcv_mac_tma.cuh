@@ -11,7 +11,10 @@
 // registers or issue slots (no LDG, no L2 prefetch, no address arithmetic in the math
 // warps), so the pipeline can run NS rows ahead of the arithmetic.
 //
-//   grid : x = spectrum tiles of 128 float4 (2 KB), y = ceil(streams / S), z = outputs
+//   work item = (spectrum tile of 128 float4 = 2 KB, group of S streams, output), tile fastest
+//   grid : persistent, 1-D: CTA c takes items c, c + gridDim.x, ...; the producer runs ahead of
+//          the consumers across item boundaries, so the pipeline is filled once per CTA and the
+//          next item's rows arrive while the consumers store the current item's Y
 //   block: 160 threads = 4 consumer warps (one float4 column each) + 1 producer warp
 //   smem : NS stages x (S + 1) x 2 KB
 #pragma once
@@ -82,12 +85,11 @@ __global__ void __launch_bounds__(THREADS, min_ctas(T, S))
 mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__restrict__ pairs,
                const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
                const float4 *__restrict__ H, float4 *__restrict__ Y, int M4, int P, int R, int newest_slot,
-               int nout, int zero_row) {
+               int nout, int zero_row, int ntiles, int ngroups, int nitems) {
     constexpr int STAGE_BYTES = (S + 1) * TILE_BYTES;
     extern __shared__ __align__(128) unsigned char stages[];
     __shared__ uint64_t full[NS], empty[NS];
 
-    const int tile = blockIdx.x, b0 = blockIdx.y * S, o = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -100,12 +102,16 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
     __syncthreads();
 
     const int D = P + T - 1;
-    const int p0 = pair_off[o], p1 = pair_off[o + 1];
     const size_t rowb = (size_t)M4 * 16;
 
     if (warp == CONSUMER_WARPS) {
-        // ---- producer: one lane walks the same (pair, step) sequence as the consumers
+        // ---- producer: one lane walks the same (item, pair, step) sequence as the consumers
         if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
+            const int p0 = pair_off[o], p1 = pair_off[o + 1];
             const unsigned char *xbase[S];
 #pragma unroll
             for (int s = 0; s < S; s++) {
@@ -113,8 +119,6 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                 xbase[s] = reinterpret_cast<const unsigned char *>(st[b].xring) + (size_t)tile * TILE_BYTES;
             }
             const unsigned char *hbase = reinterpret_cast<const unsigned char *>(H) + (size_t)tile * TILE_BYTES;
-            int stage = 0;
-            uint32_t phase = 0;
             for (int p = p0; p < p1; p++) {
                 const int inp = pairs[p].inp;
                 const int *rows = tt_rows + pairs[p].rowbase;
@@ -140,20 +144,25 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                     }
                 }
             }
+            }
         }
         return;
     }
 
     // ---- consumers
+    int stage = 0;
+    uint32_t phase = 0;
+    const unsigned char *mine = stages + (size_t)threadIdx.x * 16;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
+    const int p0 = pair_off[o], p1 = pair_off[o + 1];
     c2 acc[T][S][2];
 #pragma unroll
     for (int t = 0; t < T; t++)
 #pragma unroll
         for (int s = 0; s < S; s++) acc[t][s][0] = acc[t][s][1] = 0ull;
 
-    int stage = 0;
-    uint32_t phase = 0;
-    const unsigned char *mine = stages + (size_t)threadIdx.x * 16;
     for (int p = p0; p < p1; p++) {
         c2x2 hw[T];
 #pragma unroll
@@ -214,6 +223,7 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                 v.b = acc[t][s][1];
                 __stcs(Y + (((size_t)(b0 + s) * nout + o) * T + t) * (size_t)M4 + e4, c2x2_to(v));
             }
+    }
 }
 
 }  // namespace tma

@@ -55,7 +55,9 @@ def main():
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`)\n\n"
                 "Command: `python bench.py --steps 20 --warmup 3 --no-cpu-baseline --skip-e2e` (santalucia, 1024 streams;\n"
-                "r01: `--blocks-per-step 1`, r01tt: 4 blocks per step).\n"
+                "r01: `--blocks-per-step 1`, r01tt: 4 blocks per step, r01f: 8 blocks per step = bench.py's default).\n"
+                "Rows with 128 streams in the grid are the 8 chunks of the one warm-up call through the host-staging\n"
+                "path (fcv_batch_process); the 1024-stream rows are the device-resident loop that `value` times.\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's\n"
                 "`kernel_ms_per_step`, not absolutes.\n\n| kernel | grid | launches | mean us | share of listed time |\n|---|---|---|---|---|\n")
         for (k, grid), v in agg.items():

@@ -3,7 +3,13 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
-int main() {
+#include <cstdlib>
+#include <time.h>
+// usage: pcie_probe [iters [sync]] -- with "sync" the measurement starts on the next multiple of 2 s of the
+// wall clock, so that probes started together on several GPUs really overlap
+int main(int argc, char **argv) {
+    const int iters_arg = argc > 1 ? atoi(argv[1]) : 10;
+    const bool wall_sync = argc > 2;
     const size_t n = 64u << 20;
     void *h0, *h1, *d0, *d1;
     cudaHostAlloc(&h0, n, cudaHostAllocDefault);
@@ -18,8 +24,16 @@ int main() {
     for (int mode = 0; mode < 3; mode++) {
         for (int rep = 0; rep < 3; rep++) {
             cudaDeviceSynchronize();
+            if (wall_sync && rep == 2) {
+                // all probes started within the same 8 s window agree on `base`; mode m starts at base + 2 m
+                static time_t base = 0;
+                timespec ts;
+                clock_gettime(CLOCK_REALTIME, &ts);
+                if (!base) base = ((ts.tv_sec + 1) / 8 + 1) * 8;
+                do clock_gettime(CLOCK_REALTIME, &ts); while (ts.tv_sec < base + 2 * mode);
+            }
             cudaEventRecord(a, s0);
-            const int iters = 10;
+            const int iters = rep == 2 ? iters_arg : 3;
             for (int i = 0; i < iters; i++) {
                 if (mode == 0 || mode == 2) cudaMemcpyAsync(d0, h0, n, cudaMemcpyHostToDevice, s0);
                 if (mode == 1 || mode == 2) cudaMemcpyAsync(h1, d1, n, cudaMemcpyDeviceToHost, mode == 2 ? s1 : s0);
