@@ -1073,14 +1073,14 @@ static void launch_mac_tt_s(const fcv_batch *b, int off, int cnt, int newest, cu
 }
 
 // TMA-staged variant (fcv_mac_tma.cuh).  Returns false when the shape is not covered.
-template <int T, int S, int NS>
+template <int T, int S, int NS, int MC = tma::min_ctas(T, S)>
 static bool launch_mac_tma(const fcv_batch *b, int off, int cnt, int newest, cudaStream_t q) {
     const fcv_filter *f = b->f;
     const int M4 = f->fragm / 2;
     if (M4 % tma::TPB != 0 || cnt < S) return false;
     const size_t smem = tma::smem_bytes(S, NS);
     // dynamic + static shared memory exceeds the 48 KB default; the attribute is per device
-    if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return false;
     // one CTA per work item; FCV_MAC_PERSIST=n runs a persistent grid of n CTAs per SM instead
@@ -1091,7 +1091,7 @@ static bool launch_mac_tma(const fcv_batch *b, int off, int cnt, int newest, cud
     if (persist > 0 && b->num_sms * persist < nitems) grid = b->num_sms * persist;
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * T * f->fragm);
-    tma::mac_tma_kernel<T, S, NS><<<grid, tma::THREADS, smem, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off,
+    tma::mac_tma_kernel<T, S, NS, MC><<<grid, tma::THREADS, smem, q>>>(b->dst + off, cnt, f->dpairs, f->dpair_off,
                                                                      f->dtt_rows, H, Y, M4, f->ring, b->R, newest,
                                                                      f->nout, f->nrows, ntiles, ngroups, nitems);
     return true;

@@ -80,8 +80,8 @@ __host__ __device__ constexpr size_t smem_bytes(int S, int NS) { return (size_t)
 // CTAs per SM the register allocation is held to (T * S accumulators + T window entries)
 __host__ __device__ constexpr int min_ctas(int T, int S) { return T * S >= 16 ? 3 : 4; }
 
-template <int T, int S, int NS>
-__global__ void __launch_bounds__(THREADS, min_ctas(T, S))
+template <int T, int S, int NS, int MC = min_ctas(T, S)>
+__global__ void __launch_bounds__(THREADS, MC)
 mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__restrict__ pairs,
                const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
                const float4 *__restrict__ H, float4 *__restrict__ Y, int M4, int P, int R, int newest_slot,
