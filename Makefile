@@ -9,7 +9,7 @@ LIB  = folve_b200/libfolve_b200.so
 
 all: $(LIB)
 
-$(LIB): $(CSRC)/fcv_engine.cu $(CSRC)/fcv_fft.cuh $(CSRC)/fcv_mac.cuh $(CSRC)/fcv_c2.cuh include/folve_b200.h
+$(LIB): $(CSRC)/fcv_engine.cu $(wildcard $(CSRC)/*.cuh) include/folve_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/fcv_engine.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "error|warning" $(CSRC)/ptxas.log || true
 

@@ -5,9 +5,10 @@
 // blocks of a stream the window of P+T-1 ring slots is read once, newest first, every X
 // row feeds all T accumulators, the filter rows slide through a register window.  What
 // changes is who moves the data: one producer warp issues 2 KB bulk copies (one per
-// stream row tile and one for the filter row tile) into a ring of NS shared-memory stages,
-// completion is signalled on an mbarrier per stage, and the four consumer warps only
-// execute  try_wait / LDS.128 / FFMA2 / arrive.  Loads in flight no longer occupy
+// stream row tile and one for the filter row tile) into a ring of NS shared-memory stages
+// (NS lanes, one ring revolution at a time, a row each), completion is signalled on an
+// mbarrier per stage, and the four consumer warps only execute
+// try_wait / LDS.128 / FFMA2 / elected arrive.  Loads in flight no longer occupy
 // registers or issue slots (no LDG, no L2 prefetch, no address arithmetic in the math
 // warps), so the pipeline can run NS rows ahead of the arithmetic.
 //
@@ -39,9 +40,6 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -63,9 +61,40 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ c2x2 lds_c2x2(const unsigned char *p) {
+// The same operations on shared-window addresses held in registers.  The addresses are made
+// opaque to the compiler once per kernel (hold_u32): at the 128-register cap ptxas otherwise
+// rematerialises them in every row (S2R SR_CgaCtaId / SR_TID + LEA chains in front of each
+// try_wait and arrive).
+__device__ __forceinline__ uint32_t hold_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// one elected lane of the (converged) warp arrives; elect.sync is also the warp-level
+// rendezvous that orders every lane's shared-memory reads of the stage before the release.
+// Predicated, so the row loop carries no divergent branch.
+__device__ __forceinline__ void mbar_arrive_elect_a(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ c2x2 lds_c2x2_a(uint32_t p) {
     c2x2 v;
-    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.a), "=l"(v.b) : "r"(smem_u32(p)));
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.a), "=l"(v.b) : "r"(p));
     return v;
 }
 
@@ -88,7 +117,8 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                int nout, int zero_row, int ntiles, int ngroups, int nitems) {
     constexpr int STAGE_BYTES = (S + 1) * TILE_BYTES;
     extern __shared__ __align__(128) unsigned char stages[];
-    __shared__ uint64_t full[NS], empty[NS];
+    __shared__ uint64_t bars[2 * NS];
+    uint64_t *const full = bars, *const empty = bars + NS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -105,11 +135,14 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
     const size_t rowb = (size_t)M4 * 16;
 
     if (warp == CONSUMER_WARPS) {
-        // ---- producer: one lane walks the same (item, pair, step) sequence as the consumers
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        // ---- producer: NS lanes of the warp take the NS rows of one ring revolution, one row
+        // each -- every lane waits for its own stage to be released and issues that row's copies.
+        // The address arithmetic and the barrier hand-shake are executed once per NS rows
+        // instead of once per row: the producer shares its scheduler with consumer warp 0, and
+        // as a single lane walking the rows (~90 instructions each) it, not HBM, paced the kernel.
+        static_assert(NS <= 32, "one lane per stage");
+        unsigned it0 = 0;  // rows issued so far: row number `it` lives in stage it % NS, phase (it / NS) & 1
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
             const int p0 = pair_off[o], p1 = pair_off[o + 1];
             const unsigned char *xbase[S];
@@ -122,28 +155,27 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
             for (int p = p0; p < p1; p++) {
                 const int inp = pairs[p].inp;
                 const int *rows = tt_rows + pairs[p].rowbase;
-                int slot = newest_slot;
-                int rown = rows[0];  // filter row of the next step, fetched one step early
-                for (int d = 0; d < D; d++) {
-                    const int rowd = rown;
-                    if (d + 1 < P) rown = rows[d + 1];
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char *dst = stages + (size_t)stage * STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], (uint32_t)((d < P ? S + 1 : S) * TILE_BYTES));
-                    const size_t xoff = ((size_t)inp * R + slot) * rowb;
+                for (int g0 = 0; g0 < D; g0 += NS) {
+                    const int d = g0 + lane;
+                    if (lane < NS && d < D) {
+                        const unsigned it = it0 + d;
+                        const int stage = it % NS;
+                        const uint32_t phase = (it / NS) & 1;
+                        int slot = newest_slot - d;   // d < D = R: at most one wrap
+                        if (slot < 0) slot += R;
+                        int row = d < P ? rows[d] : 0;
+                        if (row < 0) row = zero_row;
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        unsigned char *dst = stages + (size_t)stage * STAGE_BYTES;
+                        mbar_expect_tx(&full[stage], (uint32_t)((d < P ? S + 1 : S) * TILE_BYTES));
+                        const size_t xoff = ((size_t)inp * R + slot) * rowb;
 #pragma unroll
-                    for (int s = 0; s < S; s++) bulk_g2s(dst + s * TILE_BYTES, xbase[s] + xoff, TILE_BYTES, &full[stage]);
-                    if (d < P) {
-                        const int row = rowd < 0 ? zero_row : rowd;
-                        bulk_g2s(dst + S * TILE_BYTES, hbase + (size_t)row * rowb, TILE_BYTES, &full[stage]);
+                        for (int s = 0; s < S; s++) bulk_g2s(dst + s * TILE_BYTES, xbase[s] + xoff, TILE_BYTES, &full[stage]);
+                        if (d < P) bulk_g2s(dst + S * TILE_BYTES, hbase + (size_t)row * rowb, TILE_BYTES, &full[stage]);
                     }
-                    slot = slot == 0 ? R - 1 : slot - 1;
-                    if (++stage == NS) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    __syncwarp();
                 }
-            }
+                it0 += D;
             }
         }
         return;
@@ -152,7 +184,8 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
     // ---- consumers
     int stage = 0;
     uint32_t phase = 0;
-    const unsigned char *mine = stages + (size_t)threadIdx.x * 16;
+    const uint32_t mine = hold_u32(smem_u32(stages) + threadIdx.x * 16);
+    const uint32_t bar0 = hold_u32(smem_u32(bars));
 #pragma unroll 1
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
@@ -175,14 +208,14 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
             for (int r = 0; r < T; r++) {
                 const int d = d0 + r;
                 if (!GUARD || d < D) {
-                    mbar_wait(&full[stage], phase);
-                    const unsigned char *sp = mine + (size_t)stage * STAGE_BYTES;
+                    mbar_wait_a(bar0 + 8 * stage, phase);
+                    const uint32_t sp = mine + stage * STAGE_BYTES;
                     c2x2 x[S];
 #pragma unroll
-                    for (int s = 0; s < S; s++) x[s] = lds_c2x2(sp + s * TILE_BYTES);
+                    for (int s = 0; s < S; s++) x[s] = lds_c2x2_a(sp + s * TILE_BYTES);
                     c2x2 h;
                     h.a = h.b = 0ull;
-                    if (!GUARD || d < P) h = lds_c2x2(sp + S * TILE_BYTES);
+                    if (!GUARD || d < P) h = lds_c2x2_a(sp + S * TILE_BYTES);
                     hw[(T - 1 + r) % T] = h;  // H[d]: the newest output (t = T-1) starts on partition j = d
 #pragma unroll
                     for (int t = 0; t < T; t++) {
@@ -196,8 +229,7 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                             }
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    mbar_arrive_elect_a(bar0 + 8 * (NS + stage));
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
