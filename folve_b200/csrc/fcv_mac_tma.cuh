@@ -140,8 +140,11 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
         // The address arithmetic and the barrier hand-shake are executed once per NS rows
         // instead of once per row: the producer shares its scheduler with consumer warp 0, and
         // as a single lane walking the rows (~90 instructions each) it, not HBM, paced the kernel.
+        // Row d of every (input, output) pair lives in stage d % NS, so a lane always serves the
+        // same stage and keeps that stage's phase bit; the consumers index the stages of a
+        // T-row chunk with compile-time constants when NS divides T.
         static_assert(NS <= 32, "one lane per stage");
-        unsigned it0 = 0;  // rows issued so far: row number `it` lives in stage it % NS, phase (it / NS) & 1
+        uint32_t ph = 0;   // parity of this lane's stage: flips with every row the lane issues
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
             const int p0 = pair_off[o], p1 = pair_off[o + 1];
@@ -158,14 +161,13 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                 for (int g0 = 0; g0 < D; g0 += NS) {
                     const int d = g0 + lane;
                     if (lane < NS && d < D) {
-                        const unsigned it = it0 + d;
-                        const int stage = it % NS;
-                        const uint32_t phase = (it / NS) & 1;
+                        const int stage = lane;
                         int slot = newest_slot - d;   // d < D = R: at most one wrap
                         if (slot < 0) slot += R;
                         int row = d < P ? rows[d] : 0;
                         if (row < 0) row = zero_row;
-                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_wait(&empty[stage], ph ^ 1);
+                        ph ^= 1;
                         unsigned char *dst = stages + (size_t)stage * STAGE_BYTES;
                         mbar_expect_tx(&full[stage], (uint32_t)((d < P ? S + 1 : S) * TILE_BYTES));
                         const size_t xoff = ((size_t)inp * R + slot) * rowb;
@@ -175,15 +177,14 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                     }
                     __syncwarp();
                 }
-                it0 += D;
             }
         }
         return;
     }
 
     // ---- consumers
-    int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phases = 0;   // bit s: parity of the next fill of stage s
+    constexpr bool FIXED = T % NS == 0;   // the stage of row r of a chunk is the constant r % NS
     const uint32_t mine = hold_u32(smem_u32(stages) + threadIdx.x * 16);
     const uint32_t bar0 = hold_u32(smem_u32(bars));
 #pragma unroll 1
@@ -208,7 +209,8 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
             for (int r = 0; r < T; r++) {
                 const int d = d0 + r;
                 if (!GUARD || d < D) {
-                    mbar_wait_a(bar0 + 8 * stage, phase);
+                    const int stage = FIXED ? r % NS : (d0 + r) % NS;
+                    mbar_wait_a(bar0 + 8 * stage, (phases >> stage) & 1);
                     const uint32_t sp = mine + stage * STAGE_BYTES;
                     c2x2 x[S];
 #pragma unroll
@@ -230,10 +232,7 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
                         }
                     }
                     mbar_arrive_elect_a(bar0 + 8 * (NS + stage));
-                    if (++stage == NS) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    phases ^= 1u << stage;
                 }
             }
         };
