@@ -77,7 +77,7 @@ __device__ __forceinline__ void block_max_update(float *dst, float m) {
 // into ring slot `pt` of the stream's input-spectra ring.
 template <int LOG2N>
 __global__ void __launch_bounds__(fft_threads(LOG2N, 1), FWD_MIN_CTAS)
-fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
+fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, int fv_all, FftTables tb,
                   int ninp, int R, int T, int pt, int in_fmt, int reset_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
@@ -85,7 +85,7 @@ fwd_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     // grid: x = 2 * input channel + half, y = stream, z = block of the step
     const int i = blockIdx.x >> 1, h = blockIdx.x & 1, b = blockIdx.y, bt = blockIdx.z;
     const StreamDev s = st[b];
-    int frames = (fv ? fv[b] : T * N) - bt * N;
+    int frames = (fv ? fv[b] : fv_all) - bt * N;
     frames = frames < 0 ? 0 : (frames > N ? N : frames);
     int slot = pt + bt;
     if (slot >= R) slot -= R;
@@ -198,7 +198,7 @@ dcny_kernel(const StreamDev *__restrict__ st, const TTPair *__restrict__ pairs, 
 // by the same CTA (block t+1 overlap-adds the tail block t just saved).
 template <int LOG2N>
 __global__ void __launch_bounds__(fft_threads(LOG2N), FFT_MIN_CTAS)
-inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, FftTables tb,
+inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, int fv_all, FftTables tb,
                   const float2 *__restrict__ Y, const float2 *__restrict__ zc0, int nout, int T, int out_fmt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);
@@ -208,7 +208,7 @@ inv_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, 
     const int tid = threadIdx.x;
     const int o = blockIdx.x, b = blockIdx.y;
     const StreamDev s = st[b];
-    const int fvb = fv ? fv[b] : T * N;
+    const int fvb = fv ? fv[b] : fv_all;
     float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
     float lmax = 0.0f;
 
@@ -255,14 +255,14 @@ constexpr int f13_min_ctas(int nt) { return nt >= 256 ? 2 : 3; }
 // (stream, block): PCM and twiddles are fetched once for C transforms.
 template <int FMT, int NCH, int C>
 __global__ void __launch_bounds__(128 * C, f13_min_ctas(128 * C))
-fwd13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, f13::Tables tb,
+fwd13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, int fv_all, f13::Tables tb,
                     int ninp, int R, int T, int pt, int reset_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c2 *sm = reinterpret_cast<c2 *>(smem_raw);
     constexpr int N = f13::N;
     const int h = blockIdx.x & 1, ch0 = (blockIdx.x >> 1) * C, b = blockIdx.y, bt = blockIdx.z;
     const StreamDev s = st[b];
-    int frames = (fv ? fv[b] : T * N) - bt * N;
+    int frames = (fv ? fv[b] : fv_all) - bt * N;
     frames = frames < 0 ? 0 : (frames > N ? N : frames);
     int slot = pt + bt;
     if (slot >= R) slot -= R;
@@ -298,7 +298,7 @@ fwd13_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, f13::T
 // Inverse transform of every (stream, output channel), T blocks one after the other.
 template <int FMT, bool PF>
 __global__ void __launch_bounds__(F13_INV_NT, f13_min_ctas(F13_INV_NT))
-inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, f13::Tables tb,
+inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv, int fv_all, f13::Tables tb,
                     const float2 *__restrict__ Y, const float2 *__restrict__ zc0, int nout, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c2 *sm = reinterpret_cast<c2 *>(smem_raw);
@@ -308,7 +308,7 @@ inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
     const int tid = threadIdx.x;
     const int o = blockIdx.x, b = blockIdx.y;
     const StreamDev s = st[b];
-    const int fvb = fv ? fv[b] : T * N;
+    const int fvb = fv ? fv[b] : fv_all;
     float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
     const size_t wire = FMT == PCM_S16 ? 2 : 4;
     float lmax = 0.0f;
@@ -1124,32 +1124,36 @@ static void launch_mac_tt(const fcv_batch *b, int off, int cnt, int newest, cuda
 // fragm = 8192 forward launch: stereo and mono blocks take the vector-load kernels (stereo:
 // both channels per CTA), any other channel count one channel per CTA with scalar loads.
 template <int FMT>
-static void launch_fwd13_fmt(const fcv_batch *b, int off, int cnt, const int *fv, int pt, cudaStream_t q) {
+static void launch_fwd13_fmt(const fcv_batch *b, int off, int cnt, const int *fv, int fv_all, int pt, cudaStream_t q) {
     const fcv_filter *f = b->f;
     const int rm = b->per_block_max ? 1 : 0;
     if (f->ninp == 2)
         fwd13_stream_kernel<FMT, 2, 2><<<dim3(2, cnt, b->T), 256, 2 * f13::HALF_BYTES, q>>>(
-            b->dst + off, fv, f->tb13, f->ninp, b->R, b->T, pt, rm);
+            b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
     else if (f->ninp == 1)
         fwd13_stream_kernel<FMT, 1, 1><<<dim3(2, cnt, b->T), 128, f13::HALF_BYTES, q>>>(
-            b->dst + off, fv, f->tb13, f->ninp, b->R, b->T, pt, rm);
+            b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
     else
         fwd13_stream_kernel<FMT, 0, 1><<<dim3(2 * f->ninp, cnt, b->T), 128, f13::HALF_BYTES, q>>>(
-            b->dst + off, fv, f->tb13, f->ninp, b->R, b->T, pt, rm);
+            b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
 }
-static void launch_fwd13(const fcv_batch *b, int off, int cnt, const int *fv, int pt, cudaStream_t q) {
-    if (b->in_fmt == PCM_F32) launch_fwd13_fmt<PCM_F32>(b, off, cnt, fv, pt, q);
-    else if (b->in_fmt == PCM_S16) launch_fwd13_fmt<PCM_S16>(b, off, cnt, fv, pt, q);
-    else launch_fwd13_fmt<PCM_S24>(b, off, cnt, fv, pt, q);
+static void launch_fwd13(const fcv_batch *b, int off, int cnt, const int *fv, int fv_all, int pt, cudaStream_t q) {
+    if (b->in_fmt == PCM_F32) launch_fwd13_fmt<PCM_F32>(b, off, cnt, fv, fv_all, pt, q);
+    else if (b->in_fmt == PCM_S16) launch_fwd13_fmt<PCM_S16>(b, off, cnt, fv, fv_all, pt, q);
+    else launch_fwd13_fmt<PCM_S24>(b, off, cnt, fv, fv_all, pt, q);
 }
 
 // The three launches for streams [off, off+cnt) of the batch on CUDA stream q.
-static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaStream_t q, cudaEvent_t *ev) {
+// fv_base: per-stream valid-frame counts on the device, or nullptr = `fv_all` frames for every stream
+// (-1: the whole step)
+static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaStream_t q, cudaEvent_t *ev,
+                       int fv_all = -1) {
     fcv_filter *f = b->f;
     const int T = b->T, R = b->R;
     // the step's first block goes to ring slot (step * T) mod R
     const int pt = (int)((b->step * (unsigned long long)T) % (unsigned long long)R);
     const int *fv = fv_base ? fv_base + off : nullptr;
+    if (fv_all < 0) fv_all = b->T * f->fragm;
     const FftTables tb = f->tb;
     // diagnostic: FCV_ONLY=1|2|4 (bit mask fwd|mac|inv) launches only those kernels
     static const int only = getenv("FCV_ONLY") ? atoi(getenv("FCV_ONLY")) : 7;
@@ -1157,10 +1161,10 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     const bool k13 = use_f13(f->log2n);
     if (!(only & 1)) {
     } else if (k13) {
-        launch_fwd13(b, off, cnt, fv, pt, q);
+        launch_fwd13(b, off, cnt, fv, fv_all, pt, q);
     } else
     DISPATCH_LOG2N(f->log2n, (fwd_stream_kernel<L><<<dim3(2 * f->ninp, cnt, T), fft_threads(L, 1), fft_smem_bytes(L, 1), q>>>(
-                                  b->dst + off, fv, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
+                                  b->dst + off, fv, fv_all, tb, f->ninp, R, T, pt, b->in_fmt, b->per_block_max ? 1 : 0)));
     if (ev) cudaEventRecord(ev[1], q);
     if (!(only & 2)) {
     } else if (T == 1) {
@@ -1187,7 +1191,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     }
     if (!(only & 4)) {
     } else if (k13) {
-#define FCV_INV13_ARGS b->dst + off, fv, f->tb13, Y, zc0, f->nout, T
+#define FCV_INV13_ARGS b->dst + off, fv, fv_all, f->tb13, Y, zc0, f->nout, T
         const dim3 grid(f->nout, cnt);
         const size_t smem = 2 * f13::HALF_BYTES;
         static const bool pf = !(getenv("FCV_INV_PF") && atoi(getenv("FCV_INV_PF")) == 0);
@@ -1201,7 +1205,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
 #undef FCV_INV13_ARGS
     } else
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
-                                  b->dst + off, fv, tb, Y, zc0, f->nout, T, b->out_fmt)));
+                                  b->dst + off, fv, fv_all, tb, Y, zc0, f->nout, T, b->out_fmt)));
     if (ev) cudaEventRecord(ev[3], q);
     g_launches += 4;
     cudaError_t e = cudaGetLastError();
@@ -1504,11 +1508,10 @@ extern "C" int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_in
     if (frames_valid < 0 || frames_valid > f->fragm) return fail(FCV_E_PARAM, "frames_valid out of range");
     CU_TRY(cudaSetDevice(f->device));
     cudaStream_t q = b->q[0];
-    b->hfv[0] = frames_valid;
-    CU_TRY(cudaMemcpyAsync(b->dfv, b->hfv, sizeof(int), cudaMemcpyHostToDevice, q));
     if (frames_valid > 0)
         CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)frames_valid * f->ninp * sizeof(float), cudaMemcpyHostToDevice, q));
-    int rc = run_kernels(b, 0, 1, b->dfv, q, nullptr);
+    // the valid-frame count of the one stream travels as a kernel argument
+    int rc = run_kernels(b, 0, 1, nullptr, q, nullptr, frames_valid);
     if (rc) return rc;
     // one copy brings back the whole output block and the running maximum behind it
     CU_TRY(cudaMemcpyAsync(b->hin, b->dout, b->out_block + sizeof(float), cudaMemcpyDeviceToHost, q));
