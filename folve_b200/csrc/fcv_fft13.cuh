@@ -75,6 +75,14 @@ __device__ __forceinline__ c2 ldg_c2(const float2 *p) {
     const float2 v = __ldg(p);
     return c2_pack(v.x, v.y);
 }
+// Read-once data (spectrum rows written by the previous kernel): kept out of L1, where the
+// ~100 KB of twiddle tables every CTA of the SM re-reads have to survive next to 2 x 66 KB
+// of shared memory.
+__device__ __forceinline__ c2 ldg_stream_c2(const float2 *p) {
+    c2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
 
 // z[n] = (x[2n], x[2n+1]) of C consecutive channels starting at ch0, frames >= fv read as 0.
 // NCH = 2: stereo block and both channels wanted (one vector load); NCH = 1: mono block;
@@ -84,17 +92,17 @@ __device__ __forceinline__ void load_z(const void *in, int nchan, int ch0, int n
     float2 v[C];
     if (NCH == 2 && C == 2) {
         if (FMT == PCM_F32) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(in) + n);
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(in) + n);
             v[0] = make_float2(t.x, t.z);
             v[1] = make_float2(t.y, t.w);
         } else if (FMT == PCM_S16) {
             constexpr float K = 1.0f / 32768.0f;
-            const short4 t = __ldg(reinterpret_cast<const short4 *>(in) + n);
+            const short4 t = __ldcs(reinterpret_cast<const short4 *>(in) + n);
             v[0] = make_float2(t.x * K, t.z * K);
             v[1] = make_float2(t.y * K, t.w * K);
         } else {
             constexpr float K = 1.0f / 8388608.0f;
-            const int4 t = __ldg(reinterpret_cast<const int4 *>(in) + n);
+            const int4 t = __ldcs(reinterpret_cast<const int4 *>(in) + n);
             v[0] = make_float2(t.x * K, t.z * K);
             v[1] = make_float2(t.y * K, t.w * K);
         }
@@ -284,8 +292,8 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
         c2 y1[16], y2[16], v1[16], v2[16];
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
-            y1[k2] = ldg_c2(y + 256 * k2);
-            y2[k2] = ldg_c2(y + 256 * k2 + 128);
+            y1[k2] = ldg_stream_c2(y + 256 * k2);
+            y2[k2] = ldg_stream_c2(y + 256 * k2 + 128);
         }
         v1[0] = zc0;
 #pragma unroll
@@ -317,8 +325,8 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
         c2 y1[16], y2[16], w[16];
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
-            y1[k2] = ldg_c2(y + 256 * k2 + c);
-            y2[k2] = ldg_c2(y + 256 * k2 + cc);
+            y1[k2] = ldg_stream_c2(y + 256 * k2 + c);
+            y2[k2] = ldg_stream_c2(y + 256 * k2 + cc);
             w[k2] = ldg_c2(twu + 256 * k2 + c);
         }
 #pragma unroll
@@ -358,7 +366,7 @@ __device__ __forceinline__ float inv_pass_a(const c2 *sm, const Tables &tb, floa
         Bfly<16>::template run<+1>(vb);
         float2 tl[16];
 #pragma unroll
-        for (int r = 0; r < 16; r++) tl[r] = tail[u + 256 * out16(r)];
+        for (int r = 0; r < 16; r++) tl[r] = __ldcg(&tail[u + 256 * out16(r)]);  // L2 only: read once per block
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             const int n2 = out16(r), n = u + 256 * n2;
