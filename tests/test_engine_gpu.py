@@ -292,17 +292,22 @@ def test_time_tiled_batch_equals_block_by_block(T):
     f.close()
 
 
-@pytest.mark.parametrize("nin,nout,T", [(1, 1, 4), (3, 2, 4), (1, 2, 8), (6, 6, 2)])
-def test_time_tiled_other_channel_counts_and_s24(nin, nout, T):
+@pytest.mark.parametrize("nin,nout,T,size", [(1, 1, 4, 30000), (3, 2, 4, 30000), (1, 2, 8, 30000), (6, 6, 2, 30000),
+                                             (3, 2, 8, 30000), (6, 6, 8, 30000), (2, 2, 8, 110000), (2, 3, 4, 110000)])
+def test_time_tiled_other_channel_counts_and_s24(nin, nout, T, size):
     """fragm = 8192 with mono, odd and 5.1 channel counts: the forward kernel's mono and
     scalar-load paths, several blocks per step, 24-bit wire format; tiled == block by block
-    and both == oracle."""
-    r = _rng(90 + 10 * nin + nout + T)
-    spec = FilterSpec(nin, nout, 30000)
+    and both == oracle.  The T = 8 cases with several inputs per output walk more than one
+    (input, output) pair per work item of the TMA-staged MAC (rows of a pair restart on
+    pipeline stage 0), the long filters more than one ring revolution per pair; 3 streams
+    leave the last stream group half empty."""
+    r = _rng(90 + 10 * nin + nout + T + size // 10000)
+    spec = FilterSpec(nin, nout, size)
     for i in range(nin):
         for o in range(nout):
-            if (i + o) % 2 == 0 or nin == 1:
-                spec.add(i, o, r.standard_normal(8000 + 4000 * ((i + o) % 3)) * 0.004, 3000 * ((i * nout + o) % 5))
+            if (i + o) % 2 == 0 or nin == 1 or size > 30000:
+                taps = 8000 + 4000 * ((i + o) % 3) if size == 30000 else size - 20000 - 7000 * ((i + o) % 3)
+                spec.add(i, o, r.standard_normal(taps) * (0.004 if size == 30000 else 0.001), 3000 * ((i * nout + o) % 5))
     f = _engine(spec)
     N, B = spec.fragm, 3
     assert N == 8192
