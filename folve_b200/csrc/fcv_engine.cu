@@ -152,12 +152,9 @@ __device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables 
     return lmax;
 }
 
-// DC and Nyquist are real bins sharing entry 0 of a spectrum: their products are two real
-// multiply-accumulates over the partition history (the MAC kernels treat entry 0 as one
-// complex value, which the inverse transform ignores).  One warp per (stream, output,
-// block of the step), lanes split the partitions; the result is stored as entry 0 of the
-// complex N-point sequence the inverse transform starts from: (dc + ny, dc - ny).
-// Runs between the forward transform and the inverse one, off their critical paths.
+// DC / Nyquist products (dcny_warp, fcv_mac.cuh) of a multi-block step: one warp per (stream,
+// output, block of the step).  Runs between the MAC and the inverse transform, off their
+// critical paths; the block-by-block MAC kernel does the same inside its own launch.
 __global__ void __launch_bounds__(256)
 dcny_kernel(const StreamDev *__restrict__ st, const TTPair *__restrict__ pairs, const int *__restrict__ pair_off,
             const int *__restrict__ tt_rows, const float2 *__restrict__ H, float2 *__restrict__ zc0, int nwarps,
@@ -165,31 +162,10 @@ dcny_kernel(const StreamDev *__restrict__ st, const TTPair *__restrict__ pairs, 
     const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nwarps) return;
     const int bt = w % T, o = (w / T) % nout, b = w / (T * nout);
-    const float2 *xring = st[b].xring;
     int newest = pt + bt;
     if (newest >= R) newest -= R;
-    float dc = 0.f, ny = 0.f;
-    for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
-        const int inp = pairs[p].inp;
-        const int *rows = tt_rows + pairs[p].rowbase;
-        for (int j = lane; j < P; j += 32) {
-            const int row = rows[j];
-            if (row >= 0) {
-                int slot = newest - j;
-                if (slot < 0) slot += R;
-                const float2 x = xring[(size_t)(inp * R + slot) * M];
-                const float2 h = H[(size_t)row * M];
-                dc = fmaf(x.x, h.x, dc);
-                ny = fmaf(x.y, h.y, ny);
-            }
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        dc += __shfl_xor_sync(0xffffffffu, dc, d);
-        ny += __shfl_xor_sync(0xffffffffu, ny, d);
-    }
-    if (lane == 0) zc0[w] = make_float2(dc + ny, dc - ny);
+    const float2 z = dcny_warp(st[b].xring, pairs, pair_off, tt_rows, H, o, P, R, newest, M, lane);
+    if (lane == 0) zc0[w] = z;
 }
 
 // Inverse transform of every (stream, output channel) with fused DC/Nyquist
@@ -1048,12 +1024,15 @@ static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_
     dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->ngroups);
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * f->fragm);
+#define FCV_MAC1_ARGS b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout, f->dpairs, f->dpair_off, \
+                      f->dtt_rows, b->zc0 + (size_t)off * f->nout, f->ring
     if (TPB == 128)
-        mac_kernel<NO, S, 128><<<grid, 128, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout);
+        mac_kernel<NO, S, 128><<<grid, 128, 0, q>>>(FCV_MAC1_ARGS);
     else if (TPB == 64)
-        mac_kernel<NO, S, 64><<<grid, 64, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout);
+        mac_kernel<NO, S, 64><<<grid, 64, 0, q>>>(FCV_MAC1_ARGS);
     else
-        mac_kernel<NO, S, 32><<<grid, 32, 0, q>>>(b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout);
+        mac_kernel<NO, S, 32><<<grid, 32, 0, q>>>(FCV_MAC1_ARGS);
+#undef FCV_MAC1_ARGS
 }
 
 // Time-tiled MAC: T blocks per stream per launch, one output channel per grid.z.
@@ -1184,7 +1163,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     if (ev) cudaEventRecord(ev[2], q);
     const float2 *Y = b->Y + (size_t)off * f->nout * T * f->fragm;
     float2 *zc0 = b->zc0 + (size_t)off * f->nout * T;
-    if (only & 4) {
+    if ((only & 4) && T > 1) {   // T == 1: done inside mac_kernel
         const int nwarps = cnt * f->nout * T;
         dcny_kernel<<<(nwarps + 7) / 8, 256, 0, q>>>(b->dst + off, f->dpairs, f->dpair_off, f->dtt_rows, f->dH, zc0,
                                                      nwarps, f->nout, f->ring, R, T, pt, f->fragm);
@@ -1207,7 +1186,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     DISPATCH_LOG2N(f->log2n, (inv_stream_kernel<L><<<dim3(f->nout, cnt), fft_threads(L), fft_smem_bytes(L), q>>>(
                                   b->dst + off, fv, fv_all, tb, Y, zc0, f->nout, T, b->out_fmt)));
     if (ev) cudaEventRecord(ev[3], q);
-    g_launches += 4;
+    g_launches += T > 1 ? 4 : 3;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(FCV_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return 0;

@@ -67,12 +67,52 @@ __device__ __forceinline__ float4 ld_keep(const float4 *p) {
     return __ldg(p);
 }
 
+struct TTPair {
+    int inp;      // input channel feeding this output
+    int rowbase;  // index into tt_rows: P consecutive filter-row numbers (absent -> the zero row)
+};
+
+// DC and Nyquist are real bins sharing entry 0 of a spectrum: their products are two real
+// multiply-accumulates over the partition history (the MAC kernels treat entry 0 as one
+// complex value, which the inverse transform ignores).  One warp per (stream, output, block):
+// lanes split the partitions; returns, on every lane, entry 0 of the complex N-point
+// sequence the inverse transform starts from: (dc + ny, dc - ny).  One code path for every
+// kernel that needs it, so that all block sizes / tilings round identically.
+__device__ __forceinline__ float2 dcny_warp(const float2 *__restrict__ xring, const TTPair *__restrict__ pairs,
+                                            const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
+                                            const float2 *__restrict__ H, int o, int P, int R, int newest, int M,
+                                            int lane) {
+    float dc = 0.f, ny = 0.f;
+    for (int p = pair_off[o]; p < pair_off[o + 1]; p++) {
+        const int inp = pairs[p].inp;
+        const int *rows = tt_rows + pairs[p].rowbase;
+        for (int j = lane; j < P; j += 32) {
+            const int row = rows[j];
+            if (row >= 0) {
+                int slot = newest - j;
+                if (slot < 0) slot += R;
+                const float2 x = xring[(size_t)(inp * R + slot) * M];
+                const float2 h = H[(size_t)row * M];
+                dc = fmaf(x.x, h.x, dc);
+                ny = fmaf(x.y, h.y, ny);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        dc += __shfl_xor_sync(0xffffffffu, dc, d);
+        ny += __shfl_xor_sync(0xffffffffu, ny, d);
+    }
+    return make_float2(dc + ny, dc - ny);
+}
+
 // grid: x = M/2/TPB (tiles of 2*TPB entries), y = ceil(nstreams/S), z = output groups.
 template <int NO, int S, int TPB>
 __global__ void __launch_bounds__(TPB)
 mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__restrict__ steps,
            const int *__restrict__ group_off, const float4 *__restrict__ H, float4 *__restrict__ Y,
-           int M4, int P, int pt, int nout) {
+           int M4, int P, int pt, int nout, const TTPair *__restrict__ pairs, const int *__restrict__ pair_off,
+           const int *__restrict__ tt_rows, float2 *__restrict__ zc0, int Pfilt) {
     const int e4 = blockIdx.x * TPB + threadIdx.x;
     const int b0 = blockIdx.y * S;
     const int g = blockIdx.z;
@@ -121,6 +161,19 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
             }
         }
     }
+    // the CTAs of the first spectrum tile also do the DC / Nyquist products of their streams and
+    // outputs (block-by-block path: no separate launch for them)
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        for (int o = 0; o < NO; o++) {
+            const int oo = g * NO + o;
+            if (oo >= nout) break;
+            for (int s = 0; s < S && b0 + s < nstreams; s++) {
+                const float2 z = dcny_warp(st[b0 + s].xring, pairs, pair_off, tt_rows, reinterpret_cast<const float2 *>(H),
+                                           oo, Pfilt, P, pt, 2 * M4, threadIdx.x);
+                if (threadIdx.x == 0) zc0[(size_t)(b0 + s) * nout + oo] = z;
+            }
+        }
+    }
 }
 
 // ---- time-tiled variant ------------------------------------------------------------
@@ -133,10 +186,6 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
 //
 //   step d = 0 .. P+T-2 :  X row of block u = t0+T-1-d ;  output t uses H[j = t-(T-1)+d]
 //   H[j] for output t at step d lives in window register (t + d) mod T.
-struct TTPair {
-    int inp;      // input channel feeding this output
-    int rowbase;  // index into tt_rows: P consecutive filter-row numbers (absent -> the zero row)
-};
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
