@@ -361,7 +361,8 @@ def main():
             ts.append(time.perf_counter() - t1)
         ts = np.array(ts[100:]) * 1e6
         lat = {"median": float(np.median(ts)), "p99": float(np.percentile(ts, 99)), "blocks": int(ts.size),
-               "what": "fcv_stream_process: pinned block -> H2D, 3 kernels, D2H -> pinned block, one stream"}
+               "what": "fcv_stream_process, one stream: pinned block read by the forward kernel over the link, "
+                       "3 kernels, D2H -> pinned block"}
         st.close()
     barrier()
 
