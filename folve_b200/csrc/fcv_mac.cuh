@@ -130,6 +130,38 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
         for (int s = 0; s < S; s++) acc[o][s] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const int t0 = group_off[g], t1 = group_off[g + 1];
+    if (S == 1) {
+        // A lone stream (the per-file path) is latency bound: a chain of dependent round trips,
+        // step table -> X row / filter rows -> FMA.  All loads of U steps are issued before the
+        // first of them is used.
+        constexpr int U = NO <= 2 ? 8 : 4;
+#pragma unroll 1
+        for (int t = t0; t < t1; t += U) {
+            float4 x[U], h[U][NO];
+            int row[U][NO];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool live = t + u < t1;
+                const MacStep *sp = steps + (live ? t + u : t);
+                const int inp = __ldg(&sp->inp), part = __ldg(&sp->part);
+                int slot = pt - part;
+                if (slot < 0) slot += P;
+                x[u] = ld_stream(xb[0] + (size_t)(inp * P + slot) * (size_t)M4);
+#pragma unroll
+                for (int o = 0; o < NO; o++) row[u][o] = live ? __ldg(&sp->row[o]) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int o = 0; o < NO; o++)
+                    h[u][o] = row[u][o] >= 0 ? ld_keep(H + (size_t)row[u][o] * (size_t)M4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int o = 0; o < NO; o++)
+                    if (row[u][o] >= 0) cmac2(acc[o][0], x[u], h[u][o]);
+        }
+    } else {
 #pragma unroll 2
     for (int t = t0; t < t1; t++) {
         const MacStep *sp = steps + t;
@@ -149,6 +181,7 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
                 for (int s = 0; s < S; s++) cmac2(acc[o][s], x[s], h);
             }
         }
+    }
     }
 #pragma unroll
     for (int o = 0; o < NO; o++) {
