@@ -1030,7 +1030,7 @@ static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_
     const fcv_filter *f = b->f;
     const int M4 = f->fragm / 2;
     const int TPB = M4 >= 128 ? 128 : M4;  // M4 is a power of two >= 32
-    dim3 grid(M4 / TPB, (cnt + S - 1) / S, f->ngroups);
+    dim3 grid(M4 / TPB + 1, (cnt + S - 1) / S, f->ngroups);   // + 1: the DC / Nyquist column
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(b->Y + (size_t)off * f->nout * f->fragm);
 #define FCV_MAC1_ARGS b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout, f->dpairs, f->dpair_off, \

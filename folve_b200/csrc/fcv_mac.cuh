@@ -106,7 +106,7 @@ __device__ __forceinline__ float2 dcny_warp(const float2 *__restrict__ xring, co
     return make_float2(dc + ny, dc - ny);
 }
 
-// grid: x = M/2/TPB (tiles of 2*TPB entries), y = ceil(nstreams/S), z = output groups.
+// grid: x = M/2/TPB tiles of 2*TPB entries + 1 DC/Nyquist column, y = ceil(nstreams/S), z = output groups.
 template <int NO, int S, int TPB>
 __global__ void __launch_bounds__(TPB)
 mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__restrict__ steps,
@@ -116,6 +116,23 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
     const int e4 = blockIdx.x * TPB + threadIdx.x;
     const int b0 = blockIdx.y * S;
     const int g = blockIdx.z;
+
+    // one extra column of CTAs (blockIdx.x == gridDim.x - 1) does the DC / Nyquist products of its
+    // streams and outputs beside the spectrum tiles (block-by-block path: no separate launch)
+    if (blockIdx.x == gridDim.x - 1) {
+        if (threadIdx.x < 32) {
+            for (int o = 0; o < NO; o++) {
+                const int oo = g * NO + o;
+                if (oo >= nout) break;
+                for (int s = 0; s < S && b0 + s < nstreams; s++) {
+                    const float2 z = dcny_warp(st[b0 + s].xring, pairs, pair_off, tt_rows, reinterpret_cast<const float2 *>(H),
+                                               oo, Pfilt, P, pt, 2 * M4, threadIdx.x);
+                    if (threadIdx.x == 0) zc0[(size_t)(b0 + s) * nout + oo] = z;
+                }
+            }
+        }
+        return;
+    }
 
     const float4 *xb[S];
 #pragma unroll
@@ -191,19 +208,6 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
             for (int s = 0; s < S; s++) {
                 if (b0 + s < nstreams)
                     __stcs(Y + ((size_t)(b0 + s) * nout + oo) * (size_t)M4 + e4, acc[o][s]);
-            }
-        }
-    }
-    // the CTAs of the first spectrum tile also do the DC / Nyquist products of their streams and
-    // outputs (block-by-block path: no separate launch for them)
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        for (int o = 0; o < NO; o++) {
-            const int oo = g * NO + o;
-            if (oo >= nout) break;
-            for (int s = 0; s < S && b0 + s < nstreams; s++) {
-                const float2 z = dcny_warp(st[b0 + s].xring, pairs, pair_off, tt_rows, reinterpret_cast<const float2 *>(H),
-                                           oo, Pfilt, P, pt, 2 * M4, threadIdx.x);
-                if (threadIdx.x == 0) zc0[(size_t)(b0 + s) * nout + oo] = z;
             }
         }
     }
