@@ -236,6 +236,8 @@ fwd13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c2 *sm = reinterpret_cast<c2 *>(smem_raw);
     constexpr int N = f13::N;
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x & 1, ch0 = (blockIdx.x >> 1) * C, b = blockIdx.y, bt = blockIdx.z;
     const StreamDev s = st[b];
     int frames = (fv ? fv[b] : fv_all) - bt * N;
@@ -281,6 +283,8 @@ inv13_stream_kernel(const StreamDev *__restrict__ st, const int *__restrict__ fv
     constexpr int NT = F13_INV_NT;
     __shared__ float red[NT / 32];
     constexpr int N = f13::N, M = N;
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int o = blockIdx.x, b = blockIdx.y;
     const StreamDev s = st[b];
@@ -1025,6 +1029,31 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     return b;
 }
 
+// <<<>>> with the programmatic-stream-serialization attribute when `pdl` (single-stream path:
+// the next kernel's launch latency hides behind the tail of the previous one)
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t q, bool pdl, Args... args) {
+    if (!pdl) {
+        kernel<<<grid, block, smem, q>>>(KArgs(args)...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = q;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+static bool use_pdl(const fcv_batch *b) {
+    static const bool on = !(getenv("FCV_PDL") && atoi(getenv("FCV_PDL")) == 0);
+    return on && b->per_block_max;   // single-stream handles only
+}
+
 template <int NO, int S>
 static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_t q) {
     const fcv_filter *f = b->f;
@@ -1036,11 +1065,11 @@ static void launch_mac(const fcv_batch *b, int off, int cnt, int pt, cudaStream_
 #define FCV_MAC1_ARGS b->dst + off, cnt, f->dsteps, f->dgroup_off, H, Y, M4, b->R, pt, f->nout, f->dpairs, f->dpair_off, \
                       f->dtt_rows, b->zc0 + (size_t)off * f->nout, f->ring
     if (TPB == 128)
-        mac_kernel<NO, S, 128><<<grid, 128, 0, q>>>(FCV_MAC1_ARGS);
+        launch_k(mac_kernel<NO, S, 128>, grid, dim3(128), 0, q, use_pdl(b), FCV_MAC1_ARGS);
     else if (TPB == 64)
-        mac_kernel<NO, S, 64><<<grid, 64, 0, q>>>(FCV_MAC1_ARGS);
+        launch_k(mac_kernel<NO, S, 64>, grid, dim3(64), 0, q, use_pdl(b), FCV_MAC1_ARGS);
     else
-        mac_kernel<NO, S, 32><<<grid, 32, 0, q>>>(FCV_MAC1_ARGS);
+        launch_k(mac_kernel<NO, S, 32>, grid, dim3(32), 0, q, use_pdl(b), FCV_MAC1_ARGS);
 #undef FCV_MAC1_ARGS
 }
 
@@ -1116,14 +1145,14 @@ static void launch_fwd13_fmt(const fcv_batch *b, int off, int cnt, const int *fv
     const fcv_filter *f = b->f;
     const int rm = b->per_block_max ? 1 : 0;
     if (f->ninp == 2)
-        fwd13_stream_kernel<FMT, 2, 2><<<dim3(2, cnt, b->T), 256, 2 * f13::HALF_BYTES, q>>>(
-            b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
+        launch_k(fwd13_stream_kernel<FMT, 2, 2>, dim3(2, cnt, b->T), dim3(256), 2 * f13::HALF_BYTES, q, use_pdl(b),
+                 b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
     else if (f->ninp == 1)
-        fwd13_stream_kernel<FMT, 1, 1><<<dim3(2, cnt, b->T), 128, f13::HALF_BYTES, q>>>(
-            b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
+        launch_k(fwd13_stream_kernel<FMT, 1, 1>, dim3(2, cnt, b->T), dim3(128), f13::HALF_BYTES, q, use_pdl(b),
+                 b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
     else
-        fwd13_stream_kernel<FMT, 0, 1><<<dim3(2 * f->ninp, cnt, b->T), 128, f13::HALF_BYTES, q>>>(
-            b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
+        launch_k(fwd13_stream_kernel<FMT, 0, 1>, dim3(2 * f->ninp, cnt, b->T), dim3(128), f13::HALF_BYTES, q, use_pdl(b),
+                 b->dst + off, fv, fv_all, f->tb13, f->ninp, b->R, b->T, pt, rm);
 }
 static void launch_fwd13(const fcv_batch *b, int off, int cnt, const int *fv, int fv_all, int pt, cudaStream_t q) {
     if (b->in_fmt == PCM_F32) launch_fwd13_fmt<PCM_F32>(b, off, cnt, fv, fv_all, pt, q);
@@ -1185,7 +1214,7 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
         static const bool pf = !(getenv("FCV_INV_PF") && atoi(getenv("FCV_INV_PF")) == 0);
 #define FCV_INV13_LAUNCH(F) \
         do { if (pf && T > 1) inv13_stream_kernel<F, true><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS); \
-             else inv13_stream_kernel<F, false><<<grid, F13_INV_NT, smem, q>>>(FCV_INV13_ARGS); } while (0)
+             else launch_k(inv13_stream_kernel<F, false>, grid, dim3(F13_INV_NT), smem, q, use_pdl(b), FCV_INV13_ARGS); } while (0)
         if (b->out_fmt == PCM_F32) FCV_INV13_LAUNCH(PCM_F32);
         else if (b->out_fmt == PCM_S16) FCV_INV13_LAUNCH(PCM_S16);
         else FCV_INV13_LAUNCH(PCM_S24);

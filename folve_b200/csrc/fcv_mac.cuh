@@ -27,6 +27,13 @@
 
 namespace fcv {
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; pdl_wait() returns
+// once the predecessor has completed and its writes are visible, pdl_trigger() lets the successor
+// be scheduled.  Both are no-ops for launches without the attribute (every batched launch).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // Per-stream device descriptor (array owned by a batch or a single stream).
 struct StreamDev {
     float2 *xring;  // [ninp][P][M] input-spectra ring
@@ -113,6 +120,8 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
            const int *__restrict__ group_off, const float4 *__restrict__ H, float4 *__restrict__ Y,
            int M4, int P, int pt, int nout, const TTPair *__restrict__ pairs, const int *__restrict__ pair_off,
            const int *__restrict__ tt_rows, float2 *__restrict__ zc0, int Pfilt) {
+    pdl_trigger();
+    pdl_wait();
     const int e4 = blockIdx.x * TPB + threadIdx.x;
     const int b0 = blockIdx.y * S;
     const int g = blockIdx.z;
