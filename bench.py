@@ -205,7 +205,9 @@ def run_reference(args, rank, world):
         filter_dir = workloads.write_filter_dir(wl, os.path.join(tmp, wl.name))
         kind, run, what = cpu_arm(wl, filter_dir)
         audio, wall = run(cores, 8)
-        nb = max(8, min(20000, int(8 * 4.0 / wall)))   # ~4 s of CPU work per step
+        # bounded sample: ~4 s of CPU work per step, and at most ~90 s for the whole run whatever K is
+        per_step_s = min(4.0, 90.0 / max(1, args.steps))
+        nb = max(8, min(20000, int(8 * per_step_s / wall)))
         for _ in range(args.warmup):
             run(cores, max(4, nb // 8))
         t_audio = t_wall = 0.0
