@@ -280,6 +280,57 @@ int fh_run_library(const char *config_file, int samplerate, int channels, int ga
     return fh_run_library_tiled(config_file, samplerate, channels, gapless, slots, threads, nfiles, chain_of_file, pcm,
                                 frames, out_pcm, out_frames, max_values, gapless_flags, steps_out, 1);
 }
+static double NowSeconds() {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+// ---- throughput of the batched submit layer --------------------------------------
+// `nchains` album chains of `files_per_chain` in-memory float files each (lengths around
+// `frames_per_file`, never a multiple of the block size, all reading the same white-noise
+// buffer), every chain in flight at once, output discarded.  Returns the wall seconds of
+// BatchConvolver::Run, <0 on error; *audio_seconds = what was convolved.
+double fh_bench_library(const char *config_file, int samplerate, int channels, int gapless, int nchains,
+                        int files_per_chain, long frames_per_file, int blocks_per_step, int threads,
+                        double *audio_seconds) {
+    folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
+        config_file, samplerate, channels, nchains, gapless != 0, SoundProcessor::Device(), blocks_per_step);
+    if (!bc) return -1.0;
+    const int nout = bc->output_channels();
+    const long longest = frames_per_file + 4099;
+    std::vector<float> pcm((size_t)longest * (size_t)channels);
+    uint32_t s = 12345u;
+    for (size_t i = 0; i < pcm.size(); i++) {
+        s = s * 1664525u + 1013904223u;
+        pcm[i] = 0.03f * ((float)(s >> 8) * (1.0f / 8388608.0f) - 1.0f);
+    }
+    std::vector<folve_b200::Chain> chains((size_t)nchains);
+    double frames_total = 0.0;
+    for (int c = 0; c < nchains; c++)
+        for (int k = 0; k < files_per_chain; k++) {
+            folve_b200::ChainFile f;
+            f.frames = frames_per_file + 1 + (long)((c * 131 + k * 977) % 4097);
+            f.in = sf_shim_open_memory_read(pcm.data(), f.frames, channels, samplerate, SF_FORMAT_FLOAT);
+            f.out = sf_shim_open_null_write(nout, samplerate, SF_FORMAT_FLOAT);
+            frames_total += (double)f.frames;
+            chains[(size_t)c].push_back(f);
+        }
+    std::vector<folve_b200::Chain *> ptrs;
+    for (auto &c : chains) ptrs.push_back(&c);
+    const double t0 = NowSeconds();
+    const bool ok = bc->Run(ptrs, threads);
+    const double wall = NowSeconds() - t0;
+    for (auto &c : chains)
+        for (auto &f : c) {
+            sf_close(f.in);
+            sf_close(f.out);
+        }
+    delete bc;
+    if (audio_seconds) *audio_seconds = frames_total / (double)samplerate;
+    return ok ? wall : -2.0;
+}
+
 #endif
 
 // ---- throughput of the synchronous drop-in API ---------------------------------
