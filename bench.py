@@ -473,10 +473,10 @@ def main():
                     cores = len(os.sched_getaffinity(0))
                     harness_run(HOST_SO, wl, filter_dir, cores, 20)
                     a, w = harness_run(HOST_SO, wl, filter_dir, cores, 400)
-                    a2, w2 = library_run(wl, filter_dir, B, 2, 60.0, T, cores)
+                    a2, w2 = library_run(wl, filter_dir, B, 2, 120.0, T, cores)
                     line["e2e"]["batch_convolver"] = {
                         "value": a2 / w2, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
-                        "what": f"BatchConvolver::Run: {B} gapless chains x 2 in-memory float files of ~60 s in flight at "
+                        "what": f"BatchConvolver::Run: {B} gapless chains x 2 in-memory float files of ~120 s in flight at "
                                 f"once, {T} blocks per chain and step, SNDFILE in / SNDFILE out on {cores} host threads"}
                     line["e2e"]["soundprocessor_sync"] = {
                         "value": a / w, "unit": "x realtime (audio-s per wall-s)", "threads": cores,

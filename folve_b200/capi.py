@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
         "fcv_batch_reset_slot": (i, [vp, i]),
         "fcv_batch_get_max": (i, [vp, fp]),
         "fcv_batch_get_block_max": (i, [vp, fp]),
+        "fcv_batch_reset_slot_async": (i, [vp, i]),
+        "fcv_batch_host_block_max_slot": (vp, [vp, i]),
         "fcv_batch_cuda_stream": (vp, [vp]),
         "fcv_batch_event_record": (i, [vp, i]),
         "fcv_batch_event_elapsed_ms": (i, [vp, i, i, fp]),

@@ -891,6 +891,7 @@ struct fcv_batch {
     // second host staging slot + per-slot completion events for the asynchronous submit/wait pair
     unsigned char *hin1 = nullptr, *hout1 = nullptr;
     int *dfv1 = nullptr, *hfv1 = nullptr;
+    float *hbmax[2] = {nullptr, nullptr};   // [B][T] block maxima of the step submitted from each host slot
     cudaEvent_t slot_done[2][4] = {};
     bool slot_busy[2] = {false, false};
     // streams
@@ -924,6 +925,7 @@ static void batch_free(fcv_batch *b) {
     if (b->hout1) cudaFreeHost(b->hout1);
     if (b->hfv1) cudaFreeHost(b->hfv1);
     if (b->dfv1) cudaFree(b->dfv1);
+    for (int k = 0; k < 2; k++) if (b->hbmax[k]) cudaFreeHost(b->hbmax[k]);
     for (int k = 0; k < 2; k++)
         for (int i = 0; i < 4; i++)
             if (b->slot_done[k][i]) cudaEventDestroy(b->slot_done[k][i]);
@@ -1353,6 +1355,23 @@ extern "C" int fcv_batch_wait(fcv_batch *b, int slot) {
     return 0;
 }
 
+// Chunks of streams a submit is split into (each chunk: copy in, kernels, copy out on one of NQ
+// CUDA streams, round robin -- a given stream of the batch always lands on the same CUDA stream).
+static int submit_chunks(const fcv_batch *b) {
+    if (b->profiling) return 1;
+    static const int env_chunks = getenv("FCV_CHUNKS") ? atoi(getenv("FCV_CHUNKS")) : 0;  // tuning knob
+    int nchunk = env_chunks > 0 ? env_chunks : b->B / 128;
+    if (nchunk > 16) nchunk = 16;
+    if (nchunk > b->B) nchunk = b->B;
+    if (nchunk < 1) nchunk = 1;
+    return nchunk;
+}
+static cudaStream_t submit_stream_of(const fcv_batch *b, int stream_index) {
+    const int nchunk = submit_chunks(b);
+    const int per = (b->B + nchunk - 1) / nchunk;
+    return b->q[nchunk == 1 ? 0 : (stream_index / per) % fcv_batch::NQ];
+}
+
 // Enqueue one block for every stream from host staging slot `slot`:
 // per chunk of streams host->device copy, the three kernels, device->host copy,
 // round-robin over NQ CUDA streams.  Chunks of consecutive submits run in order
@@ -1374,13 +1393,10 @@ extern "C" int fcv_batch_submit(fcv_batch *b, int slot, const int *frames_valid)
             hfv[s] = v;
         }
     }
-    int nchunk = 1;
-    if (!b->profiling) {
-        static const int env_chunks = getenv("FCV_CHUNKS") ? atoi(getenv("FCV_CHUNKS")) : 0;  // tuning knob
-        nchunk = env_chunks > 0 ? env_chunks : b->B / 128;
-        if (nchunk > 16) nchunk = 16;
-        if (nchunk > b->B) nchunk = b->B;
-        if (nchunk < 1) nchunk = 1;
+    const int nchunk = submit_chunks(b);
+    if (!b->hbmax[slot]) {
+        CU_TRY(cudaHostAlloc((void **)&b->hbmax[slot], (size_t)b->B * b->T * sizeof(float), cudaHostAllocDefault));
+        memset(b->hbmax[slot], 0, (size_t)b->B * b->T * sizeof(float));
     }
     static const bool env_nokernels = getenv("FCV_COPY_ONLY") != nullptr;  // diagnostic: copies without kernels
     const int per = (b->B + nchunk - 1) / nchunk;
@@ -1395,6 +1411,8 @@ extern "C" int fcv_batch_submit(fcv_batch *b, int slot, const int *frames_valid)
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(hout + (size_t)off * b->out_block, b->dout + (size_t)off * b->out_block,
                                (size_t)cnt * b->out_block, cudaMemcpyDeviceToHost, q));
+        CU_TRY(cudaMemcpyAsync(b->hbmax[slot] + (size_t)off * b->T, b->bmax + (size_t)off * b->T,
+                               (size_t)cnt * b->T * sizeof(float), cudaMemcpyDeviceToHost, q));
     }
     for (int i = 0; i < fcv_batch::NQ; i++) {
         if (!b->slot_done[slot][i]) CU_TRY(cudaEventCreateWithFlags(&b->slot_done[slot][i], cudaEventDisableTiming));
@@ -1425,6 +1443,25 @@ extern "C" int fcv_batch_reset_slot(fcv_batch *b, int slot) {
     CU_TRY(cudaMemsetAsync(b->maxv + slot, 0, sizeof(float), b->q[0]));
     CU_TRY(cudaStreamSynchronize(b->q[0]));
     return 0;
+}
+
+extern "C" int fcv_batch_reset_slot_async(fcv_batch *b, int slot) {
+    if (!b || slot < 0 || slot >= b->B) return fail(FCV_E_PARAM, "bad slot");
+    CU_TRY(cudaSetDevice(b->f->device));
+    const fcv_filter *f = b->f;
+    const size_t N = (size_t)f->fragm;
+    // the CUDA stream every submit processes this stream of the batch on: the reset lands behind
+    // the steps already submitted and ahead of the next one
+    cudaStream_t q = submit_stream_of(b, slot);
+    CU_TRY(cudaMemsetAsync(b->xring + (size_t)slot * f->ninp * b->R * N, 0, b->state_bytes_per_stream, q));
+    CU_TRY(cudaMemsetAsync(b->tail + (size_t)slot * f->nout * N, 0, (size_t)f->nout * N * sizeof(float), q));
+    CU_TRY(cudaMemsetAsync(b->maxv + slot, 0, sizeof(float), q));
+    return 0;
+}
+
+extern "C" const float *fcv_batch_host_block_max_slot(fcv_batch *b, int slot) {
+    if (!b || slot < 0 || slot > 1) return nullptr;
+    return b->hbmax[slot];
 }
 
 extern "C" int fcv_batch_get_max(fcv_batch *b, float *max_out) {

@@ -5,7 +5,9 @@
 #include <syslog.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 
 #include "../../include/folve_b200.h"
@@ -25,17 +27,84 @@ struct BatchConvolver::BlockPlan {
     int nfinished = 0;
 };
 
+// One step of a chain as it was assembled: kept until its output has come back, while the
+// next step of the same slot is already being assembled (two steps are in flight).
+struct BatchConvolver::StepPlan {
+    Chain *chain = nullptr;  // whose files the shares refer to
+    BlockPlan block[8];
+    int nblocks = 0;
+    int fill = 0;            // frames of the whole step (frames_valid of the batch call)
+    bool fresh = false;      // the step started from a reset processor: the running maximum restarts
+};
+
 // One chain in flight.
 struct BatchConvolver::Slot {
     Chain *chain = nullptr;
     size_t k = 0;          // file being read
     long left = 0;         // frames of file k not yet read
-    BlockPlan block[8];    // the blocks of the step being assembled
+    BlockPlan *block = nullptr;  // the blocks of the step being assembled (in one of plan[])
     int nblocks = 0;
-    int fill = 0;          // frames of the whole step (frames_valid of the batch call)
+    int fill = 0;
     bool reset_before_next = false;  // next block starts from the fresh state
-    float running_max = 0.0f;        // SoundProcessor::max_output_value() of the chain's processor
+    StepPlan plan[2];                // per host staging slot
+    float running_max = 0.0f;        // SoundProcessor::max_output_value() of the chain's processor (drain side)
     bool active() const { return chain != nullptr; }
+};
+
+// A fixed set of host threads that run `fn(i)` for i in [0, n) on request.
+class BatchConvolver::Workers {
+public:
+    explicit Workers(int n) {
+        for (int t = 0; t < n; t++) pool_.emplace_back([this] { Loop(); });
+    }
+    ~Workers() {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (auto &th : pool_) th.join();
+    }
+    void Run(int n, const std::function<void(int)> &fn) {
+        if (pool_.empty()) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
+        std::unique_lock<std::mutex> l(mu_);
+        fn_ = &fn;
+        n_ = n;
+        next_ = 0;
+        busy_ = (int)pool_.size();
+        gen_++;
+        cv_.notify_all();
+        done_.wait(l, [this] { return busy_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void Loop() {
+        unsigned long seen = 0;
+        std::unique_lock<std::mutex> l(mu_);
+        for (;;) {
+            cv_.wait(l, [&] { return quit_ || gen_ != seen; });
+            if (quit_) return;
+            seen = gen_;
+            const std::function<void(int)> *fn = fn_;
+            const int n = n_;
+            l.unlock();
+            for (int i = next_.fetch_add(1); i < n; i = next_.fetch_add(1)) (*fn)(i);
+            l.lock();
+            if (--busy_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> pool_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, busy_ = 0;
+    std::atomic<int> next_{0};
+    unsigned long gen_ = 0;
+    bool quit_ = false;
 };
 
 BatchConvolver *BatchConvolver::Create(const std::string &config_file, int samplerate, int channels, int slots,
@@ -53,6 +122,13 @@ BatchConvolver *BatchConvolver::Create(const std::string &config_file, int sampl
     fcv_batch *batch = fcv_batch_create_tiled(cfg.filter, slots, FCV_PCM_F32, FCV_PCM_F32, blocks_per_step);
     if (!batch) {
         syslog(LOG_ERR, "folve-b200: %s: %s", config_file.c_str(), fcv_last_error());
+        fcv_filter_unref(cfg.filter);
+        return nullptr;
+    }
+    // both host staging slots up front: pinning ~1 GB takes a few hundred milliseconds
+    if (!fcv_batch_host_in_slot(batch, 1) || !fcv_batch_host_out_slot(batch, 1)) {
+        syslog(LOG_ERR, "folve-b200: %s: %s", config_file.c_str(), fcv_last_error());
+        fcv_batch_destroy(batch);
         fcv_filter_unref(cfg.filter);
         return nullptr;
     }
@@ -149,11 +225,12 @@ void BatchConvolver::FillSlot(Slot &s, float *in_step) {
     }
 }
 
-void BatchConvolver::DrainSlot(Slot &s, const float *out_step, const float *block_max) {
-    Chain &c = *s.chain;
+void BatchConvolver::DrainSlot(Slot &s, const StepPlan &sp, const float *out_step, const float *block_max) {
+    Chain &c = *sp.chain;
     const size_t out_stride = (size_t)fragm_ * nout_;
-    for (int t = 0; t < s.nblocks; t++) {
-        const BlockPlan &p = s.block[t];
+    if (sp.fresh) s.running_max = 0.0f;   // SoundProcessor::Reset() (sound-processor.cc:139-145)
+    for (int t = 0; t < sp.nblocks; t++) {
+        const BlockPlan &p = sp.block[t];
         const float *out_block = out_step + (size_t)t * out_stride;
         int pos = 0;
         for (int i = 0; i < p.nshare; i++) {
@@ -168,77 +245,99 @@ void BatchConvolver::DrainSlot(Slot &s, const float *out_step, const float *bloc
     }
 }
 
+// Two steps are in flight: while the GPU works on step k (host staging slot k & 1) the host
+// threads write the output of step k - 1 to the files and read the input of step k + 1.
+// Resets between steps are enqueued on the device (fcv_batch_reset_slot_async), the per-block
+// maxima come back with each step's output: the host never waits for anything but a finished step.
 bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
     if (threads < 1) threads = 1;
     std::vector<Slot> slots((size_t)slots_);
-    std::vector<int> fv((size_t)slots_, 0);
-    std::vector<float> maxv((size_t)slots_ * tblocks_, 0.0f);
-    float *hin = (float *)fcv_batch_host_in(batch_);
-    const float *hout = (const float *)fcv_batch_host_out(batch_);
+    std::vector<int> fv[2] = {std::vector<int>((size_t)slots_, 0), std::vector<int>((size_t)slots_, 0)};
+    float *hin[2] = {(float *)fcv_batch_host_in_slot(batch_, 0), (float *)fcv_batch_host_in_slot(batch_, 1)};
+    const float *hout[2] = {(const float *)fcv_batch_host_out_slot(batch_, 0),
+                            (const float *)fcv_batch_host_out_slot(batch_, 1)};
+    if (!hin[0] || !hin[1] || !hout[0] || !hout[1]) return false;
     const size_t in_stride = (size_t)tblocks_ * fragm_ * ninp_, out_stride = (size_t)tblocks_ * fragm_ * nout_;
     size_t next_chain = 0;
     bool ok = true;
+    Workers workers(threads > 1 ? threads : 0);
 
-    auto parallel = [&](const std::function<void(int)> &fn) {
-        if (threads == 1) {
-            for (int i = 0; i < slots_; i++) fn(i);
+    // output of the step submitted from staging slot `h` -> files
+    auto drain = [&](int h) {
+        if (fcv_batch_wait(batch_, h) != 0) {
+            syslog(LOG_ERR, "folve-b200: batch step failed: %s", fcv_last_error());
+            ok = false;
             return;
         }
-        std::atomic<int> next(0);
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; t++)
-            pool.emplace_back([&] {
-                for (int i = next.fetch_add(1); i < slots_; i = next.fetch_add(1)) fn(i);
-            });
-        for (auto &th : pool) th.join();
+        const float *bmax = fcv_batch_host_block_max_slot(batch_, h);
+        workers.Run(slots_, [&](int i) {
+            Slot &s = slots[(size_t)i];
+            const StepPlan &sp = s.plan[h];
+            if (!sp.chain || fv[h][(size_t)i] == 0) return;
+            DrainSlot(s, sp, hout[h] + (size_t)i * out_stride, bmax + (size_t)i * tblocks_);
+        });
+        for (int i = 0; i < slots_; i++) {
+            blocks_ += fv[h][(size_t)i] > 0 ? slots[(size_t)i].plan[h].nblocks : 0;
+            fv[h][(size_t)i] = 0;
+        }
     };
 
-    for (;;) {
+    bool pending[2] = {false, false};
+    for (long step = 0;; step++) {
+        const int h = (int)(step & 1);
+        if (pending[h]) {  // the staging slot is about to be refilled: its previous step has to be out
+            drain(h);
+            pending[h] = false;
+        }
         // hand idle slots a new chain (from a reset state), reset where a hand-off chain ended
         for (int i = 0; i < slots_; i++) {
             Slot &s = slots[(size_t)i];
             if (s.active() && s.k >= s.chain->size()) s.chain = nullptr;
             if (!s.active() && next_chain < chains.size()) {
-                s = Slot();
                 s.chain = chains[next_chain++];
                 s.k = 0;
                 s.left = s.chain->empty() ? 0 : (*s.chain)[0].frames;
                 s.reset_before_next = true;
             }
+            s.plan[h].chain = s.chain;
+            s.plan[h].fresh = false;
+            s.plan[h].nblocks = 0;
             if (s.active() && s.reset_before_next) {
-                if (fcv_batch_reset_slot(batch_, i) != 0) ok = false;
+                if (fcv_batch_reset_slot_async(batch_, i) != 0) ok = false;
                 s.reset_before_next = false;
-                s.running_max = 0.0f;   // SoundProcessor::Reset() (sound-processor.cc:139-145)
+                s.plan[h].fresh = true;
             }
         }
-        bool any = false;
-        parallel([&](int i) {
+        workers.Run(slots_, [&](int i) {
             Slot &s = slots[(size_t)i];
-            fv[(size_t)i] = 0;
+            fv[h][(size_t)i] = 0;
             if (!s.active()) return;
-            FillSlot(s, hin + (size_t)i * in_stride);
-            fv[(size_t)i] = s.fill;
+            s.block = s.plan[h].block;
+            FillSlot(s, hin[h] + (size_t)i * in_stride);
+            s.plan[h].nblocks = s.nblocks;
+            s.plan[h].fill = s.fill;
+            fv[h][(size_t)i] = s.fill;
         });
-        for (int i = 0; i < slots_; i++) any |= fv[(size_t)i] > 0;
+        bool any = false;
+        for (int i = 0; i < slots_; i++) any |= fv[h][(size_t)i] > 0;
         if (!any) {
             bool more = next_chain < chains.size();
             for (auto &s : slots) more |= s.active() && s.k < s.chain->size();
             if (!more) break;
-            continue;  // only empty files / premature EOFs this round
+            step--;        // only empty files / premature EOFs this round: same staging slot again
+            continue;
         }
-        if (fcv_batch_process(batch_, fv.data()) != 0) {
+        if (fcv_batch_submit(batch_, h, fv[h].data()) != 0) {
             syslog(LOG_ERR, "folve-b200: batch step failed: %s", fcv_last_error());
             return false;
         }
-        if (fcv_batch_get_block_max(batch_, maxv.data()) != 0) ok = false;
-        parallel([&](int i) {
-            Slot &s = slots[(size_t)i];
-            if (!s.active() || fv[(size_t)i] == 0) return;
-            DrainSlot(s, hout + (size_t)i * out_stride, maxv.data() + (size_t)i * tblocks_);
-        });
+        pending[h] = true;
         steps_++;
-        for (int i = 0; i < slots_; i++) blocks_ += slots[(size_t)i].active() && fv[(size_t)i] > 0 ? slots[(size_t)i].nblocks : 0;
     }
+    // drain what is still in flight, oldest first
+    const int last = (int)(steps_ & 1);   // staging slot the next step would have used = the older one
+    if (pending[last]) drain(last);
+    if (pending[last ^ 1]) drain(last ^ 1);
     return ok;
 }
 

@@ -70,9 +70,11 @@ private:
     BatchConvolver() {}
     struct Slot;
     struct BlockPlan;
+    struct StepPlan;
+    class Workers;
     void FillBlock(Slot &s, BlockPlan &b, float *in_block);
     void FillSlot(Slot &s, float *in_step);
-    void DrainSlot(Slot &s, const float *out_step, const float *block_max);
+    void DrainSlot(Slot &s, const StepPlan &sp, const float *out_step, const float *block_max);
 
     fcv_filter *filter_ = nullptr;
     fcv_batch *batch_ = nullptr;

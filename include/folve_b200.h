@@ -198,6 +198,12 @@ int fcv_batch_get_max(fcv_batch *b, float *max_out /* [nstreams] */);
  * block (sound-processor.cc:120-123), so that a caller stepping several blocks at once
  * can still tell the running maximum at the block where a file ended. */
 int fcv_batch_get_block_max(fcv_batch *b, float *max_out /* [nstreams][blocks_per_step] */);
+/* The same two operations for a caller that keeps two steps in flight with fcv_batch_submit /
+ * fcv_batch_wait: the reset is enqueued behind the steps already submitted and ahead of the
+ * next one (no host synchronisation); the block maxima of the step submitted from host slot
+ * `slot` travel back with its output and are valid after fcv_batch_wait(b, slot). */
+int fcv_batch_reset_slot_async(fcv_batch *b, int slot);
+const float *fcv_batch_host_block_max_slot(fcv_batch *b, int slot /* -> [nstreams][blocks_per_step] */);
 
 /* cudaStream_t the batch launches on (as void*), for CUDA-event timing by the caller. */
 void *fcv_batch_cuda_stream(fcv_batch *b);
