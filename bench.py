@@ -139,19 +139,19 @@ def harness_run(so, wl, filter_dir, nthreads, nblocks):
     return nthreads * nblocks * fragm.value / wl.fs, wall
 
 
-def library_run(wl, filter_dir, nchains, files_per_chain, seconds_per_file, blocks_per_step, threads):
+def library_run(wl, filter_dir, nchains, files_per_chain, seconds_per_file, blocks_per_step, threads, pcm16):
     """BatchConvolver (folve_b200/host/batch-convolver.cc): gapless album chains of in-memory files
     through the batched submit layer; returns (audio_s, wall_s)."""
     L = C.CDLL(HOST_SO)
     L.fh_bench_library.restype = C.c_double
     L.fh_bench_library.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int,
-                                   C.POINTER(C.c_double)]
+                                   C.c_int, C.POINTER(C.c_double)]
     cfg = os.path.join(filter_dir, f"filter-{wl.fs}-{wl.ninp}.conf")
     if not os.path.exists(cfg):
         cfg = os.path.join(filter_dir, f"filter-{wl.fs}.conf")
     audio = C.c_double(0)
     wall = L.fh_bench_library(cfg.encode(), wl.fs, wl.ninp, 1, nchains, files_per_chain,
-                              int(seconds_per_file * wl.fs), blocks_per_step, threads, C.byref(audio))
+                              int(seconds_per_file * wl.fs), blocks_per_step, threads, 1 if pcm16 else 0, C.byref(audio))
     if wall <= 0:
         raise RuntimeError("fh_bench_library failed")
     return audio.value, wall
@@ -473,11 +473,14 @@ def main():
                     cores = len(os.sched_getaffinity(0))
                     harness_run(HOST_SO, wl, filter_dir, cores, 20)
                     a, w = harness_run(HOST_SO, wl, filter_dir, cores, 400)
-                    a2, w2 = library_run(wl, filter_dir, B, 2, 120.0, T, cores)
+                    a2, w2 = library_run(wl, filter_dir, B, 2, 120.0, T, cores, fmt == capi.PCM_S16)
+                    a3, w3 = library_run(wl, filter_dir, B, 2, 120.0, T, cores, False)
                     line["e2e"]["batch_convolver"] = {
                         "value": a2 / w2, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
-                        "what": f"BatchConvolver::Run: {B} gapless chains x 2 in-memory float files of ~120 s in flight at "
-                                f"once, {T} blocks per chain and step, SNDFILE in / SNDFILE out on {cores} host threads"}
+                        "wire_format": args.wire, "f32_wire_value": a3 / w3,
+                        "what": f"BatchConvolver::Run: {B} gapless chains x 2 in-memory files of ~120 s in flight at once, "
+                                f"{T} blocks per chain and step, SNDFILE in / SNDFILE out on {cores} host threads, two "
+                                f"steps in flight"}
                     line["e2e"]["soundprocessor_sync"] = {
                         "value": a / w, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
                         "what": "SoundProcessor::FillBuffer/WriteProcessed block loop, one file per host thread, "

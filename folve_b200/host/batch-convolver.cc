@@ -108,7 +108,7 @@ private:
 };
 
 BatchConvolver *BatchConvolver::Create(const std::string &config_file, int samplerate, int channels, int slots,
-                                       bool gapless, int device, int blocks_per_step) {
+                                       bool gapless, int device, int blocks_per_step, bool pcm16) {
     FilterConfig cfg;
     cfg.fsamp = samplerate;
     cfg.ninp = channels;
@@ -119,7 +119,8 @@ BatchConvolver *BatchConvolver::Create(const std::string &config_file, int sampl
         fcv_filter_unref(cfg.filter);
         return nullptr;
     }
-    fcv_batch *batch = fcv_batch_create_tiled(cfg.filter, slots, FCV_PCM_F32, FCV_PCM_F32, blocks_per_step);
+    const int wire = pcm16 ? FCV_PCM_S16 : FCV_PCM_F32;
+    fcv_batch *batch = fcv_batch_create_tiled(cfg.filter, slots, wire, wire, blocks_per_step);
     if (!batch) {
         syslog(LOG_ERR, "folve-b200: %s: %s", config_file.c_str(), fcv_last_error());
         fcv_filter_unref(cfg.filter);
@@ -141,6 +142,8 @@ BatchConvolver *BatchConvolver::Create(const std::string &config_file, int sampl
     bc->slots_ = slots;
     bc->tblocks_ = blocks_per_step;
     bc->gapless_ = gapless;
+    bc->pcm16_ = pcm16;
+    bc->sample_bytes_ = pcm16 ? sizeof(short) : sizeof(float);
     return bc;
 }
 
@@ -152,7 +155,13 @@ BatchConvolver::~BatchConvolver() {
 // Assemble the next block of a chain: FillBuffer on file k, and -- if that file
 // ends inside the block and gapless joining is on -- one top-up from file k+1
 // (PassoverProcessor, convolve-file-handler.cc:345-348).
-void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, float *in_block) {
+// sf_readf_* of `frames` frames into the block at `dst`, `frame_offset` frames in
+long BatchConvolver::ReadFrames(SNDFILE *in, void *dst, long frame_offset, long frames) const {
+    char *p = (char *)dst + (size_t)frame_offset * ninp_ * sample_bytes_;
+    return pcm16_ ? (long)sf_readf_short(in, (short *)p, frames) : (long)sf_readf_float(in, (float *)p, frames);
+}
+
+void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, void *in_block) {
     Chain &c = *s.chain;
     p = BlockPlan();
     // skip empty files: AddMoreSoundData returns false at once for them
@@ -162,7 +171,7 @@ void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, float *in_block) {
     if (s.k >= c.size()) return;
     ChainFile &a = c[s.k];
     int r = (int)(s.left < fragm_ ? s.left : fragm_);
-    r = (int)sf_readf_float(a.in, in_block, r);
+    r = (int)ReadFrames(a.in, in_block, 0, r);
     if (r == 0) {  // premature EOF: the file is over, nothing is written for it
         s.left = 0;
         s.reset_before_next = true;
@@ -185,7 +194,7 @@ void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, float *in_block) {
     // hand the half-filled block over to the alphabetically next file
     ChainFile &b = c[s.k + 1];
     int r2 = (int)((long)(fragm_ - p.fill) < b.frames ? (fragm_ - p.fill) : b.frames);
-    r2 = (int)sf_readf_float(b.in, in_block + (size_t)p.fill * ninp_, r2);
+    r2 = (int)ReadFrames(b.in, in_block, p.fill, r2);
     a.out_gapless = true;
     b.in_gapless = true;
     p.fill += r2;
@@ -209,14 +218,14 @@ void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, float *in_block) {
 // ends early where the per-file path would go on from a reset processor (end of a chain,
 // no hand-off, swallowed successor, premature EOF): a time-tiled step cannot reset a
 // stream between two of its blocks, and only the last block of a step may be short.
-void BatchConvolver::FillSlot(Slot &s, float *in_step) {
+void BatchConvolver::FillSlot(Slot &s, void *in_step) {
     s.nblocks = 0;
     s.fill = 0;
     s.reset_before_next = false;
-    const size_t in_stride = (size_t)fragm_ * ninp_;
+    const size_t in_stride = (size_t)fragm_ * ninp_ * sample_bytes_;
     while (s.nblocks < tblocks_) {
         BlockPlan &p = s.block[s.nblocks];
-        FillBlock(s, p, in_step + (size_t)s.nblocks * in_stride);
+        FillBlock(s, p, (char *)in_step + (size_t)s.nblocks * in_stride);
         if (p.fill > 0) {
             s.nblocks++;
             s.fill += p.fill;
@@ -225,17 +234,19 @@ void BatchConvolver::FillSlot(Slot &s, float *in_step) {
     }
 }
 
-void BatchConvolver::DrainSlot(Slot &s, const StepPlan &sp, const float *out_step, const float *block_max) {
+void BatchConvolver::DrainSlot(Slot &s, const StepPlan &sp, const void *out_step, const float *block_max) {
     Chain &c = *sp.chain;
-    const size_t out_stride = (size_t)fragm_ * nout_;
+    const size_t out_stride = (size_t)fragm_ * nout_ * sample_bytes_;
     if (sp.fresh) s.running_max = 0.0f;   // SoundProcessor::Reset() (sound-processor.cc:139-145)
     for (int t = 0; t < sp.nblocks; t++) {
         const BlockPlan &p = sp.block[t];
-        const float *out_block = out_step + (size_t)t * out_stride;
+        const char *out_block = (const char *)out_step + (size_t)t * out_stride;
         int pos = 0;
         for (int i = 0; i < p.nshare; i++) {
             ChainFile &f = c[p.share[i].file];
-            sf_writef_float(f.out, out_block + (size_t)pos * nout_, p.share[i].frames);
+            const char *src = out_block + (size_t)pos * nout_ * sample_bytes_;
+            if (pcm16_) sf_writef_short(f.out, (const short *)src, p.share[i].frames);
+            else sf_writef_float(f.out, (const float *)src, p.share[i].frames);
             f.written += p.share[i].frames;
             pos += p.share[i].frames;
         }
@@ -253,11 +264,12 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
     if (threads < 1) threads = 1;
     std::vector<Slot> slots((size_t)slots_);
     std::vector<int> fv[2] = {std::vector<int>((size_t)slots_, 0), std::vector<int>((size_t)slots_, 0)};
-    float *hin[2] = {(float *)fcv_batch_host_in_slot(batch_, 0), (float *)fcv_batch_host_in_slot(batch_, 1)};
-    const float *hout[2] = {(const float *)fcv_batch_host_out_slot(batch_, 0),
-                            (const float *)fcv_batch_host_out_slot(batch_, 1)};
+    char *hin[2] = {(char *)fcv_batch_host_in_slot(batch_, 0), (char *)fcv_batch_host_in_slot(batch_, 1)};
+    const char *hout[2] = {(const char *)fcv_batch_host_out_slot(batch_, 0),
+                           (const char *)fcv_batch_host_out_slot(batch_, 1)};
     if (!hin[0] || !hin[1] || !hout[0] || !hout[1]) return false;
-    const size_t in_stride = (size_t)tblocks_ * fragm_ * ninp_, out_stride = (size_t)tblocks_ * fragm_ * nout_;
+    const size_t in_stride = (size_t)tblocks_ * fragm_ * ninp_ * sample_bytes_;
+    const size_t out_stride = (size_t)tblocks_ * fragm_ * nout_ * sample_bytes_;
     size_t next_chain = 0;
     bool ok = true;
     Workers workers(threads > 1 ? threads : 0);

@@ -51,8 +51,12 @@ class BatchConvolver {
 public:
     // `slots` chains are in flight at once.  NULL on configuration or GPU failure.
     // blocks_per_step: 1, 2, 4 or 8 consecutive blocks of every chain per GPU step.
+    // pcm16: every file of every chain is 16-bit PCM in and out (what folve serves for 16-bit FLAC):
+    // samples cross the link as int16 (sf_readf_short / sf_writef_short) with libsndfile's
+    // int <-> float conversions done by the FFT kernels -- half the bytes of the float path, the same
+    // samples in the files.
     static BatchConvolver *Create(const std::string &config_file, int samplerate, int channels, int slots,
-                                  bool gapless, int device, int blocks_per_step = 1);
+                                  bool gapless, int device, int blocks_per_step = 1, bool pcm16 = false);
     ~BatchConvolver();
 
     int fragment_size() const { return fragm_; }
@@ -72,14 +76,17 @@ private:
     struct BlockPlan;
     struct StepPlan;
     class Workers;
-    void FillBlock(Slot &s, BlockPlan &b, float *in_block);
-    void FillSlot(Slot &s, float *in_step);
-    void DrainSlot(Slot &s, const StepPlan &sp, const float *out_step, const float *block_max);
+    void FillBlock(Slot &s, BlockPlan &b, void *in_block);
+    void FillSlot(Slot &s, void *in_step);
+    void DrainSlot(Slot &s, const StepPlan &sp, const void *out_step, const float *block_max);
+    long ReadFrames(SNDFILE *in, void *dst, long frame_offset, long frames) const;
 
     fcv_filter *filter_ = nullptr;
     fcv_batch *batch_ = nullptr;
     int fragm_ = 0, ninp_ = 0, nout_ = 0, slots_ = 0, tblocks_ = 1;
     bool gapless_ = true;
+    bool pcm16_ = false;
+    size_t sample_bytes_ = sizeof(float);   // of the wire format
     long blocks_ = 0, steps_ = 0;
 };
 

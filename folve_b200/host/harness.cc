@@ -10,6 +10,7 @@
 // both.  The caller protocol restated here is
 // ConvolveFileHandler::AddMoreSoundData (convolve-file-handler.cc:370-424) and
 // ConvolveFileHandler::PassoverProcessor (convolve-file-handler.cc:328-351).
+#include <math.h>
 #include <sndfile.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -237,20 +238,22 @@ int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits,
 // files of a chain in alphabetical order -- through folve_b200::BatchConvolver with
 // `slots` chains in flight.  PCM in/out is float, [frames][channels].
 // Returns the number of output channels, <0 on failure.
-int fh_run_library_tiled(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
-                         int nfiles, const int *chain_of_file, const float *const *pcm, const long *frames,
-                         float *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
-                         long *steps_out, int blocks_per_step) {
+// pcm16 != 0: PCM in/out is int16 (16-bit files, int16 on the wire) instead of float.
+static int RunLibrary(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
+                      int nfiles, const int *chain_of_file, const void *const *pcm, const long *frames,
+                      void *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
+                      long *steps_out, int blocks_per_step, int pcm16) {
     folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, slots, gapless != 0, SoundProcessor::Device(), blocks_per_step);
+        config_file, samplerate, channels, slots, gapless != 0, SoundProcessor::Device(), blocks_per_step, pcm16 != 0);
     if (!bc) return -1;
     const int nout = bc->output_channels();
     std::vector<folve_b200::Chain> chains;
     for (int i = 0; i < nfiles; i++) {
         if (chains.empty() || (i > 0 && chain_of_file[i] != chain_of_file[i - 1])) chains.emplace_back();
         folve_b200::ChainFile f;
-        f.in = sf_shim_open_memory_read(pcm[i], frames[i], channels, samplerate, SF_FORMAT_FLOAT);
-        f.out = sf_shim_open_memory_write(nout, samplerate, SF_FORMAT_FLOAT);
+        const int fmt = pcm16 ? SF_FORMAT_PCM_16 : SF_FORMAT_FLOAT;
+        f.in = sf_shim_open_memory_read(pcm[i], frames[i], channels, samplerate, fmt);
+        f.out = sf_shim_open_memory_write(nout, samplerate, fmt);
         f.frames = frames[i];
         chains.back().push_back(f);
     }
@@ -262,7 +265,7 @@ int fh_run_library_tiled(const char *config_file, int samplerate, int channels, 
         for (auto &f : c) {
             const long n = (long)sf_shim_memory_frames(f.out);
             out_frames[i] = n;
-            if (n > 0) memcpy(out_pcm[i], sf_shim_memory_data(f.out), (size_t)n * (size_t)nout * sizeof(float));
+            if (n > 0) memcpy(out_pcm[i], sf_shim_memory_data(f.out), (size_t)n * (size_t)nout * (pcm16 ? sizeof(short) : sizeof(float)));
             max_values[i] = f.max_value;
             gapless_flags[i] = (f.in_gapless ? 1 : 0) | (f.out_gapless ? 2 : 0);
             sf_close(f.in);
@@ -272,6 +275,24 @@ int fh_run_library_tiled(const char *config_file, int samplerate, int channels, 
     if (steps_out) *steps_out = bc->steps();
     delete bc;
     return ok ? nout : -2;
+}
+
+int fh_run_library_tiled(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
+                         int nfiles, const int *chain_of_file, const float *const *pcm, const long *frames,
+                         float *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
+                         long *steps_out, int blocks_per_step) {
+    return RunLibrary(config_file, samplerate, channels, gapless, slots, threads, nfiles, chain_of_file,
+                      (const void *const *)pcm, frames, (void *const *)out_pcm, out_frames, max_values, gapless_flags,
+                      steps_out, blocks_per_step, 0);
+}
+
+int fh_run_library_pcm16(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
+                         int nfiles, const int *chain_of_file, const short *const *pcm, const long *frames,
+                         short *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
+                         long *steps_out, int blocks_per_step) {
+    return RunLibrary(config_file, samplerate, channels, gapless, slots, threads, nfiles, chain_of_file,
+                      (const void *const *)pcm, frames, (void *const *)out_pcm, out_frames, max_values, gapless_flags,
+                      steps_out, blocks_per_step, 1);
 }
 
 int fh_run_library(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
@@ -292,27 +313,31 @@ static double NowSeconds() {
 // buffer), every chain in flight at once, output discarded.  Returns the wall seconds of
 // BatchConvolver::Run, <0 on error; *audio_seconds = what was convolved.
 double fh_bench_library(const char *config_file, int samplerate, int channels, int gapless, int nchains,
-                        int files_per_chain, long frames_per_file, int blocks_per_step, int threads,
+                        int files_per_chain, long frames_per_file, int blocks_per_step, int threads, int pcm16,
                         double *audio_seconds) {
     folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, nchains, gapless != 0, SoundProcessor::Device(), blocks_per_step);
+        config_file, samplerate, channels, nchains, gapless != 0, SoundProcessor::Device(), blocks_per_step, pcm16 != 0);
     if (!bc) return -1.0;
     const int nout = bc->output_channels();
     const long longest = frames_per_file + 4099;
     std::vector<float> pcm((size_t)longest * (size_t)channels);
+    std::vector<short> pcm_s16(pcm16 ? pcm.size() : 0);
     uint32_t s = 12345u;
     for (size_t i = 0; i < pcm.size(); i++) {
         s = s * 1664525u + 1013904223u;
         pcm[i] = 0.03f * ((float)(s >> 8) * (1.0f / 8388608.0f) - 1.0f);
+        if (pcm16) pcm_s16[i] = (short)lrintf(pcm[i] * 32768.0f);
     }
+    const int fmt = pcm16 ? SF_FORMAT_PCM_16 : SF_FORMAT_FLOAT;
+    const void *src = pcm16 ? (const void *)pcm_s16.data() : (const void *)pcm.data();
     std::vector<folve_b200::Chain> chains((size_t)nchains);
     double frames_total = 0.0;
     for (int c = 0; c < nchains; c++)
         for (int k = 0; k < files_per_chain; k++) {
             folve_b200::ChainFile f;
             f.frames = frames_per_file + 1 + (long)((c * 131 + k * 977) % 4097);
-            f.in = sf_shim_open_memory_read(pcm.data(), f.frames, channels, samplerate, SF_FORMAT_FLOAT);
-            f.out = sf_shim_open_null_write(nout, samplerate, SF_FORMAT_FLOAT);
+            f.in = sf_shim_open_memory_read(src, f.frames, channels, samplerate, fmt);
+            f.out = sf_shim_open_null_write(nout, samplerate, fmt);
             frames_total += (double)f.frames;
             chains[(size_t)c].push_back(f);
         }

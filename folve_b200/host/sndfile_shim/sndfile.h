@@ -81,6 +81,10 @@ int sf_close(SNDFILE *sndfile);
 sf_count_t sf_seek(SNDFILE *sndfile, sf_count_t frames, int whence);
 sf_count_t sf_readf_float(SNDFILE *sndfile, float *ptr, sf_count_t frames);
 sf_count_t sf_writef_float(SNDFILE *sndfile, const float *ptr, sf_count_t frames);
+/* 16-bit access for the batched submit layer's int16 wire format (libsndfile has both; the shim
+ * only implements them for 16-bit PCM files, where they are plain copies). */
+sf_count_t sf_readf_short(SNDFILE *sndfile, short *ptr, sf_count_t frames);
+sf_count_t sf_writef_short(SNDFILE *sndfile, const short *ptr, sf_count_t frames);
 int sf_command(SNDFILE *sndfile, int command, void *data, int datasize);
 const char *sf_strerror(SNDFILE *sndfile);
 const char *sf_version_string(void);

@@ -278,6 +278,38 @@ extern "C" sf_count_t sf_writef_float(SNDFILE *s, const float *ptr, sf_count_t f
     return frames;
 }
 
+extern "C" sf_count_t sf_readf_short(SNDFILE *s, short *ptr, sf_count_t frames) {
+    if (!s || s->mode != SFM_READ || frames <= 0 || s->subformat != SF_FORMAT_PCM_16) return 0;
+    const sf_count_t left = s->info.frames - s->pos;
+    if (frames > left) frames = left;
+    if (frames <= 0) return 0;
+    const size_t ch = (size_t)s->info.channels;
+    if (s->mem) {
+        memcpy(ptr, (const int16_t *)s->mem + (size_t)s->pos * ch, (size_t)frames * ch * sizeof(int16_t));
+    } else {
+        const size_t got = fread(ptr, sizeof(int16_t) * ch, (size_t)frames, s->fp);   // little-endian host
+        frames = (sf_count_t)got;
+    }
+    s->pos += frames;
+    return frames;
+}
+
+extern "C" sf_count_t sf_writef_short(SNDFILE *s, const short *ptr, sf_count_t frames) {
+    if (!s || s->mode != SFM_WRITE || frames <= 0 || s->subformat != SF_FORMAT_PCM_16) return 0;
+    const size_t n = (size_t)frames * (size_t)s->info.channels;
+    if (s->discard) {
+        long acc = 0;
+        for (size_t i = 0; i < n; i += 64) acc += ptr[i];   // touch the block like a consumer would
+        s->scratch.resize(sizeof(long));
+        memcpy(s->scratch.data(), &acc, sizeof(long));
+    } else {
+        s->w16.insert(s->w16.end(), ptr, ptr + n);
+    }
+    s->pos += frames;
+    s->info.frames = s->pos;
+    return frames;
+}
+
 extern "C" sf_count_t sf_shim_memory_frames(SNDFILE *s) { return s ? s->pos : 0; }
 
 extern "C" const void *sf_shim_memory_data(SNDFILE *s) {

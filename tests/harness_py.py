@@ -85,20 +85,22 @@ class Harness:
         return res, list(mx), list(flags)
 
     def run_library(self, config_file, samplerate, channels, chains, gapless=True, slots=4, threads=2,
-                    blocks_per_step=1):
-        """chains: list of lists of [frames, channels] float32 arrays.  Product only.
+                    blocks_per_step=1, pcm16=False):
+        """chains: list of lists of [frames, channels] float32 arrays (pcm16: int16 arrays = 16-bit
+        files in and out, int16 on the wire).  Product only.
         Returns (outputs per chain per file, max values, flags, steps)."""
         if not hasattr(self.L, "fh_run_library"):
             raise RuntimeError("fh_run_library is only in the product harness")
-        fn = self.L.fh_run_library_tiled
+        fn = self.L.fh_run_library_pcm16 if pcm16 else self.L.fh_run_library_tiled
         fn.restype = C.c_int
-        files = [np.ascontiguousarray(f, np.float32) for c in chains for f in c]
+        dt, ct = (np.int16, C.c_short) if pcm16 else (np.float32, C.c_float)
+        files = [np.ascontiguousarray(f, dt) for c in chains for f in c]
         cof = [ci for ci, c in enumerate(chains) for _ in c]
         n = len(files)
-        fp = C.POINTER(C.c_float)
+        fp = C.POINTER(ct)
         pin = (fp * n)(*[f.ctypes.data_as(fp) for f in files])
         frames = (C.c_long * n)(*[f.shape[0] for f in files])
-        outs = [np.zeros((f.shape[0], 64), np.float32) for f in files]
+        outs = [np.zeros((f.shape[0], 64), dt) for f in files]
         pout = (fp * n)(*[o.ctypes.data_as(fp) for o in outs])
         oframes = (C.c_long * n)()
         mx = (C.c_float * n)()

@@ -233,3 +233,32 @@ def test_batch_convolver_equals_per_file_path(dirs, T):
                     if files[fi].shape[0]:
                         assert mx[k] == pytest.approx(wmx[fi], abs=1e-7 if T == 1 else 2e-6), (gapless, slots, ci, fi)
                     k += 1
+
+
+@pytest.mark.parametrize("T", [1, 8])
+def test_batch_convolver_pcm16_wire_equals_per_file_16_bit_path(dirs, T):
+    """16-bit files in and out: the batched layer reads and writes int16 (sf_readf_short /
+    sf_writef_short, int16 on the link, conversions inside the FFT kernels); the per-file path
+    reads and writes floats that libsndfile converts.  Same samples in the files: bit for bit
+    at T = 1, within 1 LSB when the time-tiled MAC sums in a different order."""
+    P = H.product()
+    d, rate, ch, bits = dirs["crossfeed"]
+    conf = os.path.join(d, f"filter-{rate}.conf")
+    N = _fragm(d, rate, ch)["fragm"]
+    r = np.random.default_rng(78)
+    shapes = [[N + 1, 2 * N + 5, N + N // 3], [2 * N, N + 7], [5, 6, 7, 3 * N], [N], [9 * N + 11, 5 * N, 17 * N + 3]]
+    chains = [[r.integers(-9000, 9000, (n, ch)).astype(np.int16) for n in lens] for lens in shapes]
+    for gapless in (True, False):
+        outs, mx, fl, steps = P.run_library(conf, rate, ch, chains, gapless=gapless, slots=3, threads=3,
+                                            blocks_per_step=T, pcm16=True)
+        k = 0
+        for ci, files in enumerate(chains):
+            P.drop_pool()
+            want, wmx, wfl = P.run_chain(d, rate, ch, bits, files, gapless=gapless, in_format=H.SF_FORMAT_PCM_16,
+                                         out_format=H.SF_FORMAT_PCM_16)
+            for fi in range(len(files)):
+                assert outs[ci][fi].shape == want[fi].shape and outs[ci][fi].dtype == np.int16
+                diff = np.abs(outs[ci][fi].astype(np.int32) - want[fi].astype(np.int32))
+                assert diff.size == 0 or diff.max() <= (0 if T == 1 else 1), (gapless, ci, fi, int(diff.max()))
+                assert fl[k] == wfl[fi]
+                k += 1
