@@ -1,8 +1,11 @@
 // batch-convolver.cc -- see batch-convolver.h.
 #include "batch-convolver.h"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <syslog.h>
+#include <time.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -274,13 +277,24 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
     bool ok = true;
     Workers workers(threads > 1 ? threads : 0);
 
+    // FOLVE_B200_TRACE=1: where the host spends a step (seconds, summed over the run) on stderr
+    static const bool trace = getenv("FOLVE_B200_TRACE") != nullptr;
+    double t_wait = 0, t_drain = 0, t_assign = 0, t_fill = 0, t_submit = 0;
+    auto now = [] {
+        timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+    };
     // output of the step submitted from staging slot `h` -> files
     auto drain = [&](int h) {
+        const double t0 = now();
         if (fcv_batch_wait(batch_, h) != 0) {
             syslog(LOG_ERR, "folve-b200: batch step failed: %s", fcv_last_error());
             ok = false;
             return;
         }
+        const double t1 = now();
+        t_wait += t1 - t0;
         const float *bmax = fcv_batch_host_block_max_slot(batch_, h);
         workers.Run(slots_, [&](int i) {
             Slot &s = slots[(size_t)i];
@@ -292,6 +306,7 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
             blocks_ += fv[h][(size_t)i] > 0 ? slots[(size_t)i].plan[h].nblocks : 0;
             fv[h][(size_t)i] = 0;
         }
+        t_drain += now() - t1;
     };
 
     bool pending[2] = {false, false};
@@ -302,6 +317,7 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
             pending[h] = false;
         }
         // hand idle slots a new chain (from a reset state), reset where a hand-off chain ended
+        const double ta = now();
         for (int i = 0; i < slots_; i++) {
             Slot &s = slots[(size_t)i];
             if (s.active() && s.k >= s.chain->size()) s.chain = nullptr;
@@ -320,6 +336,8 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
                 s.plan[h].fresh = true;
             }
         }
+        const double tf = now();
+        t_assign += tf - ta;
         workers.Run(slots_, [&](int i) {
             Slot &s = slots[(size_t)i];
             fv[h][(size_t)i] = 0;
@@ -330,6 +348,8 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
             s.plan[h].fill = s.fill;
             fv[h][(size_t)i] = s.fill;
         });
+        const double ts = now();
+        t_fill += ts - tf;
         bool any = false;
         for (int i = 0; i < slots_; i++) any |= fv[h][(size_t)i] > 0;
         if (!any) {
@@ -343,6 +363,7 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
             syslog(LOG_ERR, "folve-b200: batch step failed: %s", fcv_last_error());
             return false;
         }
+        t_submit += now() - ts;
         pending[h] = true;
         steps_++;
     }
@@ -350,6 +371,9 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
     const int last = (int)(steps_ & 1);   // staging slot the next step would have used = the older one
     if (pending[last]) drain(last);
     if (pending[last ^ 1]) drain(last ^ 1);
+    if (trace)
+        fprintf(stderr, "BatchConvolver::Run: %ld steps; host seconds: wait %.3f drain %.3f assign+reset %.3f fill %.3f submit %.3f\n",
+                steps_, t_wait, t_drain, t_assign, t_fill, t_submit);
     return ok;
 }
 
