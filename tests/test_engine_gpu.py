@@ -382,3 +382,28 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(capi.FcvError):
         f.add(0, 0, [1.0], 0)                            # immutable after commit
     f.close()
+
+
+@pytest.mark.parametrize("signal", ["sine_on_bin", "sine_off_bin", "square_full_scale", "dc_step"])
+def test_deterministic_signals_against_truth(signal):
+    """SURVEY 8(c) golden set (ii): tones that sit exactly on an FFT bin and between two bins, a
+    full-scale square wave (every sample at +-1: the worst case for accumulation error) and a DC
+    step, through a 20000-tap stereo filter with a cross path -- engine vs oracle vs float64 truth."""
+    r = _rng(400)
+    spec = FilterSpec(2, 2, 20000)
+    env = np.exp(-np.arange(20000) / 3000.0)
+    for (i, o, g) in ((0, 0, 1.0), (1, 1, 1.0), (0, 1, 0.3)):
+        h = r.standard_normal(20000) * env
+        spec.add(i, o, (g * 0.9 / np.abs(h).sum()) * h, 0)          # sum |h| < 1.2 per output: no overflow at full scale
+    N = spec.fragm
+    n = np.arange(6 * N + 321)
+    if signal == "sine_on_bin":
+        k = 37                                                      # exactly bin 37 of the 2N-point transform
+        x = np.stack([np.sin(2 * np.pi * k * n / (2 * N)), np.cos(2 * np.pi * (k + 5) * n / (2 * N))], 1)
+    elif signal == "sine_off_bin":
+        x = np.stack([np.sin(2 * np.pi * 37.5 * n / (2 * N)), np.sin(2 * np.pi * 0.123456 * n)], 1)
+    elif signal == "square_full_scale":
+        x = np.stack([np.where((n // 50) % 2 == 0, 1.0, -1.0), np.where((n // 3) % 2 == 0, -1.0, 1.0)], 1)
+    else:
+        x = np.stack([(n >= N - 1).astype(np.float64), -(n >= 2 * N).astype(np.float64)], 1)
+    _three_way(spec, x.astype(np.float32))

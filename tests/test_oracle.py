@@ -119,3 +119,24 @@ def test_unused_output_is_silent():
     y, _ = _check(spec, x)
     assert np.all(y[:, 1] == 0.0)
     assert np.abs(y[:, 0] - x[:, 0]).max() < 1e-6
+
+
+@pytest.mark.parametrize("signal", ["sine_on_bin", "sine_off_bin", "square_full_scale"])
+def test_deterministic_signals(signal):
+    """Tones on and between FFT bins and a full-scale square wave (SURVEY 8(c) golden set ii):
+    the oracle against the float64 truth; the GPU suite runs the same inputs through the engine."""
+    r = _rng(400)
+    spec = FilterSpec(2, 2, 20000)
+    env = np.exp(-np.arange(20000) / 3000.0)
+    for (i, o, g) in ((0, 0, 1.0), (1, 1, 1.0), (0, 1, 0.3)):
+        h = r.standard_normal(20000) * env
+        spec.add(i, o, (g * 0.9 / np.abs(h).sum()) * h, 0)
+    N = spec.fragm
+    n = np.arange(4 * N + 321)
+    if signal == "sine_on_bin":
+        x = np.stack([np.sin(2 * np.pi * 37 * n / (2 * N)), np.cos(2 * np.pi * 42 * n / (2 * N))], 1)
+    elif signal == "sine_off_bin":
+        x = np.stack([np.sin(2 * np.pi * 37.5 * n / (2 * N)), np.sin(2 * np.pi * 0.123456 * n)], 1)
+    else:
+        x = np.stack([np.where((n // 50) % 2 == 0, 1.0, -1.0), np.where((n // 3) % 2 == 0, -1.0, 1.0)], 1)
+    _check(spec, x.astype(np.float32))
