@@ -407,3 +407,53 @@ def test_deterministic_signals_against_truth(signal):
     else:
         x = np.stack([(n >= N - 1).astype(np.float64), -(n >= 2 * N).astype(np.float64)], 1)
     _three_way(spec, x.astype(np.float32))
+
+
+def test_maximum_filter_size_128_partitions():
+    """MAXSIZE = 0x100000 taps (zita-config.h:61): 128 partitions of 8192; one stream block by block
+    and a 4-stream batch stepping 8 blocks at once (the window of 135 ring slots walks the TMA ring 17
+    times per pair) against the oracle."""
+    r = _rng(500)
+    spec = FilterSpec(1, 1, 0x100000)
+    taps = 0x100000 - 1000
+    spec.add(0, 0, r.standard_normal(taps) * np.exp(-np.arange(taps) / 250000.0) * 2e-4, 1000)
+    N = spec.fragm
+    f = _engine(spec)
+    assert f.partitions == 128 and f.ring_depth == 128
+    x = r.uniform(-0.5, 0.5, (16 * N, 1)).astype(np.float32)
+    yo = run_blocks(_oracle(spec), x, N)
+    s = capi.Stream(f)
+    y = run_blocks(s, x, N)
+    s.close()
+    assert np.abs(y - yo).max() < TOL_FS
+    B, T = 4, 8
+    bt = capi.Batch(f, B, capi.PCM_F32, capi.PCM_F32, blocks_per_step=T)
+    got = np.zeros((16 * N, 1), np.float32)
+    for k in range(2):
+        bt.host_in[:] = 0
+        bt.host_in[2] = x[k * T * N:(k + 1) * T * N]
+        bt.process()
+        got[k * T * N:(k + 1) * T * N] = bt.host_out[2]
+    bt.close()
+    f.close()
+    assert np.abs(got - yo).max() < TOL_FS
+
+
+def test_maximum_channel_counts_64x64():
+    """Convproc::MAXINP x MAXOUT = 64 x 64 (zita-fconfig.cc:49,55), every fourth pair populated."""
+    r = _rng(501)
+    spec = FilterSpec(64, 64, 9000)
+    for i in range(64):
+        for o in range(64):
+            if (i * 7 + o) % 4 == 0:
+                spec.add(i, o, r.standard_normal(3000 + 50 * ((i + o) % 7)) * 0.002, 100 * ((i + 3 * o) % 9))
+    N = spec.fragm
+    x = r.uniform(-0.2, 0.2, (3 * N + 11, 64)).astype(np.float32)
+    f = _engine(spec)
+    s = capi.Stream(f)
+    y = run_blocks(s, x, N)
+    s.close()
+    f.close()
+    yo = run_blocks(_oracle(spec), x, N)
+    assert y.shape == yo.shape == (3 * N + 11, 64)
+    assert np.abs(y - yo).max() < TOL_FS
