@@ -10,10 +10,10 @@
 #include "sound-processor.h"
 
 ProcessorPool::ProcessorPool(int max_available)
-    : max_per_config_(max_available) {}
+    : keep_per_config_(max_available) {}
 
 ProcessorPool::~ProcessorPool() {
-    for (auto &kv : pool_)
+    for (auto &kv : idle_)
         for (SoundProcessor *p : kv.second) delete p;
 }
 
@@ -41,7 +41,7 @@ SoundProcessor *ProcessorPool::GetOrCreate(const std::string &base_dir,
     }
 
     SoundProcessor *result;
-    while ((result = CheckOutOfPool(config_path)) != NULL) {
+    while ((result = TakeIdle(config_path)) != NULL) {
         if (result->ConfigStillUpToDate()) return result;
         delete result;  // configuration file was touched since
     }
@@ -61,8 +61,8 @@ void ProcessorPool::Return(SoundProcessor *processor) {
     }
     {
         std::lock_guard<std::mutex> l(pool_mutex_);
-        ProcessorList &list = pool_[processor->config_file()];
-        if (list.size() < max_per_config_) {
+        IdleList &list = idle_[processor->config_file()];
+        if (list.size() < keep_per_config_) {
             processor->Reset();
             list.push_back(processor);
             return;
@@ -71,10 +71,10 @@ void ProcessorPool::Return(SoundProcessor *processor) {
     delete processor;  // enough idle processors for this configuration
 }
 
-SoundProcessor *ProcessorPool::CheckOutOfPool(const std::string &config_path) {
+SoundProcessor *ProcessorPool::TakeIdle(const std::string &config_path) {
     std::lock_guard<std::mutex> l(pool_mutex_);
-    PoolMap::iterator found = pool_.find(config_path);
-    if (found == pool_.end() || found->second.empty()) return NULL;
+    IdleMap::iterator found = idle_.find(config_path);
+    if (found == idle_.end() || found->second.empty()) return NULL;
     SoundProcessor *result = found->second.front();
     found->second.pop_front();
     return result;

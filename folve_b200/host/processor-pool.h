@@ -34,14 +34,14 @@ public:
   void Return(SoundProcessor *processor);
 
 private:
-  typedef std::deque<SoundProcessor*> ProcessorList;
-  typedef std::map<std::string, ProcessorList> PoolMap;
+  typedef std::deque<SoundProcessor*> IdleList;
+  typedef std::map<std::string, IdleList> IdleMap;
 
-  SoundProcessor *CheckOutOfPool(const std::string &config_path);
+  SoundProcessor *TakeIdle(const std::string &config_path);
 
-  const size_t max_per_config_;
+  const size_t keep_per_config_;
   std::mutex pool_mutex_;
-  PoolMap pool_;
+  IdleMap idle_;
 };
 
 #endif  // FOLVE_B200_PROCESSOR_POOL_H

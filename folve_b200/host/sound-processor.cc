@@ -126,7 +126,7 @@ SoundProcessor::SoundProcessor(fcv_filter *filter, fcv_stream *stream, int fragm
     : filter_(filter), stream_(stream), fragm_(fragm), ninp_(ninp), nout_(nout),
       config_file_(cfg), config_file_timestamp_(cfg_mtime),
       buffer_(fcv_stream_buffer(stream)),
-      input_pos_(0), output_pos_(-1), max_out_value_observed_(0.0) {
+      filled_(0), drained_(-1), peak_seen_(0.0) {
     // a fresh stream is already in the reset state
 }
 
@@ -136,42 +136,42 @@ SoundProcessor::~SoundProcessor() {
 }
 
 int SoundProcessor::FillBuffer(SNDFILE *in) {
-    const int samples_needed = fragm_ - input_pos_;
+    const int samples_needed = fragm_ - filled_;
     assert(samples_needed);  // Otherwise, call WriteProcessed() first.
-    output_pos_ = -1;
-    const int r = sf_readf_float(in, buffer_ + input_pos_ * ninp_, samples_needed);
-    input_pos_ += r;
+    drained_ = -1;
+    const int r = sf_readf_float(in, buffer_ + filled_ * ninp_, samples_needed);
+    filled_ += r;
     return r;
 }
 
 void SoundProcessor::WriteProcessed(SNDFILE *out, int sample_count) {
-    if (output_pos_ < 0) Process();
-    assert(sample_count <= fragm_ - output_pos_);
-    sf_writef_float(out, buffer_ + output_pos_ * nout_, sample_count);
-    output_pos_ += sample_count;
-    if (output_pos_ == fragm_) input_pos_ = 0;
+    if (drained_ < 0) Process();
+    assert(sample_count <= fragm_ - drained_);
+    sf_writef_float(out, buffer_ + drained_ * nout_, sample_count);
+    drained_ += sample_count;
+    if (drained_ == fragm_) filled_ = 0;
 }
 
 void SoundProcessor::Process() {
-    // One synchronous block: the engine takes the first input_pos_ interleaved
+    // One synchronous block: the engine takes the first filled_ interleaved
     // frames of buffer_, treats the rest of the block as silence, and writes the
-    // first input_pos_ interleaved output frames back, raising the signed maximum.
-    if (fcv_stream_process(stream_, input_pos_, &max_out_value_observed_) != 0) {
+    // first filled_ interleaved output frames back, raising the signed maximum.
+    if (fcv_stream_process(stream_, filled_, &peak_seen_) != 0) {
         syslog(LOG_ERR, "folve-b200: processing failed: %s", fcv_last_error());
         memset(buffer_, 0, sizeof(float) * fragm_ * nout_);  // silence, never stale input
     }
-    output_pos_ = 0;
+    drained_ = 0;
 }
 
 bool SoundProcessor::ConfigStillUpToDate() const {
     return config_file_timestamp_ == ModificationTime(config_file_);
 }
 
-void SoundProcessor::ResetMaxValues() { max_out_value_observed_ = 0.0; }
+void SoundProcessor::ResetMaxValues() { peak_seen_ = 0.0; }
 
 void SoundProcessor::Reset() {
     fcv_stream_reset(stream_);
-    input_pos_ = 0;
-    output_pos_ = -1;
+    filled_ = 0;
+    drained_ = -1;
     ResetMaxValues();
 }

@@ -28,18 +28,18 @@ public:
                                 int samplerate, int channels);
   ~SoundProcessor();
 
-  // Fill Buffer from given sound file. Returns number of samples read.
+  // Reads up to the free part of the block from `in`; returns the frames read (sound-processor.h:38-39).
   int FillBuffer(SNDFILE *in);
 
   inline int input_channels() const { return ninp_; }
   inline int output_channels() const { return nout_; }
 
   // True once a whole block of `fragm` frames is buffered.
-  bool is_input_buffer_complete() const { return fragm_ == input_pos_; }
+  bool is_input_buffer_complete() const { return fragm_ == filled_; }
 
   // Processed frames not yet written (non-zero after a gapless hand-over).
   int pending_writes() const {
-    return output_pos_ >= 0 ? fragm_ - output_pos_ : 0;
+    return drained_ >= 0 ? fragm_ - drained_ : 0;
   }
 
   // Write `sample_count` processed frames, processing the block first if needed.
@@ -49,7 +49,7 @@ public:
   void Reset();
 
   // Largest (signed) output sample observed (>= 0.0).
-  float max_output_value() const { return max_out_value_observed_; }
+  float max_output_value() const { return peak_seen_; }
   void ResetMaxValues();
 
   const std::string &config_file() const { return config_file_; }
@@ -78,9 +78,9 @@ private:
   const time_t config_file_timestamp_;
 
   float *const buffer_;  // pinned, owned by stream_; fragm * max(ninp, nout) floats
-  int input_pos_;
-  int output_pos_;  // written position. -1, if not processed yet.
-  float max_out_value_observed_;
+  int filled_;
+  int drained_;  // frames of the processed block handed out so far; -1: block not processed yet
+  float peak_seen_;
 };
 
 #endif  // FOLVE_B200_SOUND_PROCESSOR_H
