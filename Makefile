@@ -9,12 +9,21 @@ LIB  = folve_b200/libfolve_b200.so
 
 all: $(LIB)
 
-$(LIB): $(CSRC)/fcv_engine.cu $(wildcard $(CSRC)/*.cuh) include/folve_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/fcv_engine.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
-	@grep -E "error|warning" $(CSRC)/ptxas.log || true
+# one object per kernel family (they compile in parallel: `make -j`), ptxas -v output kept per object
+CU_SRCS = fcv_engine fcv_k_fft fcv_k_fft13 fcv_k_mac fcv_k_mac_tma
+CU_OBJS = $(CU_SRCS:%=$(CSRC)/%.o)
+CU_HDRS = $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/folve_b200.h
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CU_HDRS)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(CSRC)/$*.ptxas.log || (cat $(CSRC)/$*.ptxas.log; exit 1)
+	@grep -E "error|warning" $(CSRC)/$*.ptxas.log || true
+
+$(LIB): $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS)
+	@cat $(CU_SRCS:%=$(CSRC)/%.ptxas.log) > $(CSRC)/ptxas.log
 
 clean:
-	rm -f $(LIB) $(CSRC)/ptxas.log
+	rm -f $(LIB) $(CU_OBJS) $(CSRC)/*ptxas.log
 
 .PHONY: all clean
 

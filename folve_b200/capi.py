@@ -67,6 +67,11 @@ def lib() -> C.CDLL:
         "fcv_stream_reset": (i, [vp]),
         "fcv_stream_buffer": (fp, [vp]),
         "fcv_stream_process": (i, [vp, i, fp]),
+        "fcv_stream_create_fmt": (vp, [vp, i, i]),
+        "fcv_stream_buffer_bytes": (C.c_size_t, [vp]),
+        "fcv_stream_submit": (i, [vp, i]),
+        "fcv_stream_await": (i, [vp, fp]),
+        "fcv_batch_set_copy_only": (i, [vp, i]),
         "fcv_stream_filter": (vp, [vp]),
         "fcv_batch_create": (vp, [vp, i, i, i]),
         "fcv_batch_create_tiled": (vp, [vp, i, i, i, i]),
@@ -170,13 +175,18 @@ class Filter:
 class Stream:
     """Mirror of one running Convproc as SoundProcessor drives it."""
 
-    def __init__(self, flt: Filter):
+    def __init__(self, flt: Filter, in_format=PCM_F32, out_format=PCM_F32):
         self.flt = flt
-        self._h = lib().fcv_stream_create(flt._h)
+        self.in_format, self.out_format = in_format, out_format
+        self._h = lib().fcv_stream_create_fmt(flt._h, in_format, out_format)
         if not self._h:
             raise FcvError(lib().fcv_last_error().decode())
-        n = flt.fragm * max(flt.ninp, flt.nout)
-        self.buffer = np.ctypeslib.as_array(lib().fcv_stream_buffer(self._h), shape=(n,))
+        nbytes = lib().fcv_stream_buffer_bytes(self._h)
+        raw = (C.c_char * nbytes).from_address(C.cast(lib().fcv_stream_buffer(self._h), C.c_void_p).value)
+        self.raw = np.frombuffer(raw, dtype=np.uint8)
+        self.buffer = self.raw.view(np.float32)          # the float view SoundProcessor uses
+        self.in_view = self.raw.view(_PCM_DTYPE[in_format])
+        self.out_view = self.raw.view(_PCM_DTYPE[out_format])
         self.max_value = 0.0
 
     def process(self, block: np.ndarray) -> np.ndarray:
@@ -188,6 +198,20 @@ class Stream:
         _check(lib().fcv_stream_process(self._h, frames, C.byref(m)))
         self.max_value = m.value
         return self.buffer[: frames * f.nout].reshape(frames, f.nout).copy()
+
+    def submit(self, block: np.ndarray):
+        """queue one block ([frames<=fragm, ninp] in the stream's input wire format) without waiting"""
+        frames = block.shape[0]
+        self.in_view[: frames * self.flt.ninp] = np.ascontiguousarray(block, self.in_view.dtype).reshape(-1)
+        self._frames = frames
+        _check(lib().fcv_stream_submit(self._h, frames))
+
+    def wait(self) -> np.ndarray:
+        m = C.c_float(self.max_value)
+        _check(lib().fcv_stream_await(self._h, C.byref(m)))
+        self.max_value = m.value
+        f = self.flt
+        return self.out_view[: self._frames * f.nout].reshape(self._frames, f.nout).copy()
 
     def reset(self):
         _check(lib().fcv_stream_reset(self._h))
@@ -289,6 +313,9 @@ class Batch:
         ms = C.c_float(0)
         _check(lib().fcv_batch_event_elapsed_ms(self._h, slot0, slot1, C.byref(ms)))
         return ms.value
+
+    def set_copy_only(self, on):
+        _check(lib().fcv_batch_set_copy_only(self._h, 1 if on else 0))
 
     def set_profiling(self, on):
         _check(lib().fcv_batch_set_profiling(self._h, 1 if on else 0))

@@ -29,6 +29,7 @@
 #include <stdint.h>
 
 #include "fcv_c2.cuh"
+#include "fcv_types.h"
 
 namespace fcv {
 
@@ -86,14 +87,6 @@ __host__ __device__ constexpr int smem_pad(int e) { return e + (e >> 4); }
 __host__ __device__ constexpr size_t fft_smem_bytes(int log2n, int nh = 2) {
     return (size_t)smem_pad((1 << log2n) * nh / 2) * sizeof(float2) + 64;
 }
-
-// Twiddle tables for one partition size, resident in device memory.
-struct FftTables {
-    const float2 *twA;     // [Q]   w_M^n = exp(-2 pi i n / M)
-    const float2 *twU;     // [M]   exp(-i pi k / M) for the bin stored at entry e
-    const float2 *twP[4];  // per pass t with stride S_t > 1: [(k1-1)*S_t + u] = exp(-2 pi i u k1 / Q_t)
-    const unsigned short *part;  // [M] entry holding the conjugate-partner bin (M - k) of entry e
-};
 
 // ---- complex helpers --------------------------------------------------------
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -365,7 +358,6 @@ __device__ __forceinline__ int partner_of(int e) {
 }
 
 // ---- PCM wire formats ---------------------------------------------------------
-enum { PCM_F32 = 0, PCM_S16 = 1, PCM_S24 = 2 };
 
 // Frames 2n and 2n+1 of channel `chan` of an interleaved block as (x[2n], x[2n+1]).
 // NCH = 2 / 1: stereo / mono blocks, one vector load per pair of frames;

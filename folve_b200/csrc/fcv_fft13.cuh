@@ -46,13 +46,6 @@ constexpr int ROW = 257;           // shared-memory row stride (elements): odd -
 constexpr int HALF_ELEMS = 16 * ROW;
 constexpr size_t HALF_BYTES = (size_t)HALF_ELEMS * sizeof(float2);
 
-struct Tables {
-    const float2 *twA0;  // [15][256]  w_M^(2 u k0),      k0 = 1..15   (half 0, pass A)
-    const float2 *twA1;  // [16][256]  w_M^(u (2 k0 + 1)), k0 = 0..15   (half 1, pass A, premultiply folded in)
-    const float2 *twB;   // [16][16]   w_256^(n0 k1)
-    const float2 *twU;   // [2 Q]      exp(-i pi k / M) for the bin at entry e
-};
-
 __host__ __device__ constexpr int out16(int r) { return (r >> 2) + 4 * (r & 3); }   // Bfly<16>::out
 __host__ __device__ constexpr int reg16(int k) { return ((k & 3) << 2) | (k >> 2); }  // its inverse
 

@@ -1,0 +1,244 @@
+// fcv_k_fft13.cu -- kernels and launches of the fragm = 8192 transforms (fcv_fft13.cuh): every
+// filter longer than 4096 taps (/root/reference/zita-fconfig.cc:74-77).  Role in the reference:
+// FFTW's r2c / c2r inside zita-convolver's Convlevel::process(), reached from
+// SoundProcessor::Process() (/root/reference/sound-processor.cc:98-127), with the
+// (de)interleave, zero padding, overlap-add, int/float conversion and maximum fused in.
+#include <cmath>
+#include <map>
+
+#include "fcv_internal.h"
+#include "fcv_fft13.cuh"
+
+using namespace fcv;
+
+#ifndef F13_INV_NT
+#define F13_INV_NT 256   // threads of the inverse kernel: 256 (2 CTAs/SM, <= 128 registers) or 128 (3 CTAs/SM)
+#endif
+constexpr int f13_min_ctas(int nt) { return nt >= 256 ? 2 : 3; }
+
+// Forward transform of the current block: one CTA = one half (blockIdx.x & 1) of the
+// spectra of C consecutive input channels (blockIdx.x >> 1 = channel group) of one
+// (stream, block): PCM and twiddles are fetched once for C transforms.
+template <class SEL, int FMT, int NCH, int C>
+__global__ void __launch_bounds__(128 * C, f13_min_ctas(128 * C))
+fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, int R, int T, int reset_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    constexpr int N = f13::N;
+    pdl_trigger();
+    pdl_wait();
+    const int h = blockIdx.x & 1, ch0 = (blockIdx.x >> 1) * C, b = blockIdx.y, bt = blockIdx.z;
+    const StreamDev s = sel.stream(b);
+    int frames = sel.frames(b) - bt * N;
+    frames = frames < 0 ? 0 : (frames > N ? N : frames);
+    int slot = sel.slot(b) + bt;
+    if (slot >= R) slot -= R;
+    float2 *rows[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) rows[c] = s.xring + (size_t)((ch0 + c) * R + slot) * N;
+    // per-block maximum mode: the inverse kernel of this block starts from zero
+    if (reset_max && blockIdx.x == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) s.bmax[bt] = 0.0f;  // this block's maximum starts from zero
+    if (frames == 0) {  // silence: its spectrum is zero
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            for (int e = threadIdx.x; e < f13::Q; e += 128 * C) rows[c][h * f13::Q + e] = make_float2(0.f, 0.f);
+        return;
+    }
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    const void *in = reinterpret_cast<const char *>(s.din) + (size_t)bt * N * ninp * wire;
+    if (h == 0) f13::fwd_half<0, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
+    else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
+}
+
+// Filter preparation (K6): src[row][N] floats -> dst[row][N] spectra, one half per CTA.
+__global__ void __launch_bounds__(128, f13_min_ctas(128))
+fwd13_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, f13::Tables tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    const size_t r = blockIdx.y;
+    float2 *rows[1] = {dst + r * f13::N};
+    if (blockIdx.x == 0) f13::fwd_half<0, PCM_F32, 1, 1, 128>(sm, tb, src + r * f13::N, 1, 0, f13::N, rows);
+    else f13::fwd_half<1, PCM_F32, 1, 1, 128>(sm, tb, src + r * f13::N, 1, 0, f13::N, rows);
+}
+
+// Signed maximum (>= 0) of one block over all output channels: warp reduction, then one
+// atomic per warp (positive floats order like their bit patterns).
+__device__ __forceinline__ void block_max_update13(float *dst, float m) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(m));
+}
+
+// Inverse transform of every (stream, output channel), T blocks one after the other
+// (block t+1 overlap-adds the tail block t just saved), with overlap-add, tail save,
+// re-interleave, float -> PCM and the signed maximum of the valid frames fused in.
+template <class SEL, int FMT, bool PF>
+__global__ void __launch_bounds__(F13_INV_NT, f13_min_ctas(F13_INV_NT))
+inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    constexpr int NT = F13_INV_NT;
+    __shared__ float red[NT / 32];
+    constexpr int N = f13::N, M = N;
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int o = blockIdx.x, b = blockIdx.y;
+    const StreamDev s = sel.stream(b);
+    const int fvb = sel.frames(b);
+    float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    float lmax = 0.0f;
+
+    for (int bt = 0; bt < T; bt++) {
+        int frames = fvb - bt * N;
+        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+        // entry 0 of the sequence to transform comes from the two real bins (DC / Nyquist products)
+        const float2 z0 = tid == 0 ? s.zc0[(size_t)o * T + bt] : make_float2(0.f, 0.f);
+        const float2 *yrow = s.Y + ((size_t)o * T + bt) * M;
+        if (PF && bt + 1 < T) {  // the next block's spectrum row (64 KB) is requested into L2 now
+#pragma unroll
+            for (int i = 0; i < (M * 8 / 128) / NT; i++)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + M + (size_t)(tid + i * NT) * 16));
+        }
+#pragma unroll 1
+        for (int j = tid; j < 256; j += NT) {
+            if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), j);
+            else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, j - 128);
+        }
+        __syncthreads();
+        f13::pass_b<+1, 2, NT>(sm, tb);
+        __syncthreads();
+        void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * nout * wire;
+        const float m = f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames);
+        lmax = fmaxf(lmax, m);
+        block_max_update13(s.bmax + bt, m);
+        if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+    if ((tid & 31) == 0) red[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; w++) lmax = fmaxf(lmax, red[w]);
+        // running maximum is >= 0, positive floats order like their bit patterns
+        if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
+    }
+}
+
+// ---- tables ---------------------------------------------------------------------------------
+template <class SEL, int FMT>
+static int set_attrs13() {
+    const int one = (int)f13::HALF_BYTES, two = 2 * (int)f13::HALF_BYTES;
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
+    CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    return 0;
+}
+
+namespace {
+struct Ctx13 {
+    bool have = false;
+    f13::Tables tab{};
+};
+std::mutex g_mu13;
+std::map<int, Ctx13> g_ctx13;
+}  // namespace
+
+// Twiddle tables of the fragm = 8192 transforms, double precision on the host; once per device.
+int fcv::fft13_tables(int device, f13::Tables *out) {
+    std::lock_guard<std::mutex> l(g_mu13);
+    Ctx13 &c = g_ctx13[device];
+    if (!c.have) {
+        const int M = f13::N, Q = f13::Q;
+        const double PI = 3.14159265358979323846264338327950288;
+        std::vector<float2> h((size_t)15 * 256 + 16 * 256 + 256 + 2 * Q);
+        auto unit = [&](double turns) {  // exp(-2 pi i turns)
+            const double a = -2.0 * PI * turns;
+            return make_float2((float)cos(a), (float)sin(a));
+        };
+        size_t o0 = 0, o1 = o0 + 15 * 256, oB = o1 + 16 * 256, oU = oB + 256;
+        for (int k0 = 1; k0 < 16; k0++)
+            for (int u = 0; u < 256; u++) h[o0 + (size_t)(k0 - 1) * 256 + u] = unit((double)(2 * u * k0 % M) / M);
+        for (int k0 = 0; k0 < 16; k0++)
+            for (int u = 0; u < 256; u++) h[o1 + (size_t)k0 * 256 + u] = unit((double)(u * (2 * k0 + 1) % M) / M);
+        for (int n0 = 0; n0 < 16; n0++)
+            for (int k1 = 0; k1 < 16; k1++) h[oB + (size_t)n0 * 16 + k1] = unit((double)(n0 * k1) / 256.0);
+        for (int e = 0; e < 2 * Q; e++) {
+            const int k = 2 * (e & (Q - 1)) + (e >> (f13::LOG2N - 1));
+            h[oU + e] = unit((double)k / (2.0 * M));
+        }
+        float2 *d = nullptr;
+        CU_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
+        CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        c.tab.twA0 = d + o0;
+        c.tab.twA1 = d + o1;
+        c.tab.twB = d + oB;
+        c.tab.twU = d + oU;
+        int rc = set_attrs13<BatchSel, PCM_F32>();
+        if (!rc) rc = set_attrs13<BatchSel, PCM_S16>();
+        if (!rc) rc = set_attrs13<BatchSel, PCM_S24>();
+        if (!rc) rc = set_attrs13<GroupSel, PCM_F32>();
+        if (!rc) rc = set_attrs13<GroupSel, PCM_S16>();
+        if (!rc) rc = set_attrs13<GroupSel, PCM_S24>();
+        if (rc) return rc;
+        CU_TRY(cudaFuncSetAttribute(fwd13_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f13::HALF_BYTES));
+        c.have = true;
+    }
+    *out = c.tab;
+    return 0;
+}
+
+void fcv::launch_filter_fft13(const fcv_filter *f, const float *dsrc, float2 *dst, int nrows) {
+    fwd13_raw_kernel<<<dim3(2, nrows), 128, f13::HALF_BYTES>>>(dsrc, dst, f->tb13);
+}
+
+// ---- launches -------------------------------------------------------------------------------
+// Stereo and mono blocks take the vector-load kernels (stereo: both channels per CTA), any other
+// channel count one channel per CTA with scalar loads.
+template <class SEL, int FMT>
+static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) {
+    const fcv_filter *f = a.f;
+    const int rm = a.per_block_max ? 1 : 0;
+    if (f->ninp == 2)
+        launch_k(fwd13_stream_kernel<SEL, FMT, 2, 2>, dim3(2, a.cnt, a.T), dim3(256), 2 * f13::HALF_BYTES, q, a.pdl, sel,
+                 f->tb13, f->ninp, a.R, a.T, rm);
+    else if (f->ninp == 1)
+        launch_k(fwd13_stream_kernel<SEL, FMT, 1, 1>, dim3(2, a.cnt, a.T), dim3(128), f13::HALF_BYTES, q, a.pdl, sel,
+                 f->tb13, f->ninp, a.R, a.T, rm);
+    else
+        launch_k(fwd13_stream_kernel<SEL, FMT, 0, 1>, dim3(2 * f->ninp, a.cnt, a.T), dim3(128), f13::HALF_BYTES, q, a.pdl,
+                 sel, f->tb13, f->ninp, a.R, a.T, rm);
+}
+template <class SEL>
+static void launch_fwd13_sel(const StepArgs &a, const SEL &sel, cudaStream_t q) {
+    if (a.in_fmt == PCM_F32) launch_fwd13_fmt<SEL, PCM_F32>(a, sel, q);
+    else if (a.in_fmt == PCM_S16) launch_fwd13_fmt<SEL, PCM_S16>(a, sel, q);
+    else launch_fwd13_fmt<SEL, PCM_S24>(a, sel, q);
+}
+void fcv::launch_fwd13(const StepArgs &a, cudaStream_t q) {
+    if (a.grp) launch_fwd13_sel<GroupSel>(a, *a.grp, q);
+    else launch_fwd13_sel<BatchSel>(a, a.bsel, q);
+}
+
+template <class SEL, int FMT>
+static void launch_inv13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) {
+    const dim3 grid(a.f->nout, a.cnt);
+    const size_t smem = 2 * f13::HALF_BYTES;
+    static const bool pf = !(getenv("FCV_INV_PF") && atoi(getenv("FCV_INV_PF")) == 0);
+    if (pf && a.T > 1) inv13_stream_kernel<SEL, FMT, true><<<grid, F13_INV_NT, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
+    else launch_k(inv13_stream_kernel<SEL, FMT, false>, grid, dim3(F13_INV_NT), smem, q, a.pdl, sel, a.f->tb13, a.f->nout, a.T);
+}
+template <class SEL>
+static void launch_inv13_sel(const StepArgs &a, const SEL &sel, cudaStream_t q) {
+    if (a.out_fmt == PCM_F32) launch_inv13_fmt<SEL, PCM_F32>(a, sel, q);
+    else if (a.out_fmt == PCM_S16) launch_inv13_fmt<SEL, PCM_S16>(a, sel, q);
+    else launch_inv13_fmt<SEL, PCM_S24>(a, sel, q);
+}
+void fcv::launch_inv13(const StepArgs &a, cudaStream_t q) {
+    if (a.grp) launch_inv13_sel<GroupSel>(a, *a.grp, q);
+    else launch_inv13_sel<BatchSel>(a, a.bsel, q);
+}

@@ -1,0 +1,45 @@
+// fcv_k_mac_tma.cu -- launch of the TMA-staged time-tiled complex multiply-accumulate
+// (fcv_mac_tma.cuh): T = 4 and T = 8 blocks per step, the batch path's roofline kernel.
+#include "fcv_internal.h"
+#include "fcv_mac_tma.cuh"
+
+using namespace fcv;
+
+// Returns false when the shape is not covered.
+template <int T, int S, int NS, int MC = tma::min_ctas(T, S)>
+static bool launch_tma(const StepArgs &a, int newest, cudaStream_t q) {
+    const fcv_filter *f = a.f;
+    const int M4 = f->fragm / 2;
+    if (M4 % tma::TPB != 0 || a.cnt < S) return false;
+    const size_t smem = tma::smem_bytes(S, NS);
+    // dynamic + static shared memory exceeds the 48 KB default; the attribute is per device
+    if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return false;
+    // one CTA per work item; FCV_MAC_PERSIST=n runs a persistent grid of n CTAs per SM instead
+    // (measured 5 % slower on SantaLucia x 1024 streams: 1.05 vs 1.00 ms, profiles/r01_experiments.md)
+    static const int persist = getenv("FCV_MAC_PERSIST") ? atoi(getenv("FCV_MAC_PERSIST")) : 0;
+    const int ntiles = M4 / tma::TPB, ngroups = (a.cnt + S - 1) / S, nitems = ntiles * ngroups * f->nout;
+    int grid = nitems;
+    if (persist > 0 && a.num_sms * persist < nitems) grid = a.num_sms * persist;
+    const float4 *H = reinterpret_cast<const float4 *>(f->dH);
+    float4 *Y = reinterpret_cast<float4 *>(a.Y);
+    tma::mac_tma_kernel<T, S, NS, MC><<<grid, tma::THREADS, smem, q>>>(a.bsel.st, a.cnt, f->dpairs, f->dpair_off,
+                                                                     f->dtt_rows, H, Y, M4, f->ring, a.R, newest,
+                                                                     f->nout, f->nrows, ntiles, ngroups, nitems);
+    return true;
+}
+
+bool fcv::launch_mac_tma(const StepArgs &a, int newest, cudaStream_t q) {
+    // T = 4 and T = 8 stream their rows through TMA-staged tiles whenever the shape allows
+    // (spectrum tiles of 2 KB, at least two streams); measured equal to the register-pipelined
+    // kernel at T = 8 and 2 % faster at T = 4.  FCV_MAC_TMA=0 turns it off, 2 / 3 select other
+    // stream tilings (experiments).
+    static const int use_tma = getenv("FCV_MAC_TMA") ? atoi(getenv("FCV_MAC_TMA")) : 1;
+    if (!use_tma) return false;
+    if (a.T == 8 && use_tma == 3 && launch_tma<8, 1, 12>(a, newest, q)) return true;
+    if (a.T == 8 && launch_tma<8, 2, 8>(a, newest, q)) return true;
+    if (a.T == 4 && use_tma == 2 && launch_tma<4, 4, 6>(a, newest, q)) return true;
+    if (a.T == 4 && launch_tma<4, 2, 8>(a, newest, q)) return true;
+    return false;
+}

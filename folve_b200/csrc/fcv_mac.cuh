@@ -24,34 +24,10 @@
 #include <stdint.h>
 
 #include "fcv_c2.cuh"
+#include "fcv_stream_dev.cuh"
+#include "fcv_types.h"
 
 namespace fcv {
-
-// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
-// attribute may start while its predecessor in the stream is still running; pdl_wait() returns
-// once the predecessor has completed and its writes are visible, pdl_trigger() lets the successor
-// be scheduled.  Both are no-ops for launches without the attribute (every batched launch).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
-
-// Per-stream device descriptor (array owned by a batch or a single stream).
-struct StreamDev {
-    float2 *xring;  // [ninp][P][M] input-spectra ring
-    float *tail;    // [nout][N]    overlap tails
-    const void *din;  // interleaved PCM in,  [N][ninp] wire format
-    void *dout;       // interleaved PCM out, [N][nout] wire format
-    float *maxv;    // running signed maximum
-    float *bmax;    // [T] signed maximum of each block of the last step (valid frames only)
-};
-
-constexpr int MAC_NO_MAX = 8;
-
-// One (input, partition) pair that feeds at least one output of the group.
-struct MacStep {
-    int inp;
-    int part;
-    int row[MAC_NO_MAX];  // filter row per output of the group, -1 = absent
-};
 
 // Two complex multiply-accumulates on a 16-byte vector: 4 FFMA2 (fcv_c2.cuh).
 __device__ __forceinline__ void cmac2(float4 &acc, const float4 x, const float4 h) {
@@ -73,11 +49,6 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p) {
 __device__ __forceinline__ float4 ld_keep(const float4 *p) {
     return __ldg(p);
 }
-
-struct TTPair {
-    int inp;      // input channel feeding this output
-    int rowbase;  // index into tt_rows: P consecutive filter-row numbers (absent -> the zero row)
-};
 
 // DC and Nyquist are real bins sharing entry 0 of a spectrum: their products are two real
 // multiply-accumulates over the partition history (the MAC kernels treat entry 0 as one
@@ -114,12 +85,14 @@ __device__ __forceinline__ float2 dcny_warp(const float2 *__restrict__ xring, co
 }
 
 // grid: x = M/2/TPB tiles of 2*TPB entries + 1 DC/Nyquist column, y = ceil(nstreams/S), z = output groups.
-template <int NO, int S, int TPB>
+// SEL: how the streams of the launch are addressed (fcv_stream_dev.cuh); every stream carries its
+// own ring position, Y rows and entry-0 slot.
+template <class SEL, int NO, int S, int TPB>
 __global__ void __launch_bounds__(TPB)
-mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__restrict__ steps,
-           const int *__restrict__ group_off, const float4 *__restrict__ H, float4 *__restrict__ Y,
-           int M4, int P, int pt, int nout, const TTPair *__restrict__ pairs, const int *__restrict__ pair_off,
-           const int *__restrict__ tt_rows, float2 *__restrict__ zc0, int Pfilt) {
+mac_kernel(const __grid_constant__ SEL sel, int nstreams, const MacStep *__restrict__ steps,
+           const int *__restrict__ group_off, const float4 *__restrict__ H,
+           int M4, int P, int nout, const TTPair *__restrict__ pairs, const int *__restrict__ pair_off,
+           const int *__restrict__ tt_rows, int Pfilt) {
     pdl_trigger();
     pdl_wait();
     const int e4 = blockIdx.x * TPB + threadIdx.x;
@@ -134,9 +107,10 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
                 const int oo = g * NO + o;
                 if (oo >= nout) break;
                 for (int s = 0; s < S && b0 + s < nstreams; s++) {
-                    const float2 z = dcny_warp(st[b0 + s].xring, pairs, pair_off, tt_rows, reinterpret_cast<const float2 *>(H),
-                                               oo, Pfilt, P, pt, 2 * M4, threadIdx.x);
-                    if (threadIdx.x == 0) zc0[(size_t)(b0 + s) * nout + oo] = z;
+                    const StreamDev sd = sel.stream(b0 + s);
+                    const float2 z = dcny_warp(sd.xring, pairs, pair_off, tt_rows, reinterpret_cast<const float2 *>(H),
+                                               oo, Pfilt, P, sel.slot(b0 + s), 2 * M4, threadIdx.x);
+                    if (threadIdx.x == 0) sd.zc0[oo] = z;
                 }
             }
         }
@@ -144,10 +118,15 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
     }
 
     const float4 *xb[S];
+    float4 *yb[S];
+    int pts[S];
 #pragma unroll
     for (int s = 0; s < S; s++) {
         const int b = min(b0 + s, nstreams - 1);
-        xb[s] = reinterpret_cast<const float4 *>(st[b].xring) + e4;
+        const StreamDev sd = sel.stream(b);
+        xb[s] = reinterpret_cast<const float4 *>(sd.xring) + e4;
+        yb[s] = reinterpret_cast<float4 *>(sd.Y) + e4;
+        pts[s] = sel.slot(b);
     }
     float4 acc[NO][S];
 #pragma unroll
@@ -170,7 +149,7 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
                 const bool live = t + u < t1;
                 const MacStep *sp = steps + (live ? t + u : t);
                 const int inp = __ldg(&sp->inp), part = __ldg(&sp->part);
-                int slot = pt - part;
+                int slot = pts[0] - part;
                 if (slot < 0) slot += P;
                 x[u] = ld_stream(xb[0] + (size_t)(inp * P + slot) * (size_t)M4);
 #pragma unroll
@@ -192,12 +171,13 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
     for (int t = t0; t < t1; t++) {
         const MacStep *sp = steps + t;
         const int inp = __ldg(&sp->inp), part = __ldg(&sp->part);
-        int slot = pt - part;
-        if (slot < 0) slot += P;
-        const size_t xo = (size_t)(inp * P + slot) * (size_t)M4;
         float4 x[S];
 #pragma unroll
-        for (int s = 0; s < S; s++) x[s] = ld_stream(xb[s] + xo);
+        for (int s = 0; s < S; s++) {
+            int slot = pts[s] - part;
+            if (slot < 0) slot += P;
+            x[s] = ld_stream(xb[s] + (size_t)(inp * P + slot) * (size_t)M4);
+        }
 #pragma unroll
         for (int o = 0; o < NO; o++) {
             const int row = __ldg(&sp->row[o]);
@@ -215,8 +195,7 @@ mac_kernel(const StreamDev *__restrict__ st, int nstreams, const MacStep *__rest
         if (oo < nout) {
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                if (b0 + s < nstreams)
-                    __stcs(Y + ((size_t)(b0 + s) * nout + oo) * (size_t)M4 + e4, acc[o][s]);
+                if (b0 + s < nstreams) __stcs(yb[s] + (size_t)oo * (size_t)M4, acc[o][s]);
             }
         }
     }

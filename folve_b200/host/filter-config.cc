@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <syslog.h>
 
 #include <string>
@@ -97,6 +98,7 @@ int CmdImpulseRead(Parser &ps, const char *args) {
     if (err) return err;
 
     const std::string path = (name[0] == '/') ? std::string(name) : ps.dir + "/" + name;
+    cfg->impulse_files.push_back(StampFile(path));
     SF_INFO info;
     memset(&info, 0, sizeof(info));
     SNDFILE *snd = sf_open(path.c_str(), SFM_READ, &info);
@@ -229,6 +231,24 @@ void LogError(const Parser &ps, int stat) {
 }
 
 }  // namespace
+
+FileStamp StampFile(const std::string &path) {
+    FileStamp s;
+    s.path = path;
+    struct stat st;
+    if (stat(path.c_str(), &st) == 0) {
+        s.sec = st.st_mtim.tv_sec;
+        s.nsec = st.st_mtim.tv_nsec;
+        s.size = (long long)st.st_size;
+    }
+    return s;
+}
+
+bool StampsCurrent(const std::vector<FileStamp> &stamps) {
+    for (const FileStamp &s : stamps)
+        if (!(StampFile(s.path) == s)) return false;
+    return true;
+}
 
 int FragmForSize(unsigned size) {
     // zita-fconfig.cc:74-77: start at Convproc::MAXQUANT, halve while above

@@ -16,9 +16,31 @@
 #ifndef FOLVE_B200_FILTER_CONFIG_H
 #define FOLVE_B200_FILTER_CONFIG_H
 
+#include <time.h>
+
+#include <string>
+#include <vector>
+
 #include "../../include/folve_b200.h"
 
 namespace folve_b200 {
+
+// Identity of a file at the moment it was read: nanosecond mtime and size (all zero if it
+// could not be stat'ed).  The reference compares the config file's mtime in whole seconds and
+// never looks at the impulse files (TODO at sound-processor.cc:130-131); here the config and every
+// /impulse/read file are stamped, so an edited or replaced impulse response is noticed.
+struct FileStamp {
+    std::string path;
+    time_t sec = 0;
+    long nsec = 0;
+    long long size = 0;
+    bool operator==(const FileStamp &o) const {
+        return path == o.path && sec == o.sec && nsec == o.nsec && size == o.size;
+    }
+};
+FileStamp StampFile(const std::string &path);
+// true if every file still has the stamp it was recorded with
+bool StampsCurrent(const std::vector<FileStamp> &stamps);
 
 // Same numeric values as the enum in /root/reference/zita-config.h:51.
 enum ConfigError {
@@ -34,6 +56,9 @@ struct FilterConfig {
     int ninp = 0;
     int nout = 0;
     int size = 0;
+    // every file named by an /impulse/read line that was reached (missing ones included), stamped
+    // BEFORE it was opened: a replacement racing the load is seen as a change next time
+    std::vector<FileStamp> impulse_files;
 };
 
 // Parses `config_file`.  Returns 0 on success (also when parsing stopped at an

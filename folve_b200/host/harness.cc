@@ -244,7 +244,7 @@ static int RunLibrary(const char *config_file, int samplerate, int channels, int
                       void *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
                       long *steps_out, int blocks_per_step, int pcm16) {
     folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, slots, gapless != 0, SoundProcessor::Device(), blocks_per_step, pcm16 != 0);
+        config_file, samplerate, channels, slots, gapless != 0, (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()), blocks_per_step, pcm16 != 0);
     if (!bc) return -1;
     const int nout = bc->output_channels();
     std::vector<folve_b200::Chain> chains;
@@ -316,7 +316,7 @@ double fh_bench_library(const char *config_file, int samplerate, int channels, i
                         int files_per_chain, long frames_per_file, int blocks_per_step, int threads, int pcm16,
                         double *audio_seconds) {
     folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, nchains, gapless != 0, SoundProcessor::Device(), blocks_per_step, pcm16 != 0);
+        config_file, samplerate, channels, nchains, gapless != 0, (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()), blocks_per_step, pcm16 != 0);
     if (!bc) return -1.0;
     const int nout = bc->output_channels();
     const long longest = frames_per_file + 4099;

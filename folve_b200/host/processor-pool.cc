@@ -1,5 +1,6 @@
 // processor-pool.cc -- see processor-pool.h; behaviour follows
-// /root/reference/processor-pool.cc:48-131.
+// /root/reference/processor-pool.cc:48-131 (folve, Copyright (C) 2012 Henner Zeller
+// <h.zeller@acm.org>, GPL v3 or later -- see COPYING; same terms here).
 #include "processor-pool.h"
 
 #include <stdio.h>
@@ -20,6 +21,13 @@ ProcessorPool::~ProcessorPool() {
 SoundProcessor *ProcessorPool::GetOrCreate(const std::string &base_dir,
                                            int sampling_rate, int channels,
                                            int bits, std::string *errmsg) {
+    return GetOrCreate(base_dir, sampling_rate, channels, bits, errmsg, std::string());
+}
+
+SoundProcessor *ProcessorPool::GetOrCreate(const std::string &base_dir,
+                                           int sampling_rate, int channels,
+                                           int bits, std::string *errmsg,
+                                           const std::string &placement_key) {
     // From specific to non-specific (processor-pool.cc:53-61).
     char name[3][96];
     snprintf(name[0], sizeof(name[0]), "/filter-%d-%d-%d.conf", sampling_rate, channels, bits);
@@ -40,12 +48,17 @@ SoundProcessor *ProcessorPool::GetOrCreate(const std::string &base_dir,
         return NULL;
     }
 
+    // a keyed request wants its album's GPU; an unkeyed one takes whatever is idle
+    int device = SoundProcessor::Device();
+    if (device < 0 && !placement_key.empty())
+        device = SoundProcessor::DeviceForKey(placement_key, SoundProcessor::DeviceCount());
     SoundProcessor *result;
-    while ((result = TakeIdle(config_path)) != NULL) {
+    while ((result = TakeIdle(config_path, device)) != NULL) {
         if (result->ConfigStillUpToDate()) return result;
-        delete result;  // configuration file was touched since
+        delete result;  // configuration or impulse file was touched since
     }
-    result = SoundProcessor::Create(config_path, sampling_rate, channels);
+    result = device >= 0 ? SoundProcessor::CreateOnDevice(config_path, sampling_rate, channels, device)
+                         : SoundProcessor::Create(config_path, sampling_rate, channels);
     if (result == NULL) {
         if (errmsg) *errmsg = "Problem parsing " + config_path;
         syslog(LOG_ERR, "filter-config %s is broken.", config_path.c_str());
@@ -71,11 +84,16 @@ void ProcessorPool::Return(SoundProcessor *processor) {
     delete processor;  // enough idle processors for this configuration
 }
 
-SoundProcessor *ProcessorPool::TakeIdle(const std::string &config_path) {
+SoundProcessor *ProcessorPool::TakeIdle(const std::string &config_path, int device) {
     std::lock_guard<std::mutex> l(pool_mutex_);
     IdleMap::iterator found = idle_.find(config_path);
-    if (found == idle_.end() || found->second.empty()) return NULL;
-    SoundProcessor *result = found->second.front();
-    found->second.pop_front();
-    return result;
+    if (found == idle_.end()) return NULL;
+    IdleList &list = found->second;
+    for (IdleList::iterator it = list.begin(); it != list.end(); ++it) {
+        if (device >= 0 && (*it)->device() != device) continue;
+        SoundProcessor *result = *it;
+        list.erase(it);
+        return result;
+    }
+    return NULL;
 }

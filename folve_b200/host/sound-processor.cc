@@ -1,12 +1,16 @@
 // sound-processor.cc -- see sound-processor.h.  Semantics follow
 // /root/reference/sound-processor.cc:34-145 line by line; the arithmetic runs
 // in the CUDA engine (include/folve_b200.h).
+//
+// The block protocol (FillBuffer / WriteProcessed / Process) is that of folve's
+// SoundProcessor, Copyright (C) 2012 Henner Zeller <h.zeller@acm.org>, GPL v3 or later
+// (see COPYING); this file is distributed under the same terms.
 #include "sound-processor.h"
 
 #include <assert.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/stat.h>
 #include <syslog.h>
 
 #include <map>
@@ -15,53 +19,86 @@
 #include "../../include/folve_b200.h"
 #include "filter-config.h"
 
+using folve_b200::FileStamp;
+
 namespace {
 
-std::mutex g_mutex;  // guards the device choice and the filter cache
-int g_device = -1;
+std::mutex g_mutex;  // guards the device choice, the live counts and the filter cache
+int g_device = -2;   // -2: not decided yet; kAnyDevice; or a fixed device
+int g_ndevices = -1;
+std::vector<int> g_live;              // live processors per device
+thread_local std::string t_placement_key;
 
-// Filter spectra stay resident in HBM and are shared by every processor made
-// from the same configuration file: one entry per (path, mtime, device).
+// Filter spectra stay resident in HBM and are shared by every processor made from the same
+// configuration: one entry per (config path, device), valid as long as the config file AND every
+// impulse file it read keep their nanosecond mtime and size.
 struct CachedFilter {
     fcv_filter *filter;
     int fragm, ninp, nout;
+    std::shared_ptr<const std::vector<FileStamp> > stamps;  // [0] = the config file itself
 };
-struct CacheKey {
-    std::string path;
-    time_t mtime;
-    int device;
-    bool operator<(const CacheKey &o) const {
-        if (path != o.path) return path < o.path;
-        if (mtime != o.mtime) return mtime < o.mtime;
-        return device < o.device;
-    }
-};
+typedef std::pair<std::string, int> CacheKey;
 std::map<CacheKey, CachedFilter> g_filters;
 
-time_t ModificationTime(const std::string &filename) {
-    struct stat st;
-    if (stat(filename.c_str(), &st) != 0) return 0;
-    return st.st_mtime;
+int DeviceCountLocked() {
+    if (g_ndevices < 0) {
+        const int n = fcv_device_count();
+        g_ndevices = n > 0 ? n : 0;
+        g_live.assign((size_t)(g_ndevices > 0 ? g_ndevices : 1), 0);
+    }
+    return g_ndevices;
 }
 
-int CurrentDevice() {
-    if (g_device < 0) {
+int FixedDeviceLocked() {
+    if (g_device == -2) {
         const char *env = getenv("FOLVE_B200_DEVICE");
-        g_device = env ? atoi(env) : 0;
+        g_device = (env && *env) ? atoi(env) : SoundProcessor::kAnyDevice;
     }
     return g_device;
+}
+
+void CountLive(int device, int delta) {
+    std::lock_guard<std::mutex> l(g_mutex);
+    DeviceCountLocked();
+    if (device >= 0 && (size_t)device < g_live.size()) g_live[(size_t)device] += delta;
+}
+
+uint32_t Crc32(const std::string &s) {  // reflected 0xEDB88320, as zlib.crc32
+    uint32_t c = 0xffffffffu;
+    for (unsigned char ch : s) {
+        c ^= ch;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+    }
+    return c ^ 0xffffffffu;
 }
 
 }  // namespace
 
 void SoundProcessor::SetDevice(int device) {
     std::lock_guard<std::mutex> l(g_mutex);
-    g_device = device;
+    g_device = device < 0 ? kAnyDevice : device;
 }
 
 int SoundProcessor::Device() {
     std::lock_guard<std::mutex> l(g_mutex);
-    return CurrentDevice();
+    return FixedDeviceLocked();
+}
+
+int SoundProcessor::DeviceCount() {
+    std::lock_guard<std::mutex> l(g_mutex);
+    return DeviceCountLocked();
+}
+
+int SoundProcessor::DeviceForKey(const std::string &key, int ndevices) {
+    return ndevices > 1 ? (int)(Crc32(key) % (uint32_t)ndevices) : 0;
+}
+
+void SoundProcessor::SetPlacementKey(const std::string &key) { t_placement_key = key; }
+
+int SoundProcessor::LiveProcessors(int device) {
+    std::lock_guard<std::mutex> l(g_mutex);
+    DeviceCountLocked();
+    return device >= 0 && (size_t)device < g_live.size() ? g_live[(size_t)device] : 0;
 }
 
 void SoundProcessor::PurgeFilterCache() {
@@ -72,23 +109,41 @@ void SoundProcessor::PurgeFilterCache() {
 
 SoundProcessor *SoundProcessor::Create(const std::string &config_file,
                                        int samplerate, int channels) {
+    int device;
+    {
+        std::lock_guard<std::mutex> l(g_mutex);
+        device = FixedDeviceLocked();
+        if (device == kAnyDevice) {
+            const int n = DeviceCountLocked();
+            if (!t_placement_key.empty()) {
+                device = DeviceForKey(t_placement_key, n);
+            } else {
+                device = 0;
+                for (int d = 1; d < n; d++)
+                    if (g_live[(size_t)d] < g_live[(size_t)device]) device = d;
+            }
+        }
+    }
+    return CreateOnDevice(config_file, samplerate, channels, device);
+}
+
+SoundProcessor *SoundProcessor::CreateOnDevice(const std::string &config_file,
+                                               int samplerate, int channels, int device) {
     CachedFilter cf;
-    const time_t mtime = ModificationTime(config_file);
     {
         // The reference serialises creation too (fftw_mutex, sound-processor.cc:29-43).
         std::lock_guard<std::mutex> l(g_mutex);
-        const CacheKey key{config_file, mtime, CurrentDevice()};
+        const CacheKey key(config_file, device);
         auto it = g_filters.find(key);
+        if (it != g_filters.end() && !folve_b200::StampsCurrent(*it->second.stamps)) {
+            // the config or one of its impulse files changed: that version is no longer wanted
+            fcv_filter_unref(it->second.filter);
+            g_filters.erase(it);
+            it = g_filters.end();
+        }
         if (it == g_filters.end()) {
-            // stale versions of the same file are no longer wanted
-            for (auto old = g_filters.begin(); old != g_filters.end();) {
-                if (old->first.path == config_file && old->first.device == key.device) {
-                    fcv_filter_unref(old->second.filter);
-                    old = g_filters.erase(old);
-                } else {
-                    ++old;
-                }
-            }
+            auto stamps = std::make_shared<std::vector<FileStamp> >();
+            stamps->push_back(folve_b200::StampFile(config_file));  // before reading it
             folve_b200::FilterConfig cfg;
             cfg.fsamp = samplerate;
             cfg.ninp = channels;
@@ -97,15 +152,17 @@ SoundProcessor *SoundProcessor::Create(const std::string &config_file,
                 if (cfg.filter) fcv_filter_unref(cfg.filter);
                 return NULL;  // parse error, or no /convolver/new (sound-processor.cc:44-48)
             }
-            if (fcv_filter_commit(cfg.filter, key.device) != 0) {
+            if (fcv_filter_commit(cfg.filter, device) != 0) {
                 syslog(LOG_ERR, "folve-b200: %s: %s", config_file.c_str(), fcv_last_error());
                 fcv_filter_unref(cfg.filter);
                 return NULL;
             }
+            stamps->insert(stamps->end(), cfg.impulse_files.begin(), cfg.impulse_files.end());
             cf.filter = cfg.filter;
             cf.fragm = cfg.fragm;
             cf.ninp = cfg.ninp;
             cf.nout = cfg.nout;
+            cf.stamps = stamps;
             it = g_filters.insert(std::make_pair(key, cf)).first;
         }
         cf = it->second;
@@ -117,22 +174,25 @@ SoundProcessor *SoundProcessor::Create(const std::string &config_file,
         fcv_filter_unref(cf.filter);
         return NULL;
     }
-    return new SoundProcessor(cf.filter, stream, cf.fragm, cf.ninp, cf.nout, config_file, mtime);
+    return new SoundProcessor(cf.filter, stream, cf.fragm, cf.ninp, cf.nout, config_file,
+                              (*cf.stamps)[0].sec, device, cf.stamps);
 }
 
 SoundProcessor::SoundProcessor(fcv_filter *filter, fcv_stream *stream, int fragm,
                                int ninp, int nout, const std::string &cfg,
-                               time_t cfg_mtime)
+                               time_t cfg_mtime, int device, const Stamps &stamps)
     : filter_(filter), stream_(stream), fragm_(fragm), ninp_(ninp), nout_(nout),
-      config_file_(cfg), config_file_timestamp_(cfg_mtime),
+      config_file_(cfg), config_file_timestamp_(cfg_mtime), device_(device), stamps_(stamps),
       buffer_(fcv_stream_buffer(stream)),
       filled_(0), drained_(-1), peak_seen_(0.0) {
     // a fresh stream is already in the reset state
+    CountLive(device_, +1);
 }
 
 SoundProcessor::~SoundProcessor() {
     fcv_stream_destroy(stream_);
     fcv_filter_unref(filter_);
+    CountLive(device_, -1);
 }
 
 int SoundProcessor::FillBuffer(SNDFILE *in) {
@@ -164,7 +224,9 @@ void SoundProcessor::Process() {
 }
 
 bool SoundProcessor::ConfigStillUpToDate() const {
-    return config_file_timestamp_ == ModificationTime(config_file_);
+    // The reference compares the config file's mtime only and leaves the impulse files as a
+    // TODO (sound-processor.cc:129-133); both are checked here, to the nanosecond and the byte.
+    return folve_b200::StampsCurrent(*stamps_);
 }
 
 void SoundProcessor::ResetMaxValues() { peak_seen_ = 0.0; }

@@ -2,6 +2,10 @@
 // sound-processor.h -- drop-in replacement for folve's SoundProcessor
 // (/root/reference/sound-processor.h:28-85) on top of the B200 engine.
 //
+// The public interface and the FillBuffer / WriteProcessed / Process block protocol are those
+// of folve's SoundProcessor, Copyright (C) 2012 Henner Zeller <h.zeller@acm.org>, GPL v3 or
+// later (see COPYING); this file is distributed under the same terms.
+//
 // The public interface is the reference's, member for member, so that
 // ConvolveFileHandler (convolve-file-handler.cc:78-80,335-348,373-377,408,418)
 // and ProcessorPool (processor-pool.cc:72,83,95,109) compile and behave
@@ -15,8 +19,11 @@
 #include <sndfile.h>
 #include <time.h>
 
+#include <memory>
 #include <string>
+#include <vector>
 
+namespace folve_b200 { struct FileStamp; }
 struct fcv_filter;
 struct fcv_stream;
 
@@ -57,9 +64,26 @@ public:
   bool ConfigStillUpToDate() const;
 
   // --- additions (not in the reference) ---
-  // CUDA device new processors are created on (default: $FOLVE_B200_DEVICE or 0).
+  // Placement of new processors on the GPUs of the box.  folve is ONE process; independent
+  // files / gapless album chains are spread over every usable GPU with no exchange between
+  // them (a processor, once made, carries its device with it through every gapless hand-off).
+  //   SetDevice(d >= 0) or $FOLVE_B200_DEVICE=d : every new processor on device d;
+  //   SetDevice(kAnyDevice), the default        : Create() picks the device that has the
+  //        fewest live processors, or -- when the calling thread has announced a placement
+  //        key (the album directory) -- DeviceForKey(key), a pure function of the key.
+  enum { kAnyDevice = -1 };
   static void SetDevice(int device);
-  static int Device();
+  static int Device();          // the fixed device, or kAnyDevice
+  static int DeviceCount();     // usable sm_100 devices (0 if none)
+  // CRC-32 of the key modulo the device count: the same album always lands on the same GPU
+  // (folve_b200/sharding.py computes the same function for the multi-process benchmark).
+  static int DeviceForKey(const std::string &key, int ndevices);
+  // Placement key of the processors this THREAD creates next ("" = none).
+  static void SetPlacementKey(const std::string &key);
+  static SoundProcessor *CreateOnDevice(const std::string &config_file, int samplerate, int channels,
+                                        int device);
+  int device() const { return device_; }
+  static int LiveProcessors(int device);
   // Block size and the engine handles, for the batched submit layer.
   int fragment_size() const { return fragm_; }
   fcv_stream *stream() const { return stream_; }
@@ -67,8 +91,10 @@ public:
   static void PurgeFilterCache();
 
 private:
+  typedef std::shared_ptr<const std::vector<folve_b200::FileStamp> > Stamps;
   SoundProcessor(fcv_filter *filter, fcv_stream *stream, int fragm, int ninp,
-                 int nout, const std::string &cfg_file, time_t cfg_mtime);
+                 int nout, const std::string &cfg_file, time_t cfg_mtime, int device,
+                 const Stamps &stamps);
   void Process();
 
   fcv_filter *const filter_;
@@ -76,6 +102,9 @@ private:
   const int fragm_, ninp_, nout_;
   const std::string config_file_;
   const time_t config_file_timestamp_;
+  const int device_;
+  // config file first, then every /impulse/read file: what ConfigStillUpToDate() re-checks
+  const Stamps stamps_;
 
   float *const buffer_;  // pinned, owned by stream_; fragm * max(ninp, nout) floats
   int filled_;

@@ -16,6 +16,7 @@
  *   Convproc::impdata_copy  zita-config.cc:274       fcv_filter_link
  *   (end of config())       zita-config.cc:343       fcv_filter_commit
  *   inpdata/process/outdata sound-processor.cc:106-125  fcv_stream_process
+ *                                                    (= fcv_stream_submit + fcv_stream_await)
  *   reset + start_process   sound-processor.cc:140,144  fcv_stream_reset
  *   stop_process/cleanup/delete sound-processor.cc:70-72 fcv_stream_destroy
  *
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FCV_ABI_VERSION 1
+#define FCV_ABI_VERSION 2
 
 /* Limits: Convproc::MAXINP / MAXOUT / MINPART / MAXQUANT (zita-fconfig.cc:49,55,74-75)
  * and MAXSIZE (zita-config.h:61). */
@@ -119,6 +120,11 @@ int fcv_filter_device(const fcv_filter *f);
 
 /* new Convproc + reset + start_process: all-zero state. */
 fcv_stream *fcv_stream_create(fcv_filter *f);
+/* The same with PCM wire formats other than float (FCV_PCM_*): the block buffer then holds
+ * in_format samples on the way in and out_format samples on the way out, converted on the
+ * device with libsndfile's scale factors (what sf_readf_short / sf_writef_short, or the 24-bit
+ * paths, would have done on the host around sound-processor.cc:80,91). */
+fcv_stream *fcv_stream_create_fmt(fcv_filter *f, int in_format, int out_format);
 /* stop_process + cleanup + delete (sound-processor.cc:70-72). */
 void fcv_stream_destroy(fcv_stream *s);
 /* Convproc::reset + start_process (sound-processor.cc:140,144): state identical
@@ -129,6 +135,8 @@ int fcv_stream_reset(fcv_stream *s);
  * SoundProcessor::buffer_ (sound-processor.cc:62-63).  Input frames are written
  * here interleaved; processed frames are read back from here interleaved. */
 float *fcv_stream_buffer(fcv_stream *s);
+/* Size of that block in bytes: fragm * max(ninp * input sample size, nout * output sample size). */
+size_t fcv_stream_buffer_bytes(const fcv_stream *s);
 
 /* SoundProcessor::Process() (sound-processor.cc:98-127) on the stream's own
  * buffer: the first `frames_valid` interleaved input frames are used, the rest
@@ -136,8 +144,22 @@ float *fcv_stream_buffer(fcv_stream *s);
  * `frames_valid` interleaved output frames are written back to the buffer.
  * `*max_inout`, if given, is raised to the largest SIGNED output sample seen
  * (the reference compares without fabs: sound-processor.cc:120-123).
- * Synchronous: returns when the output is in the buffer. */
+ * As in the reference, buffer content behind the first frames_valid input frames is zeroed
+ * (sound-processor.cc:99-103) and only frames_valid output frames are written back.
+ * Synchronous: returns when the output is in the buffer.
+ *
+ * Calls made at the same time from different threads on different streams of one filter
+ * (folve: one open file per thread) are coalesced inside the library into ONE launch sequence
+ * on the GPU; each caller still gets exactly the result of a call of its own. */
 int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_inout);
+
+/* The two halves of fcv_stream_process, for callers that keep several files going from one
+ * thread (north star: "one CUDA stream per open file"): submit queues the block that is in the
+ * stream's buffer and returns without waiting for the GPU; await returns when the output is in the
+ * buffer and raises *max_inout.  The buffer must not be touched in between.  One block per stream
+ * can be in flight; blocks of different streams submitted before their awaits travel together. */
+int fcv_stream_submit(fcv_stream *s, int frames_valid);
+int fcv_stream_await(fcv_stream *s, float *max_inout);
 
 fcv_filter *fcv_stream_filter(fcv_stream *s);
 
@@ -182,6 +204,11 @@ void *fcv_batch_host_in_slot(fcv_batch *b, int slot);
 void *fcv_batch_host_out_slot(fcv_batch *b, int slot);
 int fcv_batch_submit(fcv_batch *b, int slot, const int *frames_valid);
 int fcv_batch_wait(fcv_batch *b, int slot);
+
+/* Diagnostic for benchmarks: while on, fcv_batch_submit moves the PCM host->device and
+ * device->host exactly as usual but launches no kernel -- the host link's ceiling for the
+ * end-to-end loop, measured with the same code path.  Synchronises. */
+int fcv_batch_set_copy_only(fcv_batch *b, int on);
 
 /* One block for every stream on device-resident PCM (device_in -> device_out),
  * asynchronous on the batch's CUDA stream; no host copies.  Call

@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 40
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.fcv_abi_version() == 1
+    assert L.fcv_abi_version() == 2
 
 
 def test_binding_covers_header():
