@@ -448,7 +448,8 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     const size_t st_b = align_up(B * sizeof(StreamDev), 256);
     const size_t fv_b = align_up(B * sizeof(int), 256);
     const size_t zc_b = align_up(B * f->nout * (size_t)T * sizeof(float2), 256);
-    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + bmax_b + st_b + fv_b + zc_b;
+    const size_t arr_b = 256;   // single streams: arrival counter of the output-channel CTAs
+    const size_t total = xring_b + tail_b + din_b + dout_b + y_b + max_b + bmax_b + st_b + fv_b + zc_b + arr_b;
     cudaError_t e = cudaMalloc(&b->dmem, total);
     if (e != cudaSuccess) {
         fail(FCV_E_ALLOC, "cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
@@ -469,6 +470,7 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
     b->dst = (StreamDev *)p; p += st_b;
     b->dfv = (int *)p; p += fv_b;
     b->zc0 = (float2 *)p; p += zc_b;
+    unsigned *arrive = (unsigned *)p; p += arr_b;
     b->state_bytes_per_stream = (size_t)f->ninp * b->R * N * sizeof(float2);
 
     bool ok = cudaMemset(b->dmem, 0, total) == cudaSuccess;
@@ -501,6 +503,11 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
         hs[s].bmax = b->bmax + s * (size_t)T;
         hs[s].Y = b->Y + s * f->nout * T * N;
         hs[s].zc0 = b->zc0 + s * f->nout * T;
+        // single streams whose host block the device can address: the inverse kernel writes the
+        // output and the maximum there itself (host_copy_out)
+        hs[s].hout = b->in_zero_copy ? const_cast<void *>(b->hin_dev) : nullptr;
+        hs[s].hmax = b->in_zero_copy ? (float *)((unsigned char *)const_cast<void *>(b->hin_dev) + b->host_block) : nullptr;
+        hs[s].arrive = arrive;
     }
     ok = ok && cudaMemcpy(b->dst, hs.data(), B * sizeof(StreamDev), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&b->hfv, B * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
@@ -911,15 +918,20 @@ struct fcv_stream {
     FcvGroup *group = nullptr;
     int rc = 0;
     std::string err;
+    double t_submit = 0, t_launch = 0;   // tracing only
 };
 
 // A set of single-stream blocks that travel through the GPU as one launch sequence.
 struct FcvGroup {
     cudaStream_t q = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t t0 = nullptr;   // tracing only
+    double host_launch_us = 0;
     int n = 0;
     int members_left = 0;   // members that have not picked up their result yet
+    bool launched = false;  // the completion event has been recorded for this use of the group
     bool retired = false;   // completion seen, launch slot given back
+    unsigned long long gen = 0;   // counts the uses of the group object
     fcv_stream *m[GROUP_MAX];
     GroupSel sel;
 };
@@ -939,29 +951,94 @@ struct FcvCombiner {
     std::condition_variable cv;
     std::deque<fcv_stream *> pending;
     std::vector<FcvGroup *> groups, free_groups;
+    std::deque<FcvGroup *> flying;   // groups holding a launch slot, oldest first
     int inflight = 0;
-    int depth = 2;      // launch slots: groups in flight at once
+    int depth = 6;      // launch slots: groups in flight at once (measured: 2 -> 14.5 k, 4 -> 15.9 k, 6 -> 17.2 k x realtime on 16 threads)
     int group_max = GROUP_MAX;
-    bool broken = false;
+    // Waiting for a change of the queue (a leader finished launching, a launch slot came free): by
+    // default the few microseconds are spent polling `epoch` -- putting a caller to sleep on the
+    // condition variable and waking it again costs more than a whole block on the GPU.
+    std::atomic<unsigned long long> epoch{0};
+    bool spin = true;
+    // FCV_COMBINE_TRACE=1: where a block's time goes, printed when the filter is released
+    bool trace = false;
+    unsigned long long tr_groups = 0, tr_streams = 0;
+    double tr_launch_us = 0, tr_gpu_us = 0, tr_queue_us = 0, tr_total_us = 0;
 };
+
+static void combiner_notify(FcvCombiner *c) {   // with the mutex held
+    c->epoch.fetch_add(1, std::memory_order_release);
+    if (!c->spin) c->cv.notify_all();
+}
+static void combiner_wait(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
+    if (!c->spin) {
+        c->cv.wait(lk);
+        return;
+    }
+    const unsigned long long e = c->epoch.load(std::memory_order_relaxed);
+    lk.unlock();
+    for (int i = 0; i < 4000 && c->epoch.load(std::memory_order_acquire) == e; i++) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    lk.lock();
+}
+
+static double now_us() {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e6 * (double)t.tv_sec + 1e-3 * (double)t.tv_nsec;
+}
+
+static void combiner_report(FcvCombiner *c) {
+    if (c->trace && c->tr_groups)
+        fprintf(stderr, "fcv coalescer: %llu blocks in %llu groups (%.2f per group); per group: host launch %.1f us, "
+                        "GPU %.1f us; per block: queued %.1f us, submit->done %.1f us\n",
+                c->tr_streams, c->tr_groups, (double)c->tr_streams / c->tr_groups, c->tr_launch_us / c->tr_groups,
+                c->tr_gpu_us / c->tr_groups, c->tr_queue_us / c->tr_streams, c->tr_total_us / c->tr_streams);
+    c->tr_groups = c->tr_streams = 0;
+    c->tr_launch_us = c->tr_gpu_us = c->tr_queue_us = c->tr_total_us = 0;
+}
+
+static std::mutex g_trace_mu;
+static std::vector<FcvCombiner *> g_traced;
+static void combiner_report_all() {
+    std::lock_guard<std::mutex> l(g_trace_mu);
+    for (FcvCombiner *c : g_traced) combiner_report(c);
+}
 
 static FcvCombiner *combiner_create(fcv_filter *f) {
     FcvCombiner *c = new (std::nothrow) FcvCombiner();
     if (!c) return nullptr;
     c->f = f;
-    // FCV_COMBINE_DEPTH: groups in flight at once (default 2); FCV_COMBINE_MAX: streams per group
+    // FCV_COMBINE_DEPTH: groups in flight at once (default 6); FCV_COMBINE_MAX: streams per group
     // (default and maximum 32; 1 = the uncoalesced per-call path, for A/B measurements)
     if (const char *v = getenv("FCV_COMBINE_DEPTH")) c->depth = atoi(v) > 0 ? atoi(v) : 1;
     if (const char *v = getenv("FCV_COMBINE_MAX")) c->group_max = atoi(v) > 0 && atoi(v) <= GROUP_MAX ? atoi(v) : GROUP_MAX;
-    if (c->depth > 8) c->depth = 8;
+    if (c->depth > 32) c->depth = 32;
+    if (const char *v = getenv("FCV_COMBINE_SPIN")) c->spin = atoi(v) != 0;
+    c->trace = getenv("FCV_COMBINE_TRACE") != nullptr;
+    if (c->trace) {
+        std::lock_guard<std::mutex> l(g_trace_mu);
+        if (g_traced.empty()) atexit(combiner_report_all);
+        g_traced.push_back(c);
+    }
     return c;  // CUDA streams and events of the groups are made on first use
 }
 
 static void combiner_destroy(FcvCombiner *c) {
     if (!c) return;
+    if (c->trace) {
+        combiner_report(c);
+        std::lock_guard<std::mutex> l(g_trace_mu);
+        for (auto it = g_traced.begin(); it != g_traced.end(); ++it)
+            if (*it == c) { g_traced.erase(it); break; }
+    }
     for (FcvGroup *g : c->groups) {
         if (g->q) { cudaStreamSynchronize(g->q); cudaStreamDestroy(g->q); }
         if (g->done) cudaEventDestroy(g->done);
+        if (g->t0) cudaEventDestroy(g->t0);
         delete g;
     }
     delete c;
@@ -973,12 +1050,12 @@ static FcvGroup *combiner_take_group(FcvCombiner *c) {
         c->free_groups.pop_back();
         return g;
     }
-    if ((int)c->groups.size() >= c->depth + 6) return nullptr;  // all waiting to be picked up
     FcvGroup *g = new (std::nothrow) FcvGroup();
     if (!g) return nullptr;
     if (cudaSetDevice(c->f->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&g->q, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&g->done, c->trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess ||
+        (c->trace && cudaEventCreate(&g->t0) != cudaSuccess)) {
         if (g->q) cudaStreamDestroy(g->q);
         delete g;
         return nullptr;
@@ -999,9 +1076,12 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
     CU_TRY(cudaSetDevice(f->device));
     const size_t N = (size_t)f->fragm;
     const fcv_batch *b0 = g->m[0]->b;
+    const double h0 = c->trace ? now_us() : 0;
+    if (c->trace) cudaEventRecord(g->t0, g->q);
     for (int i = 0; i < g->n; i++) {
         fcv_stream *s = g->m[i];
         fcv_batch *b = s->b;
+        if (c->trace) s->t_launch = h0;
         g->sel.st[i] = b->dst;
         g->sel.fv[i] = s->frames_valid;
         g->sel.pt[i] = (int)(b->step % (unsigned long long)b->R);
@@ -1025,9 +1105,10 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
     for (int i = 0; i < g->n; i++) {
         fcv_stream *s = g->m[i];
         fcv_batch *b = s->b;
-        // The first frames_valid output frames go back into the block (sound-processor.cc:116-125),
-        // the block's maximum into the mirror behind it.  A full block whose output fills the
-        // whole host block comes back together with the maximum in one copy.
+        b->step++;
+        if (b->in_zero_copy) continue;   // the inverse kernel has written output and maximum to the host block
+        // Staged variant (FCV_STREAM_ZEROCOPY=0): the first frames_valid output frames go back into
+        // the block (sound-processor.cc:116-125), the block's maximum into the mirror behind it.
         const size_t out_bytes = (size_t)s->frames_valid * f->nout * pcm_bytes(b->out_fmt);
         if (out_bytes == b->out_block && b->out_block == b->host_block) {
             CU_TRY(cudaMemcpyAsync(b->hin, b->dout, b->out_block + sizeof(float), cudaMemcpyDeviceToHost, g->q));
@@ -1035,10 +1116,10 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
             if (out_bytes) CU_TRY(cudaMemcpyAsync(b->hin, b->dout, out_bytes, cudaMemcpyDeviceToHost, g->q));
             CU_TRY(cudaMemcpyAsync(b->hin + b->host_block, b->maxv, sizeof(float), cudaMemcpyDeviceToHost, g->q));
         }
-        b->step++;
     }
     (void)N;
     CU_TRY(cudaEventRecord(g->done, g->q));
+    if (c->trace) g->host_launch_us = now_us() - h0;
     return 0;
 }
 
@@ -1046,7 +1127,17 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
 static void combiner_pump(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
     while (!c->pending.empty() && c->inflight < c->depth) {
         FcvGroup *g = combiner_take_group(c);
-        if (!g) return;
+        if (!g) {   // no CUDA stream / event to be had: everything queued fails
+            for (fcv_stream *s : c->pending) {
+                s->rc = FCV_E_CUDA;
+                s->err = "cannot create a CUDA stream for the launch group";
+                s->group = nullptr;
+                s->state = fcv_stream::DONE;
+            }
+            c->pending.clear();
+            combiner_notify(c);
+            return;
+        }
         // everything queued with the wire formats of the oldest request, oldest first
         const fcv_batch *b0 = c->pending.front()->b;
         g->n = 0;
@@ -1063,7 +1154,10 @@ static void combiner_pump(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
         }
         g->members_left = g->n;
         g->retired = false;
+        g->launched = false;
+        g->gen++;
         c->inflight++;
+        c->flying.push_back(g);
         lk.unlock();
         const int rc = launch_group(c, g);
         const std::string err = rc ? g_err : std::string();
@@ -1073,8 +1167,49 @@ static void combiner_pump(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
             g->m[i]->err = err;
             g->m[i]->state = fcv_stream::INFLIGHT;   // on failure the event wait below returns at once or fails too
         }
-        c->cv.notify_all();
+        g->launched = true;
+        combiner_notify(c);
     }
+}
+
+// With the mutex held: wait (unlocked) for the completion event of a launched group and, if nobody
+// else did meanwhile, give its launch slot back and mark its members done.
+static void combiner_finish(FcvCombiner *c, FcvGroup *g, std::unique_lock<std::mutex> &lk) {
+    const unsigned long long gen = g->gen;
+    lk.unlock();
+    cudaError_t e = cudaSetDevice(c->f->device);
+    if (e == cudaSuccess) e = cudaEventSynchronize(g->done);
+    lk.lock();
+    if (g->gen != gen || g->retired) return;   // somebody else saw it complete (the object may be in use again)
+    g->retired = true;
+    c->inflight--;
+    if (c->trace) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g->t0, g->done) == cudaSuccess) c->tr_gpu_us += 1e3 * ms;
+        const double t = now_us();
+        c->tr_groups++;
+        c->tr_streams += (unsigned long long)g->n;
+        c->tr_launch_us += g->host_launch_us;
+        for (int i = 0; i < g->n; i++) {
+            c->tr_queue_us += g->m[i]->t_launch - g->m[i]->t_submit;
+            c->tr_total_us += t - g->m[i]->t_submit;
+        }
+    }
+    for (auto it = c->flying.begin(); it != c->flying.end(); ++it)
+        if (*it == g) { c->flying.erase(it); break; }
+    for (int i = 0; i < g->n; i++) {
+        fcv_stream *m = g->m[i];
+        if (e != cudaSuccess && m->rc == 0) {
+            m->rc = FCV_E_CUDA;
+            m->err = std::string("convolution failed: ") + cudaGetErrorString(e);
+        }
+        m->state = fcv_stream::DONE;
+    }
+    combiner_notify(c);   // members pick up their result
+    // The thread that saw the group complete is awake and holds a free launch slot: it sends off
+    // whatever queued up meanwhile before it returns to its own caller (a queued caller asleep on
+    // the condition variable would take tens of microseconds to get there, with the GPU idle).
+    combiner_pump(c, lk);
 }
 
 extern "C" fcv_stream *fcv_stream_create_fmt(fcv_filter *f, int in_format, int out_format) {
@@ -1102,6 +1237,7 @@ extern "C" int fcv_stream_submit(fcv_stream *s, int frames_valid) {
     if (s->state != fcv_stream::IDLE) return fail(FCV_E_STATE, "stream has a block in flight: call fcv_stream_await first");
     s->frames_valid = frames_valid;
     s->rc = 0;
+    if (c->trace) s->t_submit = now_us();
     s->state = fcv_stream::PENDING;
     c->pending.push_back(s);
     combiner_pump(c, lk);
@@ -1117,41 +1253,31 @@ extern "C" int fcv_stream_await(fcv_stream *s, float *max_inout) {
         switch (s->state) {
             case fcv_stream::IDLE:
                 return fail(FCV_E_STATE, "no block was submitted");
-            case fcv_stream::PENDING:
+            case fcv_stream::PENDING: {
                 combiner_pump(c, lk);
-                if (s->state == fcv_stream::PENDING) c->cv.wait(lk);
-                break;
-            case fcv_stream::LAUNCHING:
-                c->cv.wait(lk);
-                break;
-            case fcv_stream::INFLIGHT: {
-                FcvGroup *g = s->group;
-                lk.unlock();
-                cudaError_t e = cudaSetDevice(b->f->device);
-                if (e == cudaSuccess) e = cudaEventSynchronize(g->done);
-                lk.lock();
-                if (!g->retired) {
-                    g->retired = true;
-                    c->inflight--;
-                    for (int i = 0; i < g->n; i++) {
-                        fcv_stream *m = g->m[i];
-                        if (e != cudaSuccess && m->rc == 0) {
-                            m->rc = FCV_E_CUDA;
-                            m->err = std::string("convolution failed: ") + cudaGetErrorString(e);
-                        }
-                        m->state = fcv_stream::DONE;
-                    }
-                    c->cv.notify_all();   // members pick up their result, queued callers find a free slot
-                }
+                if (s->state != fcv_stream::PENDING) break;
+                // every launch slot is taken: see the oldest group in flight through (its members
+                // may all belong to this very thread, waiting to be awaited later) ...
+                FcvGroup *oldest = nullptr;
+                for (FcvGroup *g : c->flying)
+                    if (g->launched && !g->retired) { oldest = g; break; }
+                if (oldest) combiner_finish(c, oldest, lk);
+                else combiner_wait(c, lk);   // ... or wait for the leader that is launching right now
                 break;
             }
+            case fcv_stream::LAUNCHING:
+                combiner_wait(c, lk);
+                break;
+            case fcv_stream::INFLIGHT:
+                combiner_finish(c, s->group, lk);
+                break;
             case fcv_stream::DONE: {
                 FcvGroup *g = s->group;
                 s->group = nullptr;
                 s->state = fcv_stream::IDLE;
-                if (--g->members_left == 0) {
+                if (g && --g->members_left == 0) {
                     c->free_groups.push_back(g);
-                    c->cv.notify_all();
+                    combiner_notify(c);
                 }
                 const int rc = s->rc;
                 if (rc) return fail(rc, "%s", s->err.c_str());

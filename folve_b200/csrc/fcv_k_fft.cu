@@ -154,6 +154,10 @@ inv_stream_kernel(const __grid_constant__ SEL sel, FftTables tb, int nout, int T
         // running maximum is >= 0, positive floats order like their bit patterns
         if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
     }
+    if (SEL::kSingle && s.hout) {
+        const int fr = fvb < 0 ? 0 : (fvb > N ? N : fvb);
+        host_copy_out(s, nout, (size_t)fr * nout * (out_fmt == PCM_S16 ? 2 : 4), tid, NT);
+    }
 }
 
 #define DISPATCH_LOG2N(l2, CALL)                    \

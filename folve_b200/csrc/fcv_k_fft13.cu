@@ -125,6 +125,10 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
         // running maximum is >= 0, positive floats order like their bit patterns
         if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
     }
+    if (SEL::kSingle && s.hout) {
+        const int fr = fvb < 0 ? 0 : (fvb > N ? N : fvb);
+        host_copy_out(s, nout, (size_t)fr * nout * wire, tid, NT);
+    }
 }
 
 // ---- tables ---------------------------------------------------------------------------------

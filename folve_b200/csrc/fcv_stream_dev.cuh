@@ -32,9 +32,15 @@ struct StreamDev {
     float *bmax;    // [T] signed maximum of each block of the last step (valid frames only)
     float2 *Y;      // [nout][T][M] accumulated output spectra of the step
     float2 *zc0;    // [nout][T]    entry 0 of the sequences the inverse transform starts from
+    // single streams only (else null): the caller's pinned block as the device sees it, the mirror
+    // of the block maximum behind it, and the count of output-channel CTAs that have finished
+    void *hout;
+    float *hmax;
+    unsigned *arrive;
 };
 
 struct BatchSel {
+    static constexpr bool kSingle = false;
     const StreamDev *st;
     const int *fv;   // valid frames per stream, or nullptr: fv_all for every stream
     int fv_all;
@@ -44,8 +50,38 @@ struct BatchSel {
     __device__ __forceinline__ int slot(int) const { return pt; }
 };
 
+// Single-stream path: the output-channel CTA of a stream that finishes LAST copies the stream's
+// interleaved output block (just written to device memory by all of them, still in L2) and the
+// block maximum into the caller's pinned host block -- coalesced 16-byte stores over the link
+// instead of one device->host copy operation (a driver call and a copy-engine transaction) per
+// stream and block.  Only the first out_bytes of the block are written, as the reference writes
+// back only the frames it read (sound-processor.cc:116-125).  Call with all threads of the CTA,
+// after the CTA's last store to s.dout and its update of s.maxv.
+__device__ __forceinline__ void host_copy_out(const StreamDev &s, int nctas, size_t out_bytes, int tid, int nt) {
+    __shared__ int is_last;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();   // this CTA's output and maximum before its arrival
+        is_last = atomicAdd(s.arrive, 1u) == (unsigned)(nctas - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();       // the other CTAs' output after their arrivals
+    const int4 *src = reinterpret_cast<const int4 *>(s.dout);
+    int4 *dst = reinterpret_cast<int4 *>(s.hout);
+    const size_t n16 = out_bytes / 16;
+    for (size_t i = tid; i < n16; i += nt) dst[i] = __ldcg(src + i);
+    for (size_t i = n16 * 16 + tid; i < out_bytes; i += nt)
+        reinterpret_cast<unsigned char *>(s.hout)[i] = __ldcg(reinterpret_cast<const unsigned char *>(s.dout) + i);
+    if (tid == 0) {
+        *s.hmax = __ldcg(s.maxv);
+        *s.arrive = 0u;    // ready for the stream's next block (ordered by the kernel boundary)
+    }
+}
+
 constexpr int GROUP_MAX = 32;
 struct GroupSel {
+    static constexpr bool kSingle = true;   // T == 1, streams may ask for the host copy-out
     const StreamDev *st[GROUP_MAX];
     int fv[GROUP_MAX];
     int pt[GROUP_MAX];
