@@ -205,11 +205,22 @@ def cpu_baseline(wl, filter_dir, target_s=12.0):
     audio, wall = run(cores, 8)                     # calibration (also warms the cores)
     nb = max(8, min(100000, int(8 * target_s / wall)))
     audio, wall = run(cores, nb)
+    cal = fft_calibration()
+    value = audio / wall
+    # What the arm would reach with a pocketfft-class transform: per block and thread (ninp + nout)
+    # transforms of 2 * fragm points; the measured one-core difference is taken out of the block time.
+    calibrated = None
+    if "pocketfft_rfft_us" in cal and cal["n"] == 2 * wl.fragm:
+        t_blk = cores * (wl.fragm / wl.fs) / value
+        t_fft_gain = (wl.ninp + wl.nout) * 1e-6 * max(0.0, cal["oracle_r2c_us"] - cal["pocketfft_rfft_us"])
+        if t_blk > t_fft_gain:
+            calibrated = value * t_blk / (t_blk - t_fft_gain)
     return {
-        "value": audio / wall, "unit": "x realtime (audio-s per wall-s)", "cores": cores, "kind": kind,
+        "value": value, "unit": "x realtime (audio-s per wall-s)", "cores": cores, "kind": kind,
+        "value_with_pocketfft_class_fft": calibrated,
         "sample": f"{cores} files x {nb} blocks of {wl.fragm} frames ({wl.name}), one SoundProcessor/Convproc per "
                   f"file, one file per thread, {wall:.1f} s wall; {what}",
-        "fft_calibration_one_core": fft_calibration(),
+        "fft_calibration_one_core": cal,
     }
 
 
@@ -259,16 +270,6 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(wl_name, streams, T=1):
-    """dram bytes per MAC launch from the committed ncu --set full summary, if one matches."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "mac_traffic.json")))
-        e = d.get(f"{wl_name}:{streams}" if T == 1 else f"{wl_name}:{streams}:T{T}")
-        return float(e["dram_bytes_per_launch"]) if e else None
-    except Exception:
-        return None
-
-
 def emit(line):
     """The ONE JSON line of the contract goes to the real stdout; everything libraries print on
     file descriptor 1 meanwhile (NCCL's version banner at N > 1) was redirected to stderr."""
@@ -277,6 +278,272 @@ def emit(line):
 
 
 _STDOUT = sys.stdout
+
+WIRE = {"f32": (0, 4, np.float32, 1.0), "s16": (1, 2, np.int16, 32768.0), "s24": (2, 4, np.int32, 8388608.0)}
+
+
+def byte_model(flt, wl, B, T, wire_in, wire_out):
+    """HBM bytes of one step of B streams x T blocks, N = fragm, 8N bytes per spectrum row.
+
+    MAC, compulsory (time-tiled): every stream's window of P+T-1 ring slots of each input once, the
+    filter rows once, the T output rows of every output once.
+    MAC, traffic model: what the kernel requests -- one window per (output, input) PAIR with impulse
+    data (equal to the compulsory figure for diagonal filters; ncu cross-check in profiles/).
+    MAC, block-synchronous: every block re-reads its whole partition history.
+    FFT kernels: PCM in / spectra out, spectra in / PCM out + the overlap tails once per step."""
+    N, P, rows, I, O, K = wl.fragm, flt.ring_depth, flt.active_rows, wl.ninp, wl.nout, flt.active_pairs
+    row = 8 * N
+    D = P + T - 1
+    return {
+        "mac_compulsory": row * (B * D * I + rows + B * T * O),
+        "mac_traffic_model": row * (B * D * K + rows + B * T * O),
+        "mac_block_sync": 8 * (N + 1) * (B * T * P * I + rows + B * T * O),
+        "fwd": B * T * I * (N * wire_in + row),
+        "inv": B * T * O * (row + N * wire_out) + B * O * 2 * 4 * N,
+    }
+
+
+class Measure:
+    """One workload on this rank's GPU: device-resident loop, end-to-end loop, copy-only loop."""
+
+    def __init__(self, ctx, wl_name, streams, T, wire):
+        from folve_b200 import capi
+        self.ctx, self.capi = ctx, capi
+        self.wl = workloads.WORKLOADS[wl_name]()
+        self.flt = self.wl.load(capi.Filter(self.wl.ninp, self.wl.nout, self.wl.size, self.wl.fragm)).commit(ctx.local_rank)
+        self.B, self.T, self.wire = streams, T, wire
+        fmt, self.wire_bytes, dt, scale = WIRE[wire]
+        self.batch = capi.Batch(self.flt, streams, fmt, fmt, blocks_per_step=T)
+        peak_in = 0.03 if wl_name == "santalucia" else 0.25
+        x = workloads.synthetic_pcm(streams, T * self.wl.fragm, self.wl.ninp, peak_in, 1000 + ctx.rank)
+        self.x = x
+        self.batch.host_in[:] = x if wire == "f32" else np.rint(x * scale).astype(dt)
+        self.audio_per_step = ctx.world * streams * T * self.wl.fragm / self.wl.fs
+
+    def e2e(self, steps, warm, copy_only=False):
+        """-> (seconds for `steps` steps through fcv_batch_submit / fcv_batch_wait, max over ranks; launches)"""
+        L, bt = self.capi.lib(), self.batch
+        in1, _ = bt.slot_views(1)
+        in1[:] = bt.host_in
+        bt.set_copy_only(copy_only)
+        for _ in range(warm):
+            bt.process()
+        self.ctx.barrier()
+        n0 = L.fcv_kernel_launches()
+        t0 = time.perf_counter()
+        bt.submit(0)
+        for k in range(1, steps):
+            bt.submit(k & 1)
+            bt.wait((k - 1) & 1)      # step k-1 is complete in its host_out slot
+        bt.wait((steps - 1) & 1)
+        self.ctx.sync()
+        sec = self.ctx.max_over_ranks(time.perf_counter() - t0)
+        nl = L.fcv_kernel_launches() - n0
+        bt.set_copy_only(False)
+        self.ctx.barrier()
+        return sec, nl
+
+    def device(self, steps, warm):
+        """-> (ms for `steps` device-resident steps (CUDA events, max over ranks), launches, per-kernel ms per step)"""
+        L, bt = self.capi.lib(), self.batch
+        bt.set_profiling(not os.environ.get("FCV_DEVICE_CHUNKS"))
+        for _ in range(warm):
+            bt.process_device()
+        bt.profile()              # drop warm-up timings
+        self.ctx.barrier()
+        n0 = L.fcv_kernel_launches()
+        bt.event_record(0)
+        for _ in range(steps):
+            bt.process_device()
+        bt.event_record(1)
+        bt.sync()
+        self.ctx.sync()
+        ms = self.ctx.max_over_ranks(bt.event_elapsed_ms(0, 1))
+        launches = L.fcv_kernel_launches() - n0
+        kms, ksteps = bt.profile()
+        bt.set_profiling(False)
+        self.ctx.barrier()
+        k = max(1, ksteps)
+        return ms, launches, {"fwd_fft": kms[0] / k, "mac": kms[1] / k, "inv_fft": kms[2] / k}
+
+    def roofline(self, kernel_ms, step_ms, peak, peak_src):
+        bm = byte_model(self.flt, self.wl, self.B, self.T, self.wire_bytes, self.wire_bytes)
+        mac_s = kernel_ms["mac"] * 1e-3
+        gbs = lambda b, ms: b / (ms * 1e-3) / 1e9 if ms > 0 else float("nan")
+        achieved = bm["mac_compulsory"] / mac_s / 1e9
+        T = self.T
+        step_bytes = bm["fwd"] + bm["mac_compulsory"] + bm["inv"]
+        return {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": bm["mac_traffic_model"],
+            "kernel": "mac_kernel" if T == 1 else (f"mac_tma_kernel<T={T}>" if T >= 4 and not
+                                                    os.environ.get("FCV_MAC_TMA") == "0" else f"mac_tt_kernel<T={T}>"),
+            "algorithmic_bytes_per_launch": bm["mac_compulsory"], "peak_source": peak_src,
+            "what": "frac = compulsory HBM bytes of the time-tiled MAC launch (window of P+T-1 ring slots per stream and "
+                    "input once, filter rows once, T output rows per output once) / its CUDA-event time / peak; "
+                    "traffic = bytes the kernel requests (one window per (output, input) pair; equals the compulsory "
+                    "bytes for diagonal filters; ncu dram__bytes cross-check: profiles/)",
+            "traffic_frac_of_peak": bm["mac_traffic_model"] / mac_s / 1e9 / peak,
+            "block_sync_bytes_per_launch": bm["mac_block_sync"],
+            "block_sync_frac": bm["mac_block_sync"] / mac_s / 1e9 / peak,
+            "per_kernel": {
+                "fwd_fft": {"bytes": bm["fwd"], "gbs": gbs(bm["fwd"], kernel_ms["fwd_fft"]),
+                            "frac": gbs(bm["fwd"], kernel_ms["fwd_fft"]) / peak},
+                "mac": {"bytes": bm["mac_compulsory"], "gbs": achieved, "frac": achieved / peak},
+                "inv_fft": {"bytes": bm["inv"], "gbs": gbs(bm["inv"], kernel_ms["inv_fft"]),
+                            "frac": gbs(bm["inv"], kernel_ms["inv_fft"]) / peak},
+            },
+            "step": {"bytes": step_bytes, "gbs": gbs(step_bytes, step_ms), "frac": gbs(step_bytes, step_ms) / peak,
+                     "what": "all kernels of a step: compulsory bytes / device time per step / peak"},
+        }
+
+    def close(self):
+        self.batch.close()
+        self.flt.close()
+
+
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def config_block(ctx, peak, peak_src, T):
+    """Short device-resident + end-to-end runs of the other BASELINE configs (1, 3, 4) so that every
+    config has numbers from the same run as the headline: (workload, streams per GPU, wire)."""
+    plan = [("lowpass", 1024, "s16"), ("roomcorr96", 1024, "s24"), ("roomcorr192", 1024, "s24"),
+            ("crossfeed", 1024, "s16"), ("surround51", 256, "s24"), ("surround51_dense", 256, "s24")]
+    out = {}
+    for name, streams, wire in plan:
+        m = Measure(ctx, name, streams, T, wire)
+        ms, _, kms = m.device(12, 3)
+        sec, _ = m.e2e(6, 3)
+        sec_c, _ = m.e2e(6, 2, copy_only=True)
+        step_ms = ms / 12
+        rf = m.roofline(kms, step_ms, peak, peak_src)
+        wl, flt = m.wl, m.flt
+        out[name] = {
+            "workload": f"{wl.ninp}x{wl.nout} fs={wl.fs} size={wl.size} fragm={wl.fragm} ring={flt.ring_depth} "
+                        f"rows={flt.active_rows} pairs={flt.active_pairs}",
+            "streams_per_gpu": streams, "blocks_per_step": T, "wire_format": wire,
+            "value": m.audio_per_step * 12 / (ms * 1e-3), "ms_per_step": step_ms, "kernel_ms_per_step": kms,
+            "e2e": {"value": m.audio_per_step * 6 / sec, "ms_per_step": 1e3 * sec / 6,
+                    "link_ceiling": m.audio_per_step * 6 / sec_c,
+                    "h2d_bytes_per_step": streams * T * wl.fragm * wl.ninp * m.wire_bytes,
+                    "d2h_bytes_per_step": streams * T * wl.fragm * wl.nout * m.wire_bytes},
+            "mac_frac_of_hbm": rf["frac"], "mac_traffic_frac_of_hbm": rf["traffic_frac_of_peak"],
+            "step_frac_of_hbm": rf["step"]["frac"],
+            "per_kernel_frac": {k: v["frac"] for k, v in rf["per_kernel"].items()},
+        }
+        m.close()
+    return out
+
+
+def album_library(ctx, wl, filter_dir, T, pcm16, in_process_gpus=0):
+    """BASELINE config 5 as specified: 128 albums x 8 tracks of U[120 s, 360 s], every album ONE gapless
+    chain (convolve-file-handler.cc:390-415), all chains of a shard in flight at once, sharded by
+    album (folve_b200/sharding.py balanced_albums) over the ranks -- or, with in_process_gpus > 1, over
+    that many GPUs from ONE process (MultiDeviceConvolver).  -> dict"""
+    from folve_b200 import sharding
+    L = C.CDLL(HOST_SO)
+    L.fh_bench_albums.restype = C.c_double
+    L.fh_bench_albums.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    cfg = os.path.join(filter_dir, f"filter-{wl.fs}.conf")
+    cores = len(os.sched_getaffinity(0))
+    nalbums, tracks = 128, 8
+    rank, world = (0, 1) if in_process_gpus > 1 else (ctx.rank, ctx.world)
+    threads = max(2, cores // max(1, ctx.world if in_process_gpus <= 1 else in_process_gpus))
+    audio, chains = C.c_double(0), C.c_int(0)
+    ctx.barrier()
+    wall = L.fh_bench_albums(cfg.encode(), wl.fs, wl.ninp, nalbums, tracks, rank, world, in_process_gpus, T, threads,
+                             1 if pcm16 else 0, C.byref(audio), C.byref(chains))
+    if wall <= 0:
+        raise RuntimeError("fh_bench_albums failed")
+    assert chains.value == len(sharding.balanced_albums(nalbums, rank, world))
+    if in_process_gpus > 1:
+        total_audio, max_wall = audio.value, wall
+    else:
+        total_audio, max_wall = ctx.sum_over_ranks(audio.value), ctx.max_over_ranks(wall)
+    return {"value": total_audio / max_wall, "unit": "x realtime (audio-s per wall-s)", "audio_seconds": total_audio,
+            "wall_s": max_wall, "albums": nalbums, "tracks_per_album": tracks, "chains_per_gpu": chains.value
+            if in_process_gpus <= 1 else nalbums // in_process_gpus,
+            "host_threads_per_gpu": threads, "wire_format": "s16" if pcm16 else "f32", "blocks_per_step": T,
+            "sharding": (f"one process, {in_process_gpus} GPUs (MultiDeviceConvolver)" if in_process_gpus > 1 else
+                         f"{world} ranks, albums a = rank (mod {world}) (sharding.balanced_albums)"),
+            "what": "BatchConvolver::Run over SNDFILE in / SNDFILE out: 128 gapless album chains x 8 tracks of "
+                    "U[120 s, 360 s] (seed 100 + album), all chains prebuffered at t = 0, two steps in flight"}
+
+
+def parity_gate(wl, flt):
+    """Correctness gate reported with the numbers: one stream of the benchmark's own
+    filter through the single-stream C ABI against the CPU oracle (the checker) and the float64 truth."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from folve_b200 import capi
+    from oracle_py import OracleConvproc, run_blocks, truth_f64
+    N = wl.fragm
+    x = workloads.synthetic_pcm(1, 5 * N + 321, wl.ninp, 0.03 if wl.name == "santalucia" else 0.25, 4242)[0]
+    s = capi.Stream(flt)
+    y = run_blocks(s, x, N)
+    s.close()
+    yo = run_blocks(wl.load(OracleConvproc(wl.ninp, wl.nout, wl.size, reset_is_fresh=True)), x, N)
+    h = {}
+    for (i, o, d, i0) in wl.adds:
+        t = h.setdefault((i, o), np.zeros(wl.size + 1, np.float64))
+        t[i0:i0 + len(d)] += np.asarray(d, np.float64)[: len(t) - i0]
+    for (i1, o1, i2, o2) in wl.links:
+        h[(i2, o2)] = h[(i1, o1)]
+    t = truth_f64(x, h, wl.nout)
+    fs = max(1.0, float(np.abs(t).max()))
+
+    def lsb_hist(a, b, scale):
+        d = np.abs(np.rint(a.astype(np.float64) * scale) - np.rint(b.astype(np.float64) * scale)).astype(np.int64)
+        return {str(k): int((d == k).sum()) for k in range(0, 4)} | {">=4": int((d >= 4).sum())}
+
+    snr = lambda a: float(10 * np.log10((t ** 2).sum() / max(1e-300, ((a - t) ** 2).sum())))
+    return {
+        "frames": int(x.shape[0]), "max_err_engine_vs_oracle_fs": float(np.abs(y - yo).max() / fs),
+        "max_err_engine_vs_truth_fs": float(np.abs(y - t).max() / fs),
+        "max_err_oracle_vs_truth_fs": float(np.abs(yo - t).max() / fs),
+        "snr_db_engine_vs_truth": snr(y), "snr_db_oracle_vs_truth": snr(yo),
+        "lsb16_engine_vs_oracle": lsb_hist(y, yo, 32767.0), "lsb24_engine_vs_oracle": lsb_hist(y, yo, 8388607.0),
+        "lsb24_engine_vs_truth": lsb_hist(y, t, 8388607.0), "lsb24_oracle_vs_truth": lsb_hist(yo, t, 8388607.0),
+        "what": "one stream, 5 blocks + 321 frames of the benchmark's filter through fcv_stream_process; "
+                "histograms count samples by |difference| in LSBs after 16 / 24-bit quantisation",
+    }
 
 
 def main():
@@ -291,13 +558,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="santalucia", choices=sorted(workloads.WORKLOADS))
     ap.add_argument("--streams", type=int, default=1024, help="concurrent streams PER GPU")
-    ap.add_argument("--wire", default="s16", choices=["f32", "s16"],
+    ap.add_argument("--wire", default="s16", choices=["f32", "s16", "s24"],
                     help="PCM format of the host and device staging buffers (the workload is 16-bit audio; "
                          "the conversions are fused into the FFT kernels)")
     ap.add_argument("--blocks-per-step", type=int, default=8, choices=[1, 2, 4, 8],
                     help="consecutive blocks of every stream per step (>1: time-tiled MAC)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident loop")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--no-library", action="store_true", help="skip the config-5 album library leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -309,129 +578,90 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import torch
-    import torch.distributed as dist
+    # the C++ host layer (SoundProcessor, BatchConvolver) of this rank works on this rank's GPU
+    os.environ.setdefault("FOLVE_B200_DEVICE", str(local_rank))
+    ctx = Ctx()
     from folve_b200 import capi
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    wl = workloads.WORKLOADS[args.workload]()
-    flt = wl.load(capi.Filter(wl.ninp, wl.nout, wl.size, wl.fragm)).commit(local_rank)
-    B, N, K, W, T = args.streams, wl.fragm, args.steps, args.warmup, args.blocks_per_step
-    fmt = capi.PCM_F32 if args.wire == "f32" else capi.PCM_S16
-    batch = capi.Batch(flt, B, fmt, fmt, blocks_per_step=T)
-    x = workloads.synthetic_pcm(B, T * N, wl.ninp, 0.03, 1000 + rank)
-    batch.host_in[:] = x if fmt == capi.PCM_F32 else np.rint(x * 32768.0).astype(np.int16)
     L = capi.lib()
+    K, W, T, B = args.steps, args.warmup, args.blocks_per_step, args.streams
+    peak, peak_src = measured_peak()
+    small = B < 256   # contract test: keep the auxiliary legs out
 
+    m = Measure(ctx, args.workload, B, T, args.wire)
+    wl, flt, N = m.wl, m.flt, m.wl.fragm
     clocks = ClockSampler(local_rank)
+    clocks.start()
 
     # ---- end to end through the C ABI: pinned host in -> pinned host out, every step.
-    # Two host staging slots: block k+1 is submitted before block k is awaited, the
-    # way a prebuffering server keeps the copy engines busy; every step still moves
-    # its own input host->device and its own output device->host.
-    def measure_e2e(bt, steps):
-        """-> (seconds for `steps` steps, max over ranks; kernel launches)"""
-        in1, _ = bt.slot_views(1)
-        in1[:] = bt.host_in
-        for _ in range(1 if args.skip_e2e else W):
-            bt.process()
-        barrier()
-        n_0 = L.fcv_kernel_launches()
-        t_0 = time.perf_counter()
-        if not args.skip_e2e:
-            bt.submit(0)
-            for k in range(1, steps):
-                bt.submit(k & 1)
-                bt.wait((k - 1) & 1)      # block k-1 is complete in its host_out slot
-            bt.wait((steps - 1) & 1)
-        torch.cuda.synchronize()
-        sec = max_over_ranks(time.perf_counter() - t_0)
-        nl = L.fcv_kernel_launches() - n_0
-        barrier()
-        return sec, nl
-
-    clocks.start()
-    e2e_s, launches_e2e = measure_e2e(batch, K)
+    # Two host staging slots: step k+1 is submitted before step k is awaited, the way a prebuffering
+    # server keeps the copy engines busy; every step still moves its own input host->device and its
+    # own output device->host.  link_ceiling: the same loop with the kernels switched off.
+    e2e_s = launches_e2e = ceil_s = None
+    if not args.skip_e2e:
+        e2e_s, launches_e2e = m.e2e(K, W)
+        ceil_s, _ = m.e2e(max(5, K // 2), 2, copy_only=True)
 
     # ---- single-stream block latency through the synchronous drop-in call
     lat = None
     if not args.skip_e2e and rank == 0:
         st = capi.Stream(flt)
-        st.buffer[: N * wl.ninp] = x[0, :N].reshape(-1)
-        m = C.c_float(0)
+        st.buffer[: N * wl.ninp] = m.x[0, :N].reshape(-1)
+        mx = C.c_float(0)
         ts = []
         for k in range(1100):
             t1 = time.perf_counter()
-            L.fcv_stream_process(st._h, N, C.byref(m))
+            L.fcv_stream_process(st._h, N, C.byref(mx))
             ts.append(time.perf_counter() - t1)
         ts = np.array(ts[100:]) * 1e6
         lat = {"median": float(np.median(ts)), "p99": float(np.percentile(ts, 99)), "blocks": int(ts.size),
                "what": "fcv_stream_process, one stream: pinned block read by the forward kernel over the link, "
-                       "3 kernels, D2H -> pinned block"}
+                       "3 kernels, output written to the pinned block by the inverse kernel"}
         st.close()
-    barrier()
+    ctx.barrier()
 
     # ---- device resident: PCM already in HBM (left there by the steps above)
-    batch.set_profiling(not os.environ.get("FCV_DEVICE_CHUNKS"))
-    for _ in range(W):
-        batch.process_device()
-    batch.profile()              # drop warm-up timings
-    barrier()
-    n0 = L.fcv_kernel_launches()
-    batch.event_record(0)
-    for _ in range(K):
-        batch.process_device()
-    batch.event_record(1)
-    batch.sync()
-    torch.cuda.synchronize()
-    dev_ms = max_over_ranks(batch.event_elapsed_ms(0, 1))
-    launches = L.fcv_kernel_launches() - n0
-    kms, ksteps = batch.profile()
+    dev_ms, launches, kms = m.device(K, W)
     clk = clocks.stop()
-    barrier()
 
-    audio_per_step = world * B * T * N / wl.fs
-    value = audio_per_step * K / (dev_ms * 1e-3)
+    value = m.audio_per_step * K / (dev_ms * 1e-3)
     # the same end-to-end loop with float32 on the wire (what SoundProcessor's float buffer
     # would ship unconverted): twice the PCIe bytes
     e2e_f32 = None
-    if not args.skip_e2e and fmt != capi.PCM_F32:
+    if not args.skip_e2e and args.wire != "f32" and not small:
         K2 = max(10, K // 4)
-        b32 = capi.Batch(flt, B, capi.PCM_F32, capi.PCM_F32, blocks_per_step=T)
-        b32.host_in[:] = x
-        sec, _ = measure_e2e(b32, K2)
-        e2e_f32 = {"value": audio_per_step * K2 / sec, "ms_per_step": 1e3 * sec / K2, "steps": K2,
+        m32 = Measure(ctx, args.workload, B, T, "f32")
+        sec, _ = m32.e2e(K2, W)
+        e2e_f32 = {"value": m32.audio_per_step * K2 / sec, "ms_per_step": 1e3 * sec / K2, "steps": K2,
                    "h2d_bytes_per_step": B * T * N * wl.ninp * 4, "d2h_bytes_per_step": B * T * N * wl.nout * 4}
-        b32.close()
-    e2e_value = None if args.skip_e2e else audio_per_step * K / e2e_s
+        m32.close()
+    e2e_value = None if args.skip_e2e else m.audio_per_step * K / e2e_s
+    link_ceiling = None
+    if ceil_s:
+        kc = max(5, K // 2)
+        cv = m.audio_per_step * kc / ceil_s
+        link_ceiling = {"value": cv, "ms_per_step": 1e3 * ceil_s / kc, "steps": kc, "e2e_frac_of_ceiling": e2e_value / cv,
+                        "what": "the same submit/wait loop with the kernels switched off (fcv_batch_set_copy_only): "
+                                "only the host->device and device->host copies of every step"}
 
-    # roofline of the complex-MAC kernel: SURVEY section 8(d) algorithmic bytes
-    P, rows, I, O = flt.ring_depth, flt.active_rows, wl.ninp, wl.nout
-    # block-synchronous streaming model: every one of the B*T stream-blocks of a launch
-    # reads its full partition history (a time-tiled launch moves fewer bytes: see traffic)
-    bytes_mac = 8 * (N + 1) * (B * T * P * I + rows + B * T * O)
-    mac_ms = kms[1] / max(1, ksteps) if ksteps else float("nan")
-    peak, peak_src = measured_peak()
-    achieved = bytes_mac / (mac_ms * 1e-3) / 1e9
-    traffic = ncu_traffic(wl.name, B, T)
+    rf = m.roofline(kms, dev_ms / K, peak, peak_src)
+    P, rows = flt.ring_depth, flt.active_rows
+    configs = None
+    if world == 1 and not args.no_configs and not args.skip_e2e and not small:
+        configs = config_block(ctx, peak, peak_src, T)
+
+    library = library_1p = None
+    if not args.no_library and not args.skip_e2e and not small and os.path.exists(HOST_SO):
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            filter_dir = workloads.write_filter_dir(wl, os.path.join(tmp, wl.name))
+            library = album_library(ctx, wl, filter_dir, T, args.wire == "s16")
+            ngpu_box = L.fcv_device_count()
+            if world == 1 and ngpu_box > 1:
+                # every GPU of the box from this ONE process, the way folve (a single process) would
+                library_1p = album_library(ctx, wl, filter_dir, T, args.wire == "s16", in_process_gpus=ngpu_box)
 
     if rank == 0:
-        wire_bytes = 4 if fmt == capi.PCM_F32 else 2
+        wb = m.wire_bytes
         line = {
             "metric": "convolved audio-seconds per second", "value": value,
             "unit": "x realtime (audio-s per wall-s)", "n_gpus": world, "steps": K, "warmup": W,
@@ -441,39 +671,38 @@ def main():
                 "workload": f"{wl.name}: {wl.ninp}x{wl.nout} fs={wl.fs} size={wl.size} fragm={N} "
                             f"partitions={flt.partitions} (non-zero ring depth {P}, {rows} filter rows)",
                 "streams_per_gpu": B, "blocks_per_step": T, "frames_per_block": N,
-                "audio_seconds_per_step": audio_per_step, "wire_format": args.wire,
-                "l2": f"per-step working set {(bytes_mac + 0) / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2)",
+                "audio_seconds_per_step": m.audio_per_step, "wire_format": args.wire,
+                "l2": f"per-step working set {rf['step']['bytes'] / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2)",
                 "parallelism": f"{world} x independent stream shards, no collective",
             },
             "e2e": {"value": e2e_value, "unit": "x realtime (audio-s per wall-s)",
-                    "h2d_bytes_per_step": B * T * N * I * wire_bytes, "d2h_bytes_per_step": B * T * N * O * wire_bytes,
-                    "ms_per_step": 1e3 * e2e_s / K, "wire_format": args.wire, "f32_wire": e2e_f32},
-            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
-            "kernel_ms_per_step": {"fwd_fft": kms[0] / max(1, ksteps), "mac": mac_ms,
-                                   "inv_fft": kms[2] / max(1, ksteps)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "mac_kernel" if T == 1 else (f"mac_tma_kernel<T={T}>" if T >= 4 and not
-                                                                os.environ.get("FCV_MAC_TMA") == "0" else f"mac_tt_kernel<T={T}>"),
-                         "algorithmic_bytes_per_launch": bytes_mac, "peak_source": peak_src,
-                         # what the kernel really moved (ncu dram bytes) over the same measured time:
-                         # for a time-tiled launch this, not `frac`, is the fraction of the HBM peak in use
-                         "traffic_gbs": (traffic / (mac_ms * 1e-3) / 1e9) if traffic else None,
-                         "traffic_frac_of_peak": (traffic / (mac_ms * 1e-3) / 1e9 / peak) if traffic else None},
+                    "h2d_bytes_per_step": B * T * N * wl.ninp * wb, "d2h_bytes_per_step": B * T * N * wl.nout * wb,
+                    "ms_per_step": None if args.skip_e2e else 1e3 * e2e_s / K, "wire_format": args.wire,
+                    "link_ceiling": link_ceiling, "f32_wire": e2e_f32},
+            "gpu_launches": int(launches), "gpu_launches_e2e": None if launches_e2e is None else int(launches_e2e),
+            "kernel_ms_per_step": kms,
+            "roofline": rf,
             "clocks": clk,
             "block_latency_us": lat,
         }
+        if configs is not None:
+            line["configs"] = configs
+        if library is not None:
+            line["e2e"]["album_library"] = library
+        if library_1p is not None:
+            line["e2e"]["album_library_one_process"] = library_1p
         if world == 1 and not args.no_cpu_baseline:
             import tempfile
             with tempfile.TemporaryDirectory() as tmp:
                 filter_dir = workloads.write_filter_dir(wl, os.path.join(tmp, wl.name))
                 line["cpu_baseline"] = cpu_baseline(wl, filter_dir)
+                line["cpu_baseline"]["parity"] = parity_gate(wl, flt)
                 if os.path.exists(HOST_SO) and not args.skip_e2e:
                     # the drop-in API itself: one synchronous SoundProcessor per host thread on the GPU
                     cores = len(os.sched_getaffinity(0))
                     harness_run(HOST_SO, wl, filter_dir, cores, 20)
                     a, w = harness_run(HOST_SO, wl, filter_dir, cores, 400)
-                    a2, w2 = library_run(wl, filter_dir, B, 2, 120.0, T, cores, fmt == capi.PCM_S16)
+                    a2, w2 = library_run(wl, filter_dir, B, 2, 120.0, T, cores, args.wire == "s16")
                     a3, w3 = library_run(wl, filter_dir, B, 2, 120.0, T, cores, False)
                     line["e2e"]["batch_convolver"] = {
                         "value": a2 / w2, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
@@ -483,14 +712,12 @@ def main():
                                 f"steps in flight"}
                     line["e2e"]["soundprocessor_sync"] = {
                         "value": a / w, "unit": "x realtime (audio-s per wall-s)", "threads": cores,
-                        "what": "SoundProcessor::FillBuffer/WriteProcessed block loop, one file per host thread, "
-                                "one synchronous fcv_stream_process per block"}
+                        "what": "SoundProcessor::FillBuffer/WriteProcessed block loop, one file per host thread; the "
+                                "library coalesces the concurrent synchronous calls into shared launch groups"}
         emit(line)
 
-    batch.close()
-    flt.close()
-    if world > 1:
-        dist.destroy_process_group()
+    m.close()
+    ctx.close()
 
 
 if __name__ == "__main__":

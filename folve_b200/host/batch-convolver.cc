@@ -15,6 +15,7 @@
 
 #include "../../include/folve_b200.h"
 #include "filter-config.h"
+#include "sound-processor.h"
 
 namespace folve_b200 {
 
@@ -173,8 +174,8 @@ void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, void *in_block) {
     }
     if (s.k >= c.size()) return;
     ChainFile &a = c[s.k];
-    int r = (int)(s.left < fragm_ ? s.left : fragm_);
-    r = (int)ReadFrames(a.in, in_block, 0, r);
+    const int want = (int)(s.left < fragm_ ? s.left : fragm_);
+    const int r = (int)ReadFrames(a.in, in_block, 0, want);
     if (r == 0) {  // premature EOF: the file is over, nothing is written for it
         s.left = 0;
         s.reset_before_next = true;
@@ -184,6 +185,17 @@ void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, void *in_block) {
     p.fill = r;
     p.share[p.nshare].file = s.k;
     p.share[p.nshare++].frames = r;
+    if (r < want) {
+        // A short read in the middle of a file (truncated / corrupt input): the file ends here.
+        // It gets the frames that were read, hands nothing over, and whoever comes next starts
+        // from a reset processor -- zero padding is never spliced into a running convolution.
+        s.left = 0;
+        p.finished[p.nfinished++] = s.k;
+        s.k++;
+        s.left = s.k < c.size() ? c[s.k].frames : 0;
+        s.reset_before_next = true;
+        return;
+    }
     if (s.left > 0) return;  // a full block from the middle of the file
     // file k ends with this block
     p.finished[p.nfinished++] = s.k;
@@ -196,13 +208,13 @@ void BatchConvolver::FillBlock(Slot &s, BlockPlan &p, void *in_block) {
     }
     // hand the half-filled block over to the alphabetically next file
     ChainFile &b = c[s.k + 1];
-    int r2 = (int)((long)(fragm_ - p.fill) < b.frames ? (fragm_ - p.fill) : b.frames);
-    r2 = (int)ReadFrames(b.in, in_block, p.fill, r2);
+    const int want2 = (int)((long)(fragm_ - p.fill) < b.frames ? (fragm_ - p.fill) : b.frames);
+    const int r2 = (int)ReadFrames(b.in, in_block, p.fill, want2);
     a.out_gapless = true;
     b.in_gapless = true;
     p.fill += r2;
     s.k++;
-    s.left = b.frames - r2;
+    s.left = r2 < want2 ? 0 : b.frames - r2;   // a successor that is shorter than it claims ends with the top-up
     if (s.left == 0) {
         // the successor was swallowed by the top-up (quirk 4): it writes nothing,
         // and whoever comes next starts fresh
@@ -375,6 +387,68 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
         fprintf(stderr, "BatchConvolver::Run: %ld steps; host seconds: wait %.3f drain %.3f assign+reset %.3f fill %.3f submit %.3f\n",
                 steps_, t_wait, t_drain, t_assign, t_fill, t_submit);
     return ok;
+}
+
+// ---- every GPU of the box from one process ---------------------------------------------
+MultiDeviceConvolver *MultiDeviceConvolver::Create(const std::string &config_file, int samplerate, int channels,
+                                                   int slots_per_device, bool gapless,
+                                                   const std::vector<int> &devices, int blocks_per_step,
+                                                   bool pcm16) {
+    std::vector<int> ids = devices;
+    if (ids.empty()) {
+        const int n = fcv_device_count();
+        for (int d = 0; d < n; d++) ids.push_back(d);
+    }
+    if (ids.empty()) return nullptr;
+    MultiDeviceConvolver *m = new MultiDeviceConvolver();
+    for (int d : ids) {
+        BatchConvolver *bc = BatchConvolver::Create(config_file, samplerate, channels, slots_per_device, gapless, d,
+                                                    blocks_per_step, pcm16);
+        if (!bc) {
+            delete m;
+            return nullptr;
+        }
+        m->parts_.push_back(bc);
+        m->device_ids_.push_back(d);
+    }
+    return m;
+}
+
+MultiDeviceConvolver::~MultiDeviceConvolver() {
+    for (BatchConvolver *bc : parts_) delete bc;
+}
+
+int MultiDeviceConvolver::fragment_size() const { return parts_.empty() ? 0 : parts_[0]->fragment_size(); }
+int MultiDeviceConvolver::output_channels() const { return parts_.empty() ? 0 : parts_[0]->output_channels(); }
+
+int MultiDeviceConvolver::PlacementOf(const std::string &key) const {
+    return SoundProcessor::DeviceForKey(key, (int)parts_.size());
+}
+
+long MultiDeviceConvolver::blocks_processed() const {
+    long n = 0;
+    for (const BatchConvolver *bc : parts_) n += bc->blocks_processed();
+    return n;
+}
+
+bool MultiDeviceConvolver::Run(const std::vector<Chain *> &chains, const std::vector<std::string> &keys,
+                               int threads_per_device, std::vector<int> *assignment) {
+    const size_t nd = parts_.size();
+    std::vector<std::vector<Chain *> > shard(nd);
+    if (assignment) assignment->assign(chains.size(), 0);
+    for (size_t i = 0; i < chains.size(); i++) {
+        const size_t d = keys.empty() ? i % nd : (size_t)PlacementOf(keys[i]);
+        shard[d].push_back(chains[i]);
+        if (assignment) (*assignment)[i] = (int)d;
+    }
+    std::vector<char> ok(nd, 1);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; d++)
+        th.emplace_back([&, d] { ok[d] = parts_[d]->Run(shard[d], threads_per_device) ? 1 : 0; });
+    for (auto &t : th) t.join();
+    bool all = true;
+    for (char o : ok) all = all && o;
+    return all;
 }
 
 }  // namespace folve_b200

@@ -90,6 +90,39 @@ private:
     long blocks_ = 0, steps_ = 0;
 };
 
+// One process, every GPU of the box (folve is a single process): one
+// BatchConvolver per device, chains placed by their album key -- SoundProcessor::DeviceForKey, the
+// function folve_b200/sharding.py computes for the multi-process benchmark -- or round robin when
+// no keys are given, every device driven by its own host thread and its own pool of file
+// threads.  No data ever crosses GPUs: a chain lives and dies on one device, the filter spectra
+// are replicated (a few MB).  Results are those of a single BatchConvolver, chain for chain.
+class MultiDeviceConvolver {
+public:
+    // devices: CUDA device indices to use (empty: all usable ones).  NULL on failure.
+    static MultiDeviceConvolver *Create(const std::string &config_file, int samplerate, int channels,
+                                        int slots_per_device, bool gapless, const std::vector<int> &devices,
+                                        int blocks_per_step = 1, bool pcm16 = false);
+    ~MultiDeviceConvolver();
+
+    int devices() const { return (int)parts_.size(); }
+    int fragment_size() const;
+    int output_channels() const;
+    // Position (0 .. devices()-1) of the device a chain with this key is placed on.
+    int PlacementOf(const std::string &key) const;
+
+    // keys: one placement key per chain (the album directory), or empty for round robin.
+    // assignment (optional): receives, per chain, the position of the device it ran on.
+    bool Run(const std::vector<Chain *> &chains, const std::vector<std::string> &keys, int threads_per_device,
+             std::vector<int> *assignment = nullptr);
+
+    long blocks_processed() const;
+
+private:
+    MultiDeviceConvolver() {}
+    std::vector<BatchConvolver *> parts_;
+    std::vector<int> device_ids_;
+};
+
 }  // namespace folve_b200
 
 #endif

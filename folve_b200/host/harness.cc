@@ -239,14 +239,36 @@ int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits,
 // `slots` chains in flight.  PCM in/out is float, [frames][channels].
 // Returns the number of output channels, <0 on failure.
 // pcm16 != 0: PCM in/out is int16 (16-bit files, int16 on the wire) instead of float.
+// Test hooks consumed by the next RunLibrary call: the length every file CLAIMS to have (a file
+// that is shorter than its header says: truncated input), and the number of GPUs to spread the
+// chains over from this one process (0 = the single BatchConvolver on the default device).
+static std::vector<long> g_claimed_frames;
+static int g_library_devices = 0;
+static std::vector<int> g_last_assignment;
+
 static int RunLibrary(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
                       int nfiles, const int *chain_of_file, const void *const *pcm, const long *frames,
                       void *const *out_pcm, long *out_frames, float *max_values, int *gapless_flags,
                       long *steps_out, int blocks_per_step, int pcm16) {
-    folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, slots, gapless != 0, (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()), blocks_per_step, pcm16 != 0);
-    if (!bc) return -1;
-    const int nout = bc->output_channels();
+    const std::vector<long> claimed = g_claimed_frames;
+    g_claimed_frames.clear();
+    const int ndev = g_library_devices;
+    g_library_devices = 0;
+    folve_b200::BatchConvolver *bc = nullptr;
+    folve_b200::MultiDeviceConvolver *md = nullptr;
+    if (ndev > 0) {
+        std::vector<int> ids;
+        for (int d = 0; d < ndev; d++) ids.push_back(d);
+        md = folve_b200::MultiDeviceConvolver::Create(config_file, samplerate, channels, slots, gapless != 0, ids,
+                                                      blocks_per_step, pcm16 != 0);
+        if (!md) return -1;
+    } else {
+        bc = folve_b200::BatchConvolver::Create(config_file, samplerate, channels, slots, gapless != 0,
+                                                (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()),
+                                                blocks_per_step, pcm16 != 0);
+        if (!bc) return -1;
+    }
+    const int nout = bc ? bc->output_channels() : md->output_channels();
     std::vector<folve_b200::Chain> chains;
     for (int i = 0; i < nfiles; i++) {
         if (chains.empty() || (i > 0 && chain_of_file[i] != chain_of_file[i - 1])) chains.emplace_back();
@@ -254,12 +276,20 @@ static int RunLibrary(const char *config_file, int samplerate, int channels, int
         const int fmt = pcm16 ? SF_FORMAT_PCM_16 : SF_FORMAT_FLOAT;
         f.in = sf_shim_open_memory_read(pcm[i], frames[i], channels, samplerate, fmt);
         f.out = sf_shim_open_memory_write(nout, samplerate, fmt);
-        f.frames = frames[i];
+        f.frames = (size_t)i < claimed.size() ? claimed[(size_t)i] : frames[i];
         chains.back().push_back(f);
     }
     std::vector<folve_b200::Chain *> ptrs;
     for (auto &c : chains) ptrs.push_back(&c);
-    const bool ok = bc->Run(ptrs, threads);
+    bool ok;
+    if (md) {
+        // placement key of chain c: "album<c>" -- the directory name a folve mount would see
+        std::vector<std::string> keys;
+        for (size_t c = 0; c < chains.size(); c++) keys.push_back("album" + std::to_string(c));
+        ok = md->Run(ptrs, keys, threads, &g_last_assignment);
+    } else {
+        ok = bc->Run(ptrs, threads);
+    }
     int i = 0;
     for (auto &c : chains)
         for (auto &f : c) {
@@ -272,9 +302,33 @@ static int RunLibrary(const char *config_file, int samplerate, int channels, int
             sf_close(f.out);
             i++;
         }
-    if (steps_out) *steps_out = bc->steps();
+    if (steps_out) *steps_out = bc ? bc->steps() : 0;
     delete bc;
+    delete md;
     return ok ? nout : -2;
+}
+
+void fh_set_claimed_frames(const long *claimed, int n) { g_claimed_frames.assign(claimed, claimed + n); }
+void fh_set_library_devices(int ndevices) { g_library_devices = ndevices; }
+// device position every chain of the last multi-device run was placed on; returns the chain count
+int fh_last_assignment(int *out, int capacity) {
+    for (int i = 0; i < capacity && (size_t)i < g_last_assignment.size(); i++) out[i] = g_last_assignment[(size_t)i];
+    return (int)g_last_assignment.size();
+}
+int fh_device_for_key(const char *key, int ndevices) { return SoundProcessor::DeviceForKey(key, ndevices); }
+// Creates `n` processors for one config through SoundProcessor::Create (device chosen by load)
+// and reports where they live; all are deleted again.  Returns n, <0 on failure.
+int fh_processor_devices(const char *config_file, int samplerate, int channels, int *devices, int n) {
+    std::vector<SoundProcessor *> ps;
+    int rc = n;
+    for (int i = 0; i < n; i++) {
+        SoundProcessor *p = SoundProcessor::Create(config_file, samplerate, channels);
+        if (!p) { rc = -1; break; }
+        devices[i] = p->device();
+        ps.push_back(p);
+    }
+    for (SoundProcessor *p : ps) delete p;
+    return rc;
 }
 
 int fh_run_library_tiled(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
@@ -353,6 +407,83 @@ double fh_bench_library(const char *config_file, int samplerate, int channels, i
         }
     delete bc;
     if (audio_seconds) *audio_seconds = frames_total / (double)samplerate;
+    return ok ? wall : -2.0;
+}
+
+// ---- BASELINE config 5: a library of gapless albums, prebuffered all at once ------------
+// `nalbums` albums of `tracks` tracks; track lengths uniform in [120 s, 360 s) from an LCG seeded
+// with 100 + album (never a multiple of the block size); every album is ONE gapless chain through
+// one processor (convolve-file-handler.cc:390-415).  This process takes the albums
+// a = rank, rank + world, ... (folve_b200/sharding.py balanced_albums) and, when ndevices > 1,
+// spreads them over that many GPUs itself (MultiDeviceConvolver).  All chains of the shard are
+// in flight at once ("library prebuffer"); PCM comes from one shared white-noise buffer, output is
+// discarded.  Returns the wall seconds of Run, <0 on error; *audio_seconds = what was convolved.
+double fh_bench_albums(const char *config_file, int samplerate, int channels, int nalbums, int tracks, int rank,
+                       int world, int ndevices, int blocks_per_step, int threads, int pcm16, double *audio_seconds,
+                       int *chains_out) {
+    std::vector<int> mine;
+    for (int a = rank; a < nalbums; a += world) mine.push_back(a);
+    if (mine.empty()) return -1.0;
+    const int nd = ndevices > 1 ? ndevices : 1;
+    const int slots = ((int)mine.size() + nd - 1) / nd + (nd > 1 ? 2 : 0);   // room for an uneven placement
+    folve_b200::BatchConvolver *bc = nullptr;
+    folve_b200::MultiDeviceConvolver *md = nullptr;
+    if (nd > 1) {
+        std::vector<int> ids;
+        for (int d = 0; d < nd; d++) ids.push_back(d);
+        md = folve_b200::MultiDeviceConvolver::Create(config_file, samplerate, channels, slots, true, ids,
+                                                      blocks_per_step, pcm16 != 0);
+    } else {
+        bc = folve_b200::BatchConvolver::Create(config_file, samplerate, channels, slots, true,
+                                                (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()),
+                                                blocks_per_step, pcm16 != 0);
+    }
+    if (!bc && !md) return -1.0;
+    const int nout = bc ? bc->output_channels() : md->output_channels();
+    const int fragm = bc ? bc->fragment_size() : md->fragment_size();
+    const long longest = 360L * samplerate + 2;
+    std::vector<float> pcm(pcm16 ? 0 : (size_t)longest * (size_t)channels);
+    std::vector<short> pcm_s16(pcm16 ? (size_t)longest * (size_t)channels : 0);
+    uint32_t s = 12345u;
+    for (size_t i = 0; i < (size_t)longest * (size_t)channels; i++) {
+        s = s * 1664525u + 1013904223u;
+        const float v = 0.03f * ((float)(s >> 8) * (1.0f / 8388608.0f) - 1.0f);
+        if (pcm16) pcm_s16[i] = (short)lrintf(v * 32768.0f);
+        else pcm[i] = v;
+    }
+    const int fmt = pcm16 ? SF_FORMAT_PCM_16 : SF_FORMAT_FLOAT;
+    const void *src = pcm16 ? (const void *)pcm_s16.data() : (const void *)pcm.data();
+    std::vector<folve_b200::Chain> chains(mine.size());
+    std::vector<std::string> keys;
+    double frames_total = 0.0;
+    for (size_t c = 0; c < mine.size(); c++) {
+        uint32_t r = 100u + (uint32_t)mine[c];
+        for (int k = 0; k < tracks; k++) {
+            r = r * 1664525u + 1013904223u;
+            folve_b200::ChainFile f;
+            f.frames = (long)(120.0 * samplerate + (double)(r >> 8) * (1.0 / 16777216.0) * 240.0 * samplerate);
+            if (f.frames % fragm == 0) f.frames++;
+            f.in = sf_shim_open_memory_read(src, f.frames, channels, samplerate, fmt);
+            f.out = sf_shim_open_null_write(nout, samplerate, fmt);
+            frames_total += (double)f.frames;
+            chains[c].push_back(f);
+        }
+        keys.push_back("album" + std::to_string(mine[c]));
+    }
+    std::vector<folve_b200::Chain *> ptrs;
+    for (auto &c : chains) ptrs.push_back(&c);
+    const double t0 = NowSeconds();
+    const bool ok = md ? md->Run(ptrs, std::vector<std::string>(), threads) : bc->Run(ptrs, threads);
+    const double wall = NowSeconds() - t0;
+    for (auto &c : chains)
+        for (auto &f : c) {
+            sf_close(f.in);
+            sf_close(f.out);
+        }
+    delete bc;
+    delete md;
+    if (audio_seconds) *audio_seconds = frames_total / (double)samplerate;
+    if (chains_out) *chains_out = (int)mine.size();
     return ok ? wall : -2.0;
 }
 

@@ -8,8 +8,19 @@
  *   sf_writef_float  /root/reference/sound-processor.cc:91
  *   sf_open/sf_close/sf_seek/sf_command + SF_INFO and the format constants
  *                    /root/reference/zita-audiofile.cc:51-99,162-175
+ *   sf_open_fd / sf_open_virtual / sf_get_string / sf_set_string
+ *                    /root/reference/convolve-file-handler.cc:62,490-492,
+ *                    /root/reference/conversion-buffer.cc:88-98 -- so that the reference's
+ *                    own file handler and conversion buffer compile and run unmodified
+ *                    on top of this shim (oracle/Makefile target `dropin`)
  * plus memory-backed files (sf_shim_*) that stand in for the FLAC decoder /
  * encoder around SoundProcessor in tests and benchmarks.
+ *
+ * Writing through sf_open_virtual produces, for SF_FORMAT_FLAC, an UNCOMPRESSED stand-in
+ * with FLAC's header geometry: "fLaC", one STREAMINFO block (42 bytes in all, so that the
+ * byte offsets folve patches -- convolve-file-handler.cc:289-310 -- mean what they mean in a
+ * real FLAC file), then the interleaved little-endian PCM frames.  The codec itself is out of
+ * scope.  SF_FORMAT_WAV gives a plain 44-byte RIFF header.
  *
  * Supported containers: RIFF/WAVE (PCM 16/24/32 and IEEE float32, also
  * WAVE_FORMAT_EXTENSIBLE) for reading; memory sinks for writing.  Sample
@@ -67,6 +78,27 @@ enum {
 enum { SFM_READ = 0x10, SFM_WRITE = 0x20, SFM_RDWR = 0x30 };
 
 enum {
+    SF_STR_TITLE = 0x01, SF_STR_COPYRIGHT = 0x02, SF_STR_SOFTWARE = 0x03, SF_STR_ARTIST = 0x04,
+    SF_STR_COMMENT = 0x05, SF_STR_DATE = 0x06, SF_STR_ALBUM = 0x07, SF_STR_LICENSE = 0x08,
+    SF_STR_TRACKNUMBER = 0x09, SF_STR_GENRE = 0x10
+};
+#define SF_STR_FIRST SF_STR_TITLE
+#define SF_STR_LAST SF_STR_GENRE
+
+typedef sf_count_t (*sf_vio_get_filelen)(void *user_data);
+typedef sf_count_t (*sf_vio_seek)(sf_count_t offset, int whence, void *user_data);
+typedef sf_count_t (*sf_vio_read)(void *ptr, sf_count_t count, void *user_data);
+typedef sf_count_t (*sf_vio_write)(const void *ptr, sf_count_t count, void *user_data);
+typedef sf_count_t (*sf_vio_tell)(void *user_data);
+typedef struct SF_VIRTUAL_IO {
+    sf_vio_get_filelen get_filelen;
+    sf_vio_seek seek;
+    sf_vio_read read;
+    sf_vio_write write;
+    sf_vio_tell tell;
+} SF_VIRTUAL_IO;
+
+enum {
     SFC_SET_CLIPPING = 0x10C0,
     SFC_GET_CLIPPING = 0x10C1,
     SFC_UPDATE_HEADER_NOW = 0x1060,
@@ -77,6 +109,13 @@ enum { SF_AMBISONIC_NONE = 0x40, SF_AMBISONIC_B_FORMAT = 0x41 };
 enum { SF_FALSE = 0, SF_TRUE = 1 };
 
 SNDFILE *sf_open(const char *path, int mode, SF_INFO *sfinfo);
+/* SFM_READ of a RIFF/WAVE file through a descriptor (dup'ed; close_desc closes the original). */
+SNDFILE *sf_open_fd(int fd, int mode, SF_INFO *sfinfo, int close_desc);
+/* SFM_WRITE only: header and PCM go out through sfvirtual->write. */
+SNDFILE *sf_open_virtual(SF_VIRTUAL_IO *sfvirtual, int mode, SF_INFO *sfinfo, void *user_data);
+/* string tags: none are stored */
+const char *sf_get_string(SNDFILE *sndfile, int str_type);
+int sf_set_string(SNDFILE *sndfile, int str_type, const char *str);
 int sf_close(SNDFILE *sndfile);
 sf_count_t sf_seek(SNDFILE *sndfile, sf_count_t frames, int whence);
 sf_count_t sf_readf_float(SNDFILE *sndfile, float *ptr, sf_count_t frames);

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -31,10 +32,17 @@ struct SNDFILE_tag {
     std::vector<int32_t> w32;
     std::vector<float> wf;
     std::vector<unsigned char> scratch;
+    // virtual write (sf_open_virtual)
+    bool virt = false;
+    SF_VIRTUAL_IO vio{};
+    void *vuser = nullptr;
+    bool header_written = false;
 };
 
 static uint32_t rd32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 static uint16_t rd16(const unsigned char *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+static SNDFILE *open_wav_fp(FILE *fp, SF_INFO *sfinfo);
 
 static SNDFILE *open_wav(const char *path, SF_INFO *sfinfo) {
     FILE *fp = fopen(path, "rb");
@@ -42,6 +50,10 @@ static SNDFILE *open_wav(const char *path, SF_INFO *sfinfo) {
         g_error = std::string("System error : could not open '") + path + "'.";
         return nullptr;
     }
+    return open_wav_fp(fp, sfinfo);
+}
+
+static SNDFILE *open_wav_fp(FILE *fp, SF_INFO *sfinfo) {
     unsigned char hdr[12];
     if (fread(hdr, 1, 12, fp) != 12 || memcmp(hdr, "RIFF", 4) || memcmp(hdr + 8, "WAVE", 4)) {
         fclose(fp);
@@ -115,6 +127,84 @@ extern "C" SNDFILE *sf_open(const char *path, int mode, SF_INFO *sfinfo) {
     return nullptr;
 }
 
+extern "C" SNDFILE *sf_open_fd(int fd, int mode, SF_INFO *sfinfo, int close_desc) {
+    if (fd < 0 || !sfinfo || mode != SFM_READ) { g_error = "Bad argument."; return nullptr; }
+    const int own = dup(fd);
+    if (close_desc) close(fd);
+    FILE *fp = own >= 0 ? fdopen(own, "rb") : nullptr;
+    if (!fp) {
+        if (own >= 0) close(own);
+        g_error = "System error : could not use the descriptor.";
+        return nullptr;
+    }
+    fseek(fp, 0, SEEK_SET);
+    return open_wav_fp(fp, sfinfo);
+}
+
+// ---- virtual write: header once, then interleaved little-endian PCM -------------------------
+static int sub_bits(int sub) {
+    return sub == SF_FORMAT_PCM_16 ? 16 : sub == SF_FORMAT_PCM_24 ? 24 : 32;
+}
+
+static void virt_header(SNDFILE *s) {
+    if (!s->virt || s->header_written) return;
+    s->header_written = true;
+    const int ch = s->info.channels, rate = s->info.samplerate, bits = sub_bits(s->subformat);
+    unsigned char h[44];
+    memset(h, 0, sizeof(h));
+    if ((s->info.format & SF_FORMAT_TYPEMASK) == SF_FORMAT_FLAC) {
+        // "fLaC" | block header: last, STREAMINFO, 34 bytes | min/max blocksize 4096 | frame
+        // sizes 0 | rate:20 channels-1:3 bps-1:5 samples:36 | md5 = 0
+        memcpy(h, "fLaC", 4);
+        h[4] = 0x80; h[7] = 34;
+        h[8] = 0x10; h[10] = 0x10;
+        h[18] = (unsigned char)(rate >> 12);
+        h[19] = (unsigned char)(rate >> 4);
+        h[20] = (unsigned char)(((rate & 0x0f) << 4) | ((ch - 1) << 1) | (((bits - 1) & 0x10) >> 4));
+        h[21] = (unsigned char)(((bits - 1) & 0x0f) << 4);
+        s->vio.write(h, 42, s->vuser);
+        return;
+    }
+    const int block = ch * bits / 8;
+    memcpy(h, "RIFF", 4);
+    memcpy(h + 8, "WAVEfmt ", 8);
+    h[16] = 16;
+    h[20] = (unsigned char)(s->subformat == SF_FORMAT_FLOAT ? 3 : 1);
+    h[22] = (unsigned char)ch;
+    for (int i = 0; i < 4; i++) h[24 + i] = (unsigned char)((unsigned)rate >> (8 * i));
+    for (int i = 0; i < 4; i++) h[28 + i] = (unsigned char)((unsigned)(rate * block) >> (8 * i));
+    h[32] = (unsigned char)block;
+    h[34] = (unsigned char)bits;
+    memcpy(h + 36, "data", 4);
+    s->vio.write(h, 44, s->vuser);
+}
+
+extern "C" SNDFILE *sf_open_virtual(SF_VIRTUAL_IO *v, int mode, SF_INFO *sfinfo, void *user_data) {
+    if (!v || !v->write || !sfinfo || mode != SFM_WRITE) {
+        g_error = "sndfile shim: sf_open_virtual supports SFM_WRITE only.";
+        return nullptr;
+    }
+    const int type = sfinfo->format & SF_FORMAT_TYPEMASK, sub = sfinfo->format & SF_FORMAT_SUBMASK;
+    const bool sub_ok = sub == SF_FORMAT_PCM_16 || sub == SF_FORMAT_PCM_24 || sub == SF_FORMAT_PCM_32 ||
+                        (sub == SF_FORMAT_FLOAT && type == SF_FORMAT_WAV);
+    if ((type != SF_FORMAT_FLAC && type != SF_FORMAT_WAV) || !sub_ok || sfinfo->channels < 1) {
+        g_error = "Format not recognised.";
+        return nullptr;
+    }
+    SNDFILE *s = new SNDFILE_tag();
+    s->mode = SFM_WRITE;
+    s->info = *sfinfo;
+    s->info.frames = 0;
+    s->subformat = sub;
+    s->virt = true;
+    s->vio = *v;
+    s->vuser = user_data;
+    return s;
+}
+
+extern "C" const char *sf_get_string(SNDFILE *, int) { return nullptr; }
+extern "C" int sf_set_string(SNDFILE *, int, const char *) { return 0; }
+
 extern "C" SNDFILE *sf_shim_open_memory_read(const void *pcm, sf_count_t frames, int channels,
                                              int samplerate, int format) {
     const int sub = format & SF_FORMAT_SUBMASK;
@@ -160,6 +250,7 @@ extern "C" SNDFILE *sf_shim_open_null_write(int channels, int samplerate, int fo
 }
 
 extern "C" int sf_close(SNDFILE *s) {
+    if (s && s->virt) virt_header(s);
     if (!s) return 1;
     if (s->fp) fclose(s->fp);
     delete s;
@@ -249,6 +340,24 @@ static inline long quant(float x, float scale, long lo, long hi, bool clip) {
 extern "C" sf_count_t sf_writef_float(SNDFILE *s, const float *ptr, sf_count_t frames) {
     if (!s || s->mode != SFM_WRITE || frames <= 0) return 0;
     const size_t n = (size_t)frames * (size_t)s->info.channels;
+    if (s->virt) {
+        virt_header(s);
+        const int bytes = sub_bits(s->subformat) / 8;
+        s->scratch.resize(n * (size_t)bytes);
+        unsigned char *o = s->scratch.data();
+        for (size_t i = 0; i < n; i++, o += bytes) {
+            if (s->subformat == SF_FORMAT_FLOAT) { memcpy(o, ptr + i, 4); continue; }
+            long q;
+            if (bytes == 2) q = quant(ptr[i], 32767.0f, -32768, 32767, s->clipping);
+            else if (bytes == 3) q = quant(ptr[i], 8388607.0f, -8388608, 8388607, s->clipping);
+            else q = quant(ptr[i], 2147483647.0f, INT32_MIN, INT32_MAX, s->clipping);
+            for (int b = 0; b < bytes; b++) o[b] = (unsigned char)((unsigned long)q >> (8 * b));
+        }
+        s->vio.write(s->scratch.data(), (sf_count_t)s->scratch.size(), s->vuser);
+        s->pos += frames;
+        s->info.frames = s->pos;
+        return frames;
+    }
     if (s->discard) {
         // keep the conversion cost of the format, drop the result
         long acc = 0;
@@ -330,6 +439,9 @@ extern "C" int sf_command(SNDFILE *s, int command, void *data, int datasize) {
             return s && s->clipping;
         case SFC_GET_CLIPPING: return s && s->clipping;
         case SFC_WAVEX_GET_AMBISONIC: return SF_AMBISONIC_NONE;
+        case SFC_UPDATE_HEADER_NOW:
+            if (s) virt_header(s);
+            return 0;
         default: return 0;
     }
 }

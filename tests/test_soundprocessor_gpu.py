@@ -262,3 +262,104 @@ def test_batch_convolver_pcm16_wire_equals_per_file_16_bit_path(dirs, T):
                 assert diff.size == 0 or diff.max() <= (0 if T == 1 else 1), (gapless, ci, fi, int(diff.max()))
                 assert fl[k] == wfl[fi]
                 k += 1
+
+
+def test_replaced_impulse_file_invalidates_pool_and_filter_cache(dirs, tmp_path):
+    """/root/reference/sound-processor.cc:129-133 leaves the impulse files as a TODO; here a replaced
+    IR WAV (same config file, untouched) is noticed by ConfigStillUpToDate(), by the pool and by the
+    HBM filter cache -- also when the change falls into the same second (nanosecond mtime + size)."""
+    import shutil
+    P = H.product()
+    src, rate, ch, bits = dirs["tiny"]
+    d = str(tmp_path / "tiny_ir")
+    shutil.copytree(src, d)
+    x = _noise(900, ch, 0.5, 23)
+    (y0,), _, _ = P.run_chain(d, rate, ch, bits, [x])       # the processor goes back to the pool
+    # the same impulse at half the level, written right away: only the WAV changes
+    from configs import _ir
+    H.write_wav(os.path.join(d, "long.wav"), 0.5 * _ir(1000, 50)[:, None], rate, "pcm16")
+    (y1,), _, _ = P.run_chain(d, rate, ch, bits, [x])
+    assert np.abs(y0).max() > 1e-3
+    assert np.abs(y1 - 0.5 * y0).max() < 2e-4 * np.abs(y0).max() + 1e-4   # 16-bit IR quantisation of the halved taps
+    assert np.abs(y1 - y0).max() > 0.2 * np.abs(y0).max()
+    # an impulse file that appears later is noticed as well (it was stamped as missing)
+    src2 = dirs["missing_wav"][0]
+    d2 = str(tmp_path / "missing_copy")
+    shutil.copytree(src2, d2)
+    x2 = _noise(600, 2, 0.5, 24)
+    (z0,), _, _ = P.run_chain(d2, 44100, 2, 16, [x2])
+    assert not np.any(z0[:, 1])                              # parsing stopped at the missing file
+    H.write_wav(os.path.join(d2, "nothere.wav"), np.array([[0.25]]), 44100, "float")
+    (z1,), _, _ = P.run_chain(d2, 44100, 2, 16, [x2])
+    assert np.abs(z1[:, 1] - (0.25 * x2[:, 1] + 0.25 * np.concatenate([np.zeros(3, np.float32), x2[:-3, 1]]))).max() < 1e-5
+
+
+def test_batch_convolver_truncated_file_ends_there(dirs):
+    """a file shorter than its header claims (short read in the middle): it gets the frames that
+    were read, hands nothing over, and the next file starts from a reset processor -- no zero
+    padding is ever spliced into a running convolution"""
+    import ctypes as C
+    P = H.product()
+    d, rate, ch, bits = dirs["crossfeed"]
+    conf = os.path.join(d, f"filter-{rate}.conf")
+    N = _fragm(d, rate, ch)["fragm"]
+    a, b, c = _noise(2 * N + 300, ch, 0.25, 31), _noise(N + 50, ch, 0.25, 32), _noise(N // 2, ch, 0.25, 33)
+    for T in (1, 4):
+        claimed = (C.c_long * 3)(a.shape[0] + 3 * N, b.shape[0], c.shape[0])   # file a lies about its length
+        P.L.fh_set_claimed_frames(claimed, 3)
+        outs, mx, fl, steps = P.run_library(conf, rate, ch, [[a, b, c]], gapless=True, slots=2, threads=1, blocks_per_step=T)
+        P.drop_pool()
+        (wa,), _, _ = P.run_chain(d, rate, ch, bits, [a], gapless=True)
+        P.drop_pool()
+        (wb, wc), _, wfl = P.run_chain(d, rate, ch, bits, [b, c], gapless=True)
+        tol = 0 if T == 1 else 2e-6
+        assert outs[0][0].shape == wa.shape and np.abs(outs[0][0] - wa).max() <= tol
+        assert outs[0][1].shape == wb.shape and np.abs(outs[0][1] - wb).max() <= tol
+        assert outs[0][2].shape == wc.shape and np.abs(outs[0][2] - wc).max() <= tol
+        assert fl[0] == 0 and fl[1:] == wfl
+
+
+def test_album_placement_is_the_sharding_function():
+    """SoundProcessor::DeviceForKey == folve_b200/sharding.py device_for_path (CRC-32 of the album)"""
+    import ctypes as C
+    from folve_b200 import sharding
+    P = H.product()
+    P.L.fh_device_for_key.restype = C.c_int
+    P.L.fh_device_for_key.argtypes = [C.c_char_p, C.c_int]
+    for n in (1, 2, 3, 8):
+        for a in range(40):
+            album = f"/music/artist {a % 7}/album{a:03d}"
+            assert P.L.fh_device_for_key(album.encode(), n) == sharding.device_for_path(album + "/01 - track.flac", n)
+
+
+def test_one_process_many_gpus_equals_one_gpu(dirs):
+    """in-process multi-GPU: gapless chains spread over every GPU of the box from ONE process
+    (MultiDeviceConvolver, placement by album key) give every file what a single device gives it"""
+    import ctypes as C
+    from folve_b200 import capi
+    ndev = capi.lib().fcv_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs in the box")
+    P = H.product()
+    d, rate, ch, bits = dirs["crossfeed"]
+    conf = os.path.join(d, f"filter-{rate}.conf")
+    N = _fragm(d, rate, ch)["fragm"]
+    r = np.random.default_rng(5)
+    shapes = [[N + 1, 2 * N + 5, N + N // 3], [2 * N, N + 7], [N + 100, 50, 300], [3 * N + 17], [40], [N],
+              [N - 1, 1, 1, N + 2], [9 * N + 11, 5 * N, 3 * N + 3]] * 2
+    chains = [[_noise(n, ch, 0.25, int(r.integers(1 << 30))) for n in lens] for lens in shapes]
+    one, mx1, fl1, _ = P.run_library(conf, rate, ch, chains, gapless=True, slots=16, threads=2)
+    P.L.fh_set_library_devices(min(ndev, 4))
+    many, mxn, fln, _ = P.run_library(conf, rate, ch, chains, gapless=True, slots=16, threads=2)
+    where = (C.c_int * len(chains))()
+    assert P.L.fh_last_assignment(where, len(chains)) == len(chains)
+    assert len(set(where)) >= 2                       # the chains really went to different GPUs
+    for ci in range(len(chains)):
+        for fi in range(len(chains[ci])):
+            assert np.array_equal(one[ci][fi], many[ci][fi]), (ci, fi)
+    assert fl1 == fln and mx1 == mxn
+    # the drop-in API: processors are spread by load, an album key pins the device
+    P.L.fh_processor_devices.restype = C.c_int
+    devs = (C.c_int * 8)()
+    n = P.L.fh_processor_devices(conf.encode(), rate, ch, devs, 8)
+    assert n == 8 and len(set(devs)) == min(ndev, 8)
