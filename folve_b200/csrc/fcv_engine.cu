@@ -388,6 +388,38 @@ extern "C" int fcv_filter_get_impulse(fcv_filter *f, int inp, int out, float *ds
 static size_t pcm_bytes(int fmt) { return fmt == FCV_PCM_S16 ? 2 : 4; }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Pinned host staging of a batch.  Default: cudaHostAlloc.  FCV_HUGEPAGES=1 (experiment for the
+// end-to-end ceiling of multi-GPU boxes, profiles/r02_experiments.md): anonymous memory backed by
+// huge pages where the kernel grants them (MAP_HUGETLB, else transparent huge pages by madvise),
+// registered with cudaHostRegister -- 512 x fewer IOMMU / page-table entries under the DMA.
+#include <sys/mman.h>
+static bool use_hugepages() {
+    static const bool on = getenv("FCV_HUGEPAGES") && atoi(getenv("FCV_HUGEPAGES")) != 0;
+    return on;
+}
+static const size_t kHuge = 2u << 20;
+static cudaError_t staging_alloc(void **p, size_t bytes) {
+    if (!use_hugepages()) return cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
+    void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_HUGETLB, -1, 0);
+    if (m == MAP_FAILED) {
+        m = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+        m = (void *)(((uintptr_t)m + kHuge - 1) / kHuge * kHuge);   // 2 MB aligned (the slack is never unmapped)
+        madvise(m, len, MADV_HUGEPAGE);
+    }
+    memset(m, 0, len);   // fault the pages in before they are pinned
+    cudaError_t e = cudaHostRegister(m, len, cudaHostRegisterDefault);
+    if (e != cudaSuccess) return e;
+    *p = m;
+    return cudaSuccess;
+}
+static void staging_free(void *p) {
+    if (!p) return;
+    if (!use_hugepages()) { cudaFreeHost(p); return; }
+    cudaHostUnregister(p);   // the mapping itself stays until the process ends (experiment only)
+}
+
 static void batch_free(fcv_batch *b) {
     if (!b) return;
     if (b->f && b->f->device >= 0) cudaSetDevice(b->f->device);
@@ -397,11 +429,11 @@ static void batch_free(fcv_batch *b) {
     for (int i = 0; i < fcv_batch::NQ; i++)
         if (b->q[i]) { cudaStreamSynchronize(b->q[i]); cudaStreamDestroy(b->q[i]); }
     if (b->dmem) cudaFree(b->dmem);
-    if (b->hin) cudaFreeHost(b->hin);
-    if (b->hout) cudaFreeHost(b->hout);
+    if (b->hin) { if (b->per_block_max) cudaFreeHost(b->hin); else staging_free(b->hin); }
+    if (b->hout) staging_free(b->hout);
     if (b->hfv) cudaFreeHost(b->hfv);
-    if (b->hin1) cudaFreeHost(b->hin1);
-    if (b->hout1) cudaFreeHost(b->hout1);
+    if (b->hin1) staging_free(b->hin1);
+    if (b->hout1) staging_free(b->hout1);
     if (b->hfv1) cudaFreeHost(b->hfv1);
     if (b->dfv1) cudaFree(b->dfv1);
     for (int k = 0; k < 2; k++) if (b->hbmax[k]) cudaFreeHost(b->hbmax[k]);
@@ -489,8 +521,8 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
         b->in_zero_copy = ok && zc && cudaHostGetDevicePointer(&dp, b->hin, 0) == cudaSuccess && dp;
         if (b->in_zero_copy) b->hin_dev = dp;
     } else {
-        ok = ok && cudaHostAlloc((void **)&b->hin, B * b->in_block, cudaHostAllocDefault) == cudaSuccess;
-        ok = ok && cudaHostAlloc((void **)&b->hout, B * b->out_block, cudaHostAllocDefault) == cudaSuccess;
+        ok = ok && staging_alloc((void **)&b->hin, B * b->in_block) == cudaSuccess;
+        ok = ok && staging_alloc((void **)&b->hout, B * b->out_block) == cudaSuccess;
         if (ok) { memset(b->hin, 0, B * b->in_block); memset(b->hout, 0, B * b->out_block); }
     }
     std::vector<StreamDev> hs(B);
@@ -685,8 +717,8 @@ extern "C" int fcv_batch_process_device(fcv_batch *b, const int *frames_valid) {
 static int ensure_slot1(fcv_batch *b) {
     if (b->hin1) return 0;
     const size_t B = (size_t)b->B;
-    CU_TRY(cudaHostAlloc((void **)&b->hin1, B * b->in_block, cudaHostAllocDefault));
-    CU_TRY(cudaHostAlloc((void **)&b->hout1, B * b->out_block, cudaHostAllocDefault));
+    CU_TRY(staging_alloc((void **)&b->hin1, B * b->in_block));
+    CU_TRY(staging_alloc((void **)&b->hout1, B * b->out_block));
     CU_TRY(cudaHostAlloc((void **)&b->hfv1, B * sizeof(int), cudaHostAllocDefault));
     CU_TRY(cudaMalloc((void **)&b->dfv1, B * sizeof(int)));
     memset(b->hin1, 0, B * b->in_block);

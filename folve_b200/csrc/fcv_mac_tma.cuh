@@ -12,7 +12,11 @@
 // registers or issue slots (no LDG, no L2 prefetch, no address arithmetic in the math
 // warps), so the pipeline can run NS rows ahead of the arithmetic.
 //
-//   work item = (spectrum tile of 128 float4 = 2 KB, group of S streams, output), tile fastest
+//   work item = (spectrum tile of 128 float4 = 2 KB, group of S streams, output), OUTPUT fastest:
+//          the CTAs that run side by side are the outputs of one (tile, stream group).  Where
+//          several outputs are fed from the same input (crossfeed, 5.1, dense matrices) they read
+//          the same X row tiles at the same time, so all but the first read hit L2 instead of
+//          HBM; for diagonal filters the order makes no difference.
 //   grid : persistent, 1-D: CTA c takes items c, c + gridDim.x, ...; the producer runs ahead of
 //          the consumers across item boundaries, so the pipeline is filled once per CTA and the
 //          next item's rows arrive while the consumers store the current item's Y
@@ -146,7 +150,7 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
         static_assert(NS <= 32, "one lane per stage");
         uint32_t ph = 0;   // parity of this lane's stage: flips with every row the lane issues
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
+            const int o = item % nout, tile = (item / nout) % ntiles, b0 = item / (nout * ntiles) * S;
             const int p0 = pair_off[o], p1 = pair_off[o + 1];
             const unsigned char *xbase[S];
 #pragma unroll
@@ -189,7 +193,7 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
     const uint32_t bar0 = hold_u32(smem_u32(bars));
 #pragma unroll 1
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int tile = item % ntiles, b0 = (item / ntiles) % ngroups * S, o = item / (ntiles * ngroups);
+    const int o = item % nout, tile = (item / nout) % ntiles, b0 = item / (nout * ntiles) * S;
     const int p0 = pair_off[o], p1 = pair_off[o + 1];
     c2 acc[T][S][2];
 #pragma unroll
