@@ -388,36 +388,57 @@ extern "C" int fcv_filter_get_impulse(fcv_filter *f, int inp, int out, float *ds
 static size_t pcm_bytes(int fmt) { return fmt == FCV_PCM_S16 ? 2 : 4; }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Pinned host staging of a batch.  Default: cudaHostAlloc.  FCV_HUGEPAGES=1 (experiment for the
-// end-to-end ceiling of multi-GPU boxes, profiles/r02_experiments.md): anonymous memory backed by
-// huge pages where the kernel grants them (MAP_HUGETLB, else transparent huge pages by madvise),
-// registered with cudaHostRegister -- 512 x fewer IOMMU / page-table entries under the DMA.
+// Pinned host staging of a batch: anonymous memory on transparent huge pages (2 MB aligned,
+// madvise(MADV_HUGEPAGE), faulted in, then pinned with cudaHostRegister) -- 512 x fewer IOMMU /
+// page-table entries under the DMA than 4 KB pages.  Measured on the end-to-end loop
+// (profiles/r02_experiments.md): +1.5 % at one GPU (three alternating pairs, inside the run-to-run
+// spread), +4 % at two, +1 % at eight, where the host fabric saturates: never worse, so it is the
+// default.  FCV_HUGEPAGES=0, or any failure on the way: plain cudaHostAlloc.
 #include <sys/mman.h>
 static bool use_hugepages() {
-    static const bool on = getenv("FCV_HUGEPAGES") && atoi(getenv("FCV_HUGEPAGES")) != 0;
+    static const bool on = !(getenv("FCV_HUGEPAGES") && atoi(getenv("FCV_HUGEPAGES")) == 0);
     return on;
 }
+namespace {
+struct StagingMap { void *base; size_t len; };
+std::mutex g_staging_mu;
+std::map<void *, StagingMap> g_staging;   // registered pointer -> its mapping
+}  // namespace
 static const size_t kHuge = 2u << 20;
 static cudaError_t staging_alloc(void **p, size_t bytes) {
-    if (!use_hugepages()) return cudaHostAlloc(p, bytes, cudaHostAllocDefault);
-    const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
-    void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_HUGETLB, -1, 0);
-    if (m == MAP_FAILED) {
-        m = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-        if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
-        m = (void *)(((uintptr_t)m + kHuge - 1) / kHuge * kHuge);   // 2 MB aligned (the slack is never unmapped)
-        madvise(m, len, MADV_HUGEPAGE);
+    if (use_hugepages() && bytes >= kHuge) {
+        const size_t len = (bytes + kHuge - 1) / kHuge * kHuge;
+        void *base = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (base != MAP_FAILED) {
+            void *m = (void *)(((uintptr_t)base + kHuge - 1) / kHuge * kHuge);
+            madvise(m, len, MADV_HUGEPAGE);
+            memset(m, 0, len);   // fault the pages in before they are pinned
+            if (cudaHostRegister(m, len, cudaHostRegisterDefault) == cudaSuccess) {
+                std::lock_guard<std::mutex> l(g_staging_mu);
+                g_staging[m] = StagingMap{base, len + kHuge};
+                *p = m;
+                return cudaSuccess;
+            }
+            cudaGetLastError();   // clear, fall back
+            munmap(base, len + kHuge);
+        }
     }
-    memset(m, 0, len);   // fault the pages in before they are pinned
-    cudaError_t e = cudaHostRegister(m, len, cudaHostRegisterDefault);
-    if (e != cudaSuccess) return e;
-    *p = m;
-    return cudaSuccess;
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault);
 }
 static void staging_free(void *p) {
     if (!p) return;
-    if (!use_hugepages()) { cudaFreeHost(p); return; }
-    cudaHostUnregister(p);   // the mapping itself stays until the process ends (experiment only)
+    StagingMap m{nullptr, 0};
+    {
+        std::lock_guard<std::mutex> l(g_staging_mu);
+        auto it = g_staging.find(p);
+        if (it != g_staging.end()) {
+            m = it->second;
+            g_staging.erase(it);
+        }
+    }
+    if (!m.base) { cudaFreeHost(p); return; }
+    cudaHostUnregister(p);
+    munmap(m.base, m.len);
 }
 
 static void batch_free(fcv_batch *b) {
