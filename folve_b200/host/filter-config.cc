@@ -1,6 +1,12 @@
 // filter-config.cc -- see filter-config.h.  Behavioural mirror of
 // /root/reference/zita-config.cc:55-378 and zita-fconfig.cc:38-109; every
 // decision that is visible in the loaded filter cites the line it follows.
+//
+// The grammar, the error behaviour and the arithmetic order of the impulse commands follow
+// jconvolver 0.9.2's config.cc as adapted in folve (zita-config.cc, zita-fconfig.cc, zita-sstring.cc):
+// Copyright (C) 2006-2011 Fons Adriaensen <fons@linuxaudio.org>, Copyright (C) 2012 Henner Zeller
+// <h.zeller@acm.org>; GNU General Public License, version 2 or later (zita-config) / 3 or later (folve).
+// This file is distributed under the GPL, version 3 or later (COPYING).
 #include "filter-config.h"
 
 #include <ctype.h>

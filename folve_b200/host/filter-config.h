@@ -13,6 +13,12 @@
 //   /impulse/hilbert <in> <out> <gain> <delay> <length>
 //   /impulse/copy   <in> <out> <from in> <from out>
 //   /cd <path>      /input/name ...   /output/name ...   # comments
+//
+// The grammar, the error behaviour and the arithmetic order of the impulse commands follow
+// jconvolver 0.9.2's config.cc as adapted in folve (zita-config.cc, zita-fconfig.cc, zita-sstring.cc):
+// Copyright (C) 2006-2011 Fons Adriaensen <fons@linuxaudio.org>, Copyright (C) 2012 Henner Zeller
+// <h.zeller@acm.org>; GNU General Public License, version 2 or later (zita-config) / 3 or later (folve).
+// This file is distributed under the GPL, version 3 or later (COPYING).
 #ifndef FOLVE_B200_FILTER_CONFIG_H
 #define FOLVE_B200_FILTER_CONFIG_H
 
