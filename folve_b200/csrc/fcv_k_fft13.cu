@@ -138,6 +138,7 @@ static int set_attrs13() {
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
+    CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     return 0;
@@ -202,7 +203,7 @@ void fcv::launch_filter_fft13(const fcv_filter *f, const float *dsrc, float2 *ds
 
 // ---- launches -------------------------------------------------------------------------------
 // Stereo and mono blocks take the vector-load kernels (stereo: both channels per CTA), any other
-// channel count one channel per CTA with scalar loads.
+// channel count scalar loads: two channels per CTA when the count is even, else one.
 template <class SEL, int FMT>
 static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) {
     const fcv_filter *f = a.f;
@@ -213,6 +214,9 @@ static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
     else if (f->ninp == 1)
         launch_k(fwd13_stream_kernel<SEL, FMT, 1, 1>, dim3(2, a.cnt, a.T), dim3(128), f13::HALF_BYTES, q, a.pdl, sel,
                  f->tb13, f->ninp, a.R, a.T, rm);
+    else if (f->ninp % 2 == 0)   // 4, 6, 8 ... channels: pairs of channels share a CTA's twiddle loads like a stereo block
+        launch_k(fwd13_stream_kernel<SEL, FMT, 0, 2>, dim3(f->ninp, a.cnt, a.T), dim3(256), 2 * f13::HALF_BYTES, q, a.pdl,
+                 sel, f->tb13, f->ninp, a.R, a.T, rm);
     else
         launch_k(fwd13_stream_kernel<SEL, FMT, 0, 1>, dim3(2 * f->ninp, a.cnt, a.T), dim3(128), f13::HALF_BYTES, q, a.pdl,
                  sel, f->tb13, f->ninp, a.R, a.T, rm);
