@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "fcv_filter_get_spectrum": (i, [vp, i, i, i, fp]),
         "fcv_stream_get_input_spectrum": (i, [vp, i, i, fp]),
         "fcv_filter_get_impulse": (i, [vp, i, i, fp, i]),
+        "fcv_debug_set_fused": (None, [i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

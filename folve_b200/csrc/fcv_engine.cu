@@ -10,6 +10,8 @@
 // sm_100 device every entry point fails with FCV_E_CUDA.
 #include "fcv_internal.h"
 
+#include <sched.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -984,13 +986,16 @@ struct fcv_stream {
 // A set of single-stream blocks that travel through the GPU as one launch sequence.
 struct FcvGroup {
     cudaStream_t q = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;        // waited for by spinning (cudaEventSynchronize on a default event)
+    cudaEvent_t done_block = nullptr;  // the same point in the stream, waited for by sleeping (blocking-sync event)
+    bool has_block = false;            // done_block was recorded for this use of the group
     cudaEvent_t t0 = nullptr;   // tracing only
     double host_launch_us = 0;
     int n = 0;
     int members_left = 0;   // members that have not picked up their result yet
     bool launched = false;  // the completion event has been recorded for this use of the group
     bool retired = false;   // completion seen, launch slot given back
+    int busy_at_launch = 0; // launch slots in use when this group was formed (itself included)
     unsigned long long gen = 0;   // counts the uses of the group object
     fcv_stream *m[GROUP_MAX];
     GroupSel sel;
@@ -1013,26 +1018,36 @@ struct FcvCombiner {
     std::vector<FcvGroup *> groups, free_groups;
     std::deque<FcvGroup *> flying;   // groups holding a launch slot, oldest first
     int inflight = 0;
-    int depth = 6;      // launch slots: groups in flight at once (measured: 2 -> 14.5 k, 4 -> 15.9 k, 6 -> 17.2 k x realtime on 16 threads)
+    int depth = 12;     // launch slots: groups in flight at once (16 threads, one-launch groups: 4 -> 23-24 k, 8 -> 28 k, 12 -> 30 k x realtime)
     int group_max = GROUP_MAX;
     // Waiting for a change of the queue (a leader finished launching, a launch slot came free): by
     // default the few microseconds are spent polling `epoch` -- putting a caller to sleep on the
     // condition variable and waking it again costs more than a whole block on the GPU.
     std::atomic<unsigned long long> epoch{0};
     bool spin = true;
+    // ... unless there are more callers than CPUs (more open files than cores): then a spinning
+    // waiter only takes the CPU away from the thread that is launching the next group, and
+    // every wait sleeps instead (condition variable, blocking-sync event).
+    int active = 0;      // callers between submit and the return of await
+    int sleepers = 0;    // callers asleep on the condition variable
+    int ncpu = 1;
     // FCV_COMBINE_TRACE=1: where a block's time goes, printed when the filter is released
     bool trace = false;
     unsigned long long tr_groups = 0, tr_streams = 0;
+    std::atomic<unsigned long long> tr_fused{0}, tr_fused_failed{0};
     double tr_launch_us = 0, tr_gpu_us = 0, tr_queue_us = 0, tr_total_us = 0;
 };
 
+static bool combiner_crowded(const FcvCombiner *c) { return !c->spin || c->active > c->ncpu; }
 static void combiner_notify(FcvCombiner *c) {   // with the mutex held
     c->epoch.fetch_add(1, std::memory_order_release);
-    if (!c->spin) c->cv.notify_all();
+    if (c->sleepers > 0) c->cv.notify_all();
 }
 static void combiner_wait(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
-    if (!c->spin) {
+    if (combiner_crowded(c)) {
+        c->sleepers++;
         c->cv.wait(lk);
+        c->sleepers--;
         return;
     }
     const unsigned long long e = c->epoch.load(std::memory_order_relaxed);
@@ -1054,9 +1069,10 @@ static double now_us() {
 static void combiner_report(FcvCombiner *c) {
     if (c->trace && c->tr_groups)
         fprintf(stderr, "fcv coalescer: %llu blocks in %llu groups (%.2f per group); per group: host launch %.1f us, "
-                        "GPU %.1f us; per block: queued %.1f us, submit->done %.1f us\n",
+                        "GPU %.1f us; per block: queued %.1f us, submit->done %.1f us; one-launch groups %llu (failed to launch: %llu)\n",
                 c->tr_streams, c->tr_groups, (double)c->tr_streams / c->tr_groups, c->tr_launch_us / c->tr_groups,
-                c->tr_gpu_us / c->tr_groups, c->tr_queue_us / c->tr_streams, c->tr_total_us / c->tr_streams);
+                c->tr_gpu_us / c->tr_groups, c->tr_queue_us / c->tr_streams, c->tr_total_us / c->tr_streams,
+                c->tr_fused.load(), c->tr_fused_failed.load());
     c->tr_groups = c->tr_streams = 0;
     c->tr_launch_us = c->tr_gpu_us = c->tr_queue_us = c->tr_total_us = 0;
 }
@@ -1072,12 +1088,18 @@ static FcvCombiner *combiner_create(fcv_filter *f) {
     FcvCombiner *c = new (std::nothrow) FcvCombiner();
     if (!c) return nullptr;
     c->f = f;
-    // FCV_COMBINE_DEPTH: groups in flight at once (default 6); FCV_COMBINE_MAX: streams per group
+    // FCV_COMBINE_DEPTH: groups in flight at once (default 12); FCV_COMBINE_MAX: streams per group
     // (default and maximum 32; 1 = the uncoalesced per-call path, for A/B measurements)
     if (const char *v = getenv("FCV_COMBINE_DEPTH")) c->depth = atoi(v) > 0 ? atoi(v) : 1;
     if (const char *v = getenv("FCV_COMBINE_MAX")) c->group_max = atoi(v) > 0 && atoi(v) <= GROUP_MAX ? atoi(v) : GROUP_MAX;
     if (c->depth > 32) c->depth = 32;
     if (const char *v = getenv("FCV_COMBINE_SPIN")) c->spin = atoi(v) != 0;
+    {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        c->ncpu = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+        if (c->ncpu < 1) c->ncpu = 1;
+    }
     c->trace = getenv("FCV_COMBINE_TRACE") != nullptr;
     if (c->trace) {
         std::lock_guard<std::mutex> l(g_trace_mu);
@@ -1098,6 +1120,7 @@ static void combiner_destroy(FcvCombiner *c) {
     for (FcvGroup *g : c->groups) {
         if (g->q) { cudaStreamSynchronize(g->q); cudaStreamDestroy(g->q); }
         if (g->done) cudaEventDestroy(g->done);
+        if (g->done_block) cudaEventDestroy(g->done_block);
         if (g->t0) cudaEventDestroy(g->t0);
         delete g;
     }
@@ -1115,14 +1138,20 @@ static FcvGroup *combiner_take_group(FcvCombiner *c) {
     if (cudaSetDevice(c->f->device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&g->q, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&g->done, c->trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g->done_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
         (c->trace && cudaEventCreate(&g->t0) != cudaSuccess)) {
         if (g->q) cudaStreamDestroy(g->q);
+        if (g->done) cudaEventDestroy(g->done);
+        if (g->done_block) cudaEventDestroy(g->done_block);
         delete g;
         return nullptr;
     }
     c->groups.push_back(g);
     return g;
 }
+
+static std::atomic<bool> g_fused_enabled{true};
+extern "C" void fcv_debug_set_fused(int on) { g_fused_enabled.store(on != 0); }
 
 static bool use_pdl() {
     static const bool on = !(getenv("FCV_PDL") && atoi(getenv("FCV_PDL")) == 0);
@@ -1160,8 +1189,21 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
     a.num_sms = b0->num_sms;
     a.cnt = g->n;
     a.grp = &g->sel;
-    int rc = launch_step(a, g->q, nullptr);
-    if (rc) return rc;
+    // one cooperative launch for the whole group where the shape is covered (fragm 8192, stereo),
+    // else forward / MAC / inverse as three launches
+    // (a lone caller with the GPU to itself is better off with the three chained launches: 51
+    // against 58 us per block; from about four callers on the launch cost decides)
+    const bool want_fused = g->n >= 2 || g->busy_at_launch >= 4;
+    bool fused = false;
+    if (want_fused && g_fused_enabled.load(std::memory_order_relaxed) && fused13_available(f, a.in_fmt, a.out_fmt)) {
+        fused = launch_fused13(a, g->q);
+        if (fused) c->tr_fused++;
+        else c->tr_fused_failed++;
+    }
+    if (!fused) {
+        int rc = launch_step(a, g->q, nullptr);
+        if (rc) return rc;
+    }
     for (int i = 0; i < g->n; i++) {
         fcv_stream *s = g->m[i];
         fcv_batch *b = s->b;
@@ -1179,6 +1221,7 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
     }
     (void)N;
     CU_TRY(cudaEventRecord(g->done, g->q));
+    if (g->has_block) CU_TRY(cudaEventRecord(g->done_block, g->q));
     if (c->trace) g->host_launch_us = now_us() - h0;
     return 0;
 }
@@ -1217,6 +1260,8 @@ static void combiner_pump(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
         g->launched = false;
         g->gen++;
         c->inflight++;
+        g->busy_at_launch = c->inflight;
+        g->has_block = combiner_crowded(c);
         c->flying.push_back(g);
         lk.unlock();
         const int rc = launch_group(c, g);
@@ -1236,9 +1281,10 @@ static void combiner_pump(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
 // else did meanwhile, give its launch slot back and mark its members done.
 static void combiner_finish(FcvCombiner *c, FcvGroup *g, std::unique_lock<std::mutex> &lk) {
     const unsigned long long gen = g->gen;
+    cudaEvent_t ev = g->has_block && combiner_crowded(c) ? g->done_block : g->done;
     lk.unlock();
     cudaError_t e = cudaSetDevice(c->f->device);
-    if (e == cudaSuccess) e = cudaEventSynchronize(g->done);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ev);
     lk.lock();
     if (g->gen != gen || g->retired) return;   // somebody else saw it complete (the object may be in use again)
     g->retired = true;
@@ -1298,6 +1344,7 @@ extern "C" int fcv_stream_submit(fcv_stream *s, int frames_valid) {
     s->frames_valid = frames_valid;
     s->rc = 0;
     if (c->trace) s->t_submit = now_us();
+    c->active++;
     s->state = fcv_stream::PENDING;
     c->pending.push_back(s);
     combiner_pump(c, lk);
@@ -1335,6 +1382,7 @@ extern "C" int fcv_stream_await(fcv_stream *s, float *max_inout) {
                 FcvGroup *g = s->group;
                 s->group = nullptr;
                 s->state = fcv_stream::IDLE;
+                c->active--;
                 if (g && --g->members_left == 0) {
                     c->free_groups.push_back(g);
                     combiner_notify(c);

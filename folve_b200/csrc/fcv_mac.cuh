@@ -84,6 +84,43 @@ __device__ __forceinline__ float2 dcny_warp(const float2 *__restrict__ xring, co
     return make_float2(dc + ny, dc - ny);
 }
 
+// The partition walk of ONE stream for one 16-byte column (the per-file path; S = 1 in mac_kernel
+// and the MAC phase of the fused single-stream kernel): a lone stream is latency bound -- a chain
+// of dependent round trips, step table -> X row / filter rows -> FMA -- so all loads of U steps
+// are issued before the first of them is used.  acc[o][0] += X[inp][pt - part] * H[row[o]].
+template <int NO, int S>
+__device__ __forceinline__ void mac_single_steps(float4 (&acc)[NO][S], const float4 *xb, int pt,
+                                                 const MacStep *__restrict__ steps, int t0, int t1,
+                                                 const float4 *__restrict__ H, int M4, int P, int e4) {
+    constexpr int U = NO <= 2 ? 8 : 4;
+#pragma unroll 1
+    for (int t = t0; t < t1; t += U) {
+        float4 x[U], h[U][NO];
+        int row[U][NO];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool live = t + u < t1;
+            const MacStep *sp = steps + (live ? t + u : t);
+            const int inp = __ldg(&sp->inp), part = __ldg(&sp->part);
+            int slot = pt - part;
+            if (slot < 0) slot += P;
+            x[u] = ld_stream(xb + (size_t)(inp * P + slot) * (size_t)M4);
+#pragma unroll
+            for (int o = 0; o < NO; o++) row[u][o] = live ? __ldg(&sp->row[o]) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int o = 0; o < NO; o++)
+                h[u][o] = row[u][o] >= 0 ? ld_keep(H + (size_t)row[u][o] * (size_t)M4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int o = 0; o < NO; o++)
+                if (row[u][o] >= 0) cmac2(acc[o][0], x[u], h[u][o]);
+    }
+}
+
 // grid: x = M/2/TPB tiles of 2*TPB entries + 1 DC/Nyquist column, y = ceil(nstreams/S), z = output groups.
 // SEL: how the streams of the launch are addressed (fcv_stream_dev.cuh); every stream carries its
 // own ring position, Y rows and entry-0 slot.
@@ -136,36 +173,7 @@ mac_kernel(const __grid_constant__ SEL sel, int nstreams, const MacStep *__restr
 
     const int t0 = group_off[g], t1 = group_off[g + 1];
     if (S == 1) {
-        // A lone stream (the per-file path) is latency bound: a chain of dependent round trips,
-        // step table -> X row / filter rows -> FMA.  All loads of U steps are issued before the
-        // first of them is used.
-        constexpr int U = NO <= 2 ? 8 : 4;
-#pragma unroll 1
-        for (int t = t0; t < t1; t += U) {
-            float4 x[U], h[U][NO];
-            int row[U][NO];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool live = t + u < t1;
-                const MacStep *sp = steps + (live ? t + u : t);
-                const int inp = __ldg(&sp->inp), part = __ldg(&sp->part);
-                int slot = pts[0] - part;
-                if (slot < 0) slot += P;
-                x[u] = ld_stream(xb[0] + (size_t)(inp * P + slot) * (size_t)M4);
-#pragma unroll
-                for (int o = 0; o < NO; o++) row[u][o] = live ? __ldg(&sp->row[o]) : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++)
-#pragma unroll
-                for (int o = 0; o < NO; o++)
-                    h[u][o] = row[u][o] >= 0 ? ld_keep(H + (size_t)row[u][o] * (size_t)M4 + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < U; u++)
-#pragma unroll
-                for (int o = 0; o < NO; o++)
-                    if (row[u][o] >= 0) cmac2(acc[o][0], x[u], h[u][o]);
-        }
+        mac_single_steps<NO, S>(acc, xb[0], pts[0], steps, t0, t1, H, M4, P, e4);
     } else {
 #pragma unroll 2
     for (int t = t0; t < t1; t++) {

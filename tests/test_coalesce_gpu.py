@@ -143,3 +143,54 @@ def test_short_block_leaves_the_rest_of_the_buffer_zero():
     assert not np.any(s.buffer[200:2 * N])
     s.close()
     f.close()
+
+
+@pytest.mark.parametrize("fmt", [capi.PCM_F32, capi.PCM_S16, capi.PCM_S24])
+def test_one_launch_group_equals_three_launches(fmt):
+    """a group of single-stream blocks as ONE cooperative launch (fcv_k_fused13.cu) gives bit for bit
+    what the forward / MAC / inverse launches give: lone streams, short last blocks, silence,
+    many streams per group, every wire format"""
+    spec = _spec(7)
+    f = _engine(spec)
+    N = spec.fragm
+    scale = {capi.PCM_F32: 1.0, capi.PCM_S16: 32768.0, capi.PCM_S24: 8388608.0}[fmt]
+    r = np.random.default_rng(8)
+    # more streams than launch slots: the later ones queue up and travel in groups of several
+    lens = [3 * N + 17, 2 * N, N // 3, 4 * N + 1, 2 * N + N // 2, N] + [2 * N + 100 * k for k in range(18)]
+    xs = []
+    for n in lens:
+        x = r.uniform(-0.03, 0.03, (n, 2))
+        x[N // 2:N // 2 + 300] = 0.0
+        xs.append(x.astype(np.float32) if fmt == capi.PCM_F32 else np.rint(x * scale).astype(np.int32))
+    L = capi.lib()
+
+    def run(fused):
+        L.fcv_debug_set_fused(1 if fused else 0)
+        try:
+            streams = [capi.Stream(f, fmt, fmt) for _ in xs]
+            outs = [[] for _ in xs]
+            for k in range(max((len(x) + N - 1) // N for x in xs) + 1):
+                live = [i for i, x in enumerate(xs) if k * N < len(x)]
+                if k == 2:   # a block of pure silence for stream 1 in the middle of the run
+                    streams[1].submit(np.zeros((0, 2), xs[1].dtype))
+                    assert streams[1].wait().shape == (0, 2)
+                for i in live:
+                    streams[i].submit(xs[i][k * N:(k + 1) * N])
+                for i in live:
+                    outs[i].append(streams[i].wait())
+            mx = [s.max_value for s in streams]
+            [s.close() for s in streams]
+            return [np.concatenate(o) for o in outs], mx
+        finally:
+            L.fcv_debug_set_fused(1)
+
+    n0 = L.fcv_kernel_launches()
+    y3, m3 = run(False)
+    n1 = L.fcv_kernel_launches()
+    y1, m1 = run(True)
+    n2 = L.fcv_kernel_launches()
+    assert (n2 - n1) < (n1 - n0)               # groups of several streams (and busy times) take one launch instead of three
+    for a, b in zip(y3, y1):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert m3 == m1
+    f.close()
