@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "fcv_stream_get_input_spectrum": (i, [vp, i, i, fp]),
         "fcv_filter_get_impulse": (i, [vp, i, i, fp, i]),
         "fcv_debug_set_fused": (None, [i]),
+        "fcv_debug_fused_launches": (C.c_ulonglong, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -13,6 +13,7 @@
 #include <sched.h>
 
 #include <cmath>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -562,6 +563,7 @@ static fcv_batch *batch_create(fcv_filter *f, int nstreams, int in_fmt, int out_
         // output and the maximum there itself (host_copy_out)
         hs[s].hout = b->in_zero_copy ? const_cast<void *>(b->hin_dev) : nullptr;
         hs[s].hmax = b->in_zero_copy ? (float *)((unsigned char *)const_cast<void *>(b->hin_dev) + b->host_block) : nullptr;
+        hs[s].hdone = b->in_zero_copy ? (unsigned *)((unsigned char *)const_cast<void *>(b->hin_dev) + b->host_block + 64) : nullptr;
         hs[s].arrive = arrive;
     }
     ok = ok && cudaMemcpy(b->dst, hs.data(), B * sizeof(StreamDev), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -970,111 +972,79 @@ extern "C" int fcv_batch_profile(fcv_batch *b, float ms[3], int *steps) {
 // single stream == batch of one with a shared in/out host block, driven through the
 // filter's coalescer
 // ---------------------------------------------------------------------------
-struct FcvGroup;
-
 struct fcv_stream {
     fcv_batch *b = nullptr;
-    // coalescer state, guarded by the combiner's mutex
-    enum State { IDLE, PENDING, LAUNCHING, INFLIGHT, DONE } state = IDLE;
+    // request state: written by the caller (submit / await) and by the filter's dispatcher thread
+    enum State { IDLE = 0, QUEUED = 1, LAUNCHED = 2, FAILED = 3 };
+    std::atomic<int> state{IDLE};
     int frames_valid = 0;
-    FcvGroup *group = nullptr;
+    int pt = 0;                       // ring slot of the block in flight
+    unsigned seq = 0;                 // sequence number of the block in flight (what the GPU will publish)
+    cudaStream_t launched_on = nullptr;
     int rc = 0;
     std::string err;
-    double t_submit = 0, t_launch = 0;   // tracing only
+    double t_submit = 0;              // tracing only
 };
 
-// A set of single-stream blocks that travel through the GPU as one launch sequence.
-struct FcvGroup {
-    cudaStream_t q = nullptr;
-    cudaEvent_t done = nullptr;        // waited for by spinning (cudaEventSynchronize on a default event)
-    cudaEvent_t done_block = nullptr;  // the same point in the stream, waited for by sleeping (blocking-sync event)
-    bool has_block = false;            // done_block was recorded for this use of the group
-    cudaEvent_t t0 = nullptr;   // tracing only
-    double host_launch_us = 0;
-    int n = 0;
-    int members_left = 0;   // members that have not picked up their result yet
-    bool launched = false;  // the completion event has been recorded for this use of the group
-    bool retired = false;   // completion seen, launch slot given back
-    int busy_at_launch = 0; // launch slots in use when this group was formed (itself included)
-    unsigned long long gen = 0;   // counts the uses of the group object
-    fcv_stream *m[GROUP_MAX];
-    GroupSel sel;
-};
-
-// Coalescer ("group commit") of the synchronous per-file path.  folve convolves every open file
+// Dispatcher ("group commit") of the synchronous per-file path.  folve convolves every open file
 // on its own host thread, one block per call (SoundProcessor::Process, sound-processor.cc:98-127);
-// one launch sequence per call makes the process launch-rate bound (~120 k blocks/s on 16
-// threads).  Here a call queues its block; whichever caller finds a free launch slot becomes the
-// leader and sends EVERYTHING that is queued at that moment (all streams of this filter, up to
-// GROUP_MAX) through the three kernels as one group; the others wait for the group's event.
-// No thread of its own, no added latency for a lone caller (it leads its own group of one),
-// results bit-identical to one launch sequence per stream (the kernels are the same, a stream
-// never meets another stream's data).
+// one launch sequence per call makes the process launch-rate bound (a launch costs ~8 us of host
+// time in the VMs this was measured on, and launches from different threads serialise in the
+// driver).  Here
+//   * a call only queues its block and then waits for ONE WORD in its own pinned block, which the
+//     GPU writes (host_copy_out) after the block's output and maximum -- no CUDA call on the
+//     caller's side, neither to launch nor to wait;
+//   * one dispatcher thread per (filter, device) does every launch: whatever is queued when it comes
+//     round -- up to GROUP_MAX streams of the same wire formats -- travels as one launch group
+//     (one cooperative launch where the shape is covered, else forward / MAC / inverse).  Groups
+//     form by themselves: while one is being launched the next requests queue up;
+//   * results are those of one launch sequence per stream, bit for bit: the kernels are the same
+//     and a stream never meets another stream's data (tests/test_coalesce_gpu.py).
+// The dispatcher polls its queue while calls keep coming and goes to sleep on a condition variable
+// after ~200 us without work.
 struct FcvCombiner {
     fcv_filter *f = nullptr;
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<fcv_stream *> pending;
-    std::vector<FcvGroup *> groups, free_groups;
-    std::deque<FcvGroup *> flying;   // groups holding a launch slot, oldest first
-    int inflight = 0;
-    int depth = 12;     // launch slots: groups in flight at once (16 threads, one-launch groups: 4 -> 23-24 k, 8 -> 28 k, 12 -> 30 k x realtime)
-    int group_max = GROUP_MAX;
-    // Waiting for a change of the queue (a leader finished launching, a launch slot came free): by
-    // default the few microseconds are spent polling `epoch` -- putting a caller to sleep on the
-    // condition variable and waking it again costs more than a whole block on the GPU.
-    std::atomic<unsigned long long> epoch{0};
-    bool spin = true;
-    // ... unless there are more callers than CPUs (more open files than cores): then a spinning
-    // waiter only takes the CPU away from the thread that is launching the next group, and
-    // every wait sleeps instead (condition variable, blocking-sync event).
-    int active = 0;      // callers between submit and the return of await
-    int sleepers = 0;    // callers asleep on the condition variable
+    std::vector<fcv_stream *> pending;      // guarded by mu
+    std::atomic<int> npending{0};
+    bool sleeping = false, quit = false, started = false;   // guarded by mu
+    std::thread th;
+    static const int NQ = 8;
+    cudaStream_t q[NQ] = {};
+    int next_q = 0;
+    std::atomic<int> active{0};             // callers between submit and the return of await
     int ncpu = 1;
-    // FCV_COMBINE_TRACE=1: where a block's time goes, printed when the filter is released
+    int group_max = GROUP_MAX;
+    // FCV_COMBINE_TRACE=1: where a block's time goes, printed when the filter is released / at exit
     bool trace = false;
-    unsigned long long tr_groups = 0, tr_streams = 0;
-    std::atomic<unsigned long long> tr_fused{0}, tr_fused_failed{0};
-    double tr_launch_us = 0, tr_gpu_us = 0, tr_queue_us = 0, tr_total_us = 0;
+    std::atomic<unsigned long long> tr_groups{0}, tr_streams{0}, tr_fused{0}, tr_fused_failed{0};
+    double tr_launch_us = 0, tr_queue_us = 0;           // dispatcher thread only
+    std::atomic<unsigned long long> tr_total_ns{0};     // callers
 };
-
-static bool combiner_crowded(const FcvCombiner *c) { return !c->spin || c->active > c->ncpu; }
-static void combiner_notify(FcvCombiner *c) {   // with the mutex held
-    c->epoch.fetch_add(1, std::memory_order_release);
-    if (c->sleepers > 0) c->cv.notify_all();
-}
-static void combiner_wait(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
-    if (combiner_crowded(c)) {
-        c->sleepers++;
-        c->cv.wait(lk);
-        c->sleepers--;
-        return;
-    }
-    const unsigned long long e = c->epoch.load(std::memory_order_relaxed);
-    lk.unlock();
-    for (int i = 0; i < 4000 && c->epoch.load(std::memory_order_acquire) == e; i++) {
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
-    lk.lock();
-}
 
 static double now_us() {
     timespec t;
     clock_gettime(CLOCK_MONOTONIC, &t);
     return 1e6 * (double)t.tv_sec + 1e-3 * (double)t.tv_nsec;
 }
+static inline void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+}
 
 static void combiner_report(FcvCombiner *c) {
-    if (c->trace && c->tr_groups)
-        fprintf(stderr, "fcv coalescer: %llu blocks in %llu groups (%.2f per group); per group: host launch %.1f us, "
-                        "GPU %.1f us; per block: queued %.1f us, submit->done %.1f us; one-launch groups %llu (failed to launch: %llu)\n",
-                c->tr_streams, c->tr_groups, (double)c->tr_streams / c->tr_groups, c->tr_launch_us / c->tr_groups,
-                c->tr_gpu_us / c->tr_groups, c->tr_queue_us / c->tr_streams, c->tr_total_us / c->tr_streams,
+    const unsigned long long g = c->tr_groups.load(), n = c->tr_streams.load();
+    if (c->trace && g)
+        fprintf(stderr, "fcv dispatcher: %llu blocks in %llu groups (%.2f per group); per group: host launch %.1f us; "
+                        "per block: queued %.1f us, submit->done %.1f us; one-launch groups %llu (failed to launch: %llu)\n",
+                n, g, (double)n / g, c->tr_launch_us / g, c->tr_queue_us / n, 1e-3 * (double)c->tr_total_ns.load() / n,
                 c->tr_fused.load(), c->tr_fused_failed.load());
-    c->tr_groups = c->tr_streams = 0;
-    c->tr_launch_us = c->tr_gpu_us = c->tr_queue_us = c->tr_total_us = 0;
+    c->tr_groups = 0;
+    c->tr_streams = 0;
+    c->tr_total_ns = 0;
+    c->tr_launch_us = c->tr_queue_us = 0;
 }
 
 static std::mutex g_trace_mu;
@@ -1088,12 +1058,8 @@ static FcvCombiner *combiner_create(fcv_filter *f) {
     FcvCombiner *c = new (std::nothrow) FcvCombiner();
     if (!c) return nullptr;
     c->f = f;
-    // FCV_COMBINE_DEPTH: groups in flight at once (default 12); FCV_COMBINE_MAX: streams per group
-    // (default and maximum 32; 1 = the uncoalesced per-call path, for A/B measurements)
-    if (const char *v = getenv("FCV_COMBINE_DEPTH")) c->depth = atoi(v) > 0 ? atoi(v) : 1;
+    // FCV_COMBINE_MAX: streams per group (default and maximum 32; 1 = one launch group per block)
     if (const char *v = getenv("FCV_COMBINE_MAX")) c->group_max = atoi(v) > 0 && atoi(v) <= GROUP_MAX ? atoi(v) : GROUP_MAX;
-    if (c->depth > 32) c->depth = 32;
-    if (const char *v = getenv("FCV_COMBINE_SPIN")) c->spin = atoi(v) != 0;
     {
         cpu_set_t set;
         CPU_ZERO(&set);
@@ -1106,77 +1072,63 @@ static FcvCombiner *combiner_create(fcv_filter *f) {
         if (g_traced.empty()) atexit(combiner_report_all);
         g_traced.push_back(c);
     }
-    return c;  // CUDA streams and events of the groups are made on first use
+    return c;  // the dispatcher thread and its CUDA streams are made on first use
 }
 
 static void combiner_destroy(FcvCombiner *c) {
     if (!c) return;
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        c->quit = true;
+        c->cv.notify_all();
+    }
+    if (c->th.joinable()) c->th.join();
     if (c->trace) {
         combiner_report(c);
         std::lock_guard<std::mutex> l(g_trace_mu);
         for (auto it = g_traced.begin(); it != g_traced.end(); ++it)
             if (*it == c) { g_traced.erase(it); break; }
     }
-    for (FcvGroup *g : c->groups) {
-        if (g->q) { cudaStreamSynchronize(g->q); cudaStreamDestroy(g->q); }
-        if (g->done) cudaEventDestroy(g->done);
-        if (g->done_block) cudaEventDestroy(g->done_block);
-        if (g->t0) cudaEventDestroy(g->t0);
-        delete g;
-    }
+    for (int i = 0; i < FcvCombiner::NQ; i++)
+        if (c->q[i]) { cudaStreamSynchronize(c->q[i]); cudaStreamDestroy(c->q[i]); }
     delete c;
 }
 
-static FcvGroup *combiner_take_group(FcvCombiner *c) {
-    if (!c->free_groups.empty()) {
-        FcvGroup *g = c->free_groups.back();
-        c->free_groups.pop_back();
-        return g;
-    }
-    FcvGroup *g = new (std::nothrow) FcvGroup();
-    if (!g) return nullptr;
-    if (cudaSetDevice(c->f->device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&g->q, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g->done, c->trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g->done_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
-        (c->trace && cudaEventCreate(&g->t0) != cudaSuccess)) {
-        if (g->q) cudaStreamDestroy(g->q);
-        if (g->done) cudaEventDestroy(g->done);
-        if (g->done_block) cudaEventDestroy(g->done_block);
-        delete g;
-        return nullptr;
-    }
-    c->groups.push_back(g);
-    return g;
-}
-
-static std::atomic<bool> g_fused_enabled{true};
+// One cooperative launch per group (fcv_k_fused13.cu) instead of three launches: bit-identical
+// and measured SLOWER where it was meant to help (16 callers: 20-22 k against 24 k x realtime --
+// concurrent cooperative grids overlap badly on the device, and with a single launching thread a
+// launch costs ~3 us, not the ~8 us of contended launches), so it is off unless asked for:
+// FCV_FUSED=1, or fcv_debug_set_fused(1) from the tests that prove the equivalence.
+static std::atomic<bool> g_fused_enabled{getenv("FCV_FUSED") && atoi(getenv("FCV_FUSED")) != 0};
+static std::atomic<unsigned long long> g_fused_launches{0};
 extern "C" void fcv_debug_set_fused(int on) { g_fused_enabled.store(on != 0); }
+extern "C" unsigned long long fcv_debug_fused_launches(void) { return g_fused_launches.load(); }
 
 static bool use_pdl() {
     static const bool on = !(getenv("FCV_PDL") && atoi(getenv("FCV_PDL")) == 0);
     return on;
 }
 
-// Enqueue the whole group: (staged input copies,) three kernels, one or two device->host copies
-// per stream, completion event.  Runs without the combiner's mutex.
-static int launch_group(FcvCombiner *c, FcvGroup *g) {
+static unsigned *stream_done_word(const fcv_batch *b) {   // host address of the completion word
+    return reinterpret_cast<unsigned *>(b->hin + b->host_block + 64);
+}
+
+// Enqueue one group on CUDA stream q: (staged input copies,) one cooperative launch or three
+// launches, (staged output copies).  Dispatcher thread only.
+static int launch_group(FcvCombiner *c, fcv_stream *const *m, int n, cudaStream_t q) {
     const fcv_filter *f = c->f;
-    CU_TRY(cudaSetDevice(f->device));
-    const size_t N = (size_t)f->fragm;
-    const fcv_batch *b0 = g->m[0]->b;
-    const double h0 = c->trace ? now_us() : 0;
-    if (c->trace) cudaEventRecord(g->t0, g->q);
-    for (int i = 0; i < g->n; i++) {
-        fcv_stream *s = g->m[i];
+    const fcv_batch *b0 = m[0]->b;
+    GroupSel sel;
+    for (int i = 0; i < n; i++) {
+        fcv_stream *s = m[i];
         fcv_batch *b = s->b;
-        if (c->trace) s->t_launch = h0;
-        g->sel.st[i] = b->dst;
-        g->sel.fv[i] = s->frames_valid;
-        g->sel.pt[i] = (int)(b->step % (unsigned long long)b->R);
+        sel.st[i] = b->dst;
+        sel.fv[i] = s->frames_valid;
+        sel.pt[i] = s->pt;
+        sel.sq[i] = s->seq;
         if (s->frames_valid > 0 && !b->in_zero_copy)
             CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)s->frames_valid * f->ninp * pcm_bytes(b->in_fmt),
-                                   cudaMemcpyHostToDevice, g->q));
+                                   cudaMemcpyHostToDevice, q));
     }
     StepArgs a;
     a.f = f;
@@ -1187,135 +1139,111 @@ static int launch_group(FcvCombiner *c, FcvGroup *g) {
     a.pdl = use_pdl();
     a.per_block_max = true;
     a.num_sms = b0->num_sms;
-    a.cnt = g->n;
-    a.grp = &g->sel;
-    // one cooperative launch for the whole group where the shape is covered (fragm 8192, stereo),
-    // else forward / MAC / inverse as three launches
-    // (a lone caller with the GPU to itself is better off with the three chained launches: 51
-    // against 58 us per block; from about four callers on the launch cost decides)
-    const bool want_fused = g->n >= 2 || g->busy_at_launch >= 4;
+    a.cnt = n;
+    a.grp = &sel;
+    // forward / MAC / inverse as three launches chained by programmatic dependent launch -- or,
+    // when asked for and the shape is covered (fragm 8192, stereo), one cooperative launch
     bool fused = false;
-    if (want_fused && g_fused_enabled.load(std::memory_order_relaxed) && fused13_available(f, a.in_fmt, a.out_fmt)) {
-        fused = launch_fused13(a, g->q);
-        if (fused) c->tr_fused++;
+    if (g_fused_enabled.load(std::memory_order_relaxed) && fused13_available(f, a.in_fmt, a.out_fmt)) {
+        fused = launch_fused13(a, q);
+        if (fused) { c->tr_fused++; g_fused_launches++; }
         else c->tr_fused_failed++;
     }
     if (!fused) {
-        int rc = launch_step(a, g->q, nullptr);
+        int rc = launch_step(a, q, nullptr);
         if (rc) return rc;
     }
-    for (int i = 0; i < g->n; i++) {
-        fcv_stream *s = g->m[i];
+    for (int i = 0; i < n; i++) {
+        fcv_stream *s = m[i];
         fcv_batch *b = s->b;
-        b->step++;
-        if (b->in_zero_copy) continue;   // the inverse kernel has written output and maximum to the host block
+        if (b->in_zero_copy) continue;   // the inverse kernel writes output, maximum and completion word itself
         // Staged variant (FCV_STREAM_ZEROCOPY=0): the first frames_valid output frames go back into
-        // the block (sound-processor.cc:116-125), the block's maximum into the mirror behind it.
+        // the block (sound-processor.cc:116-125), then the maximum, then -- in stream order -- the
+        // completion word.
         const size_t out_bytes = (size_t)s->frames_valid * f->nout * pcm_bytes(b->out_fmt);
-        if (out_bytes == b->out_block && b->out_block == b->host_block) {
-            CU_TRY(cudaMemcpyAsync(b->hin, b->dout, b->out_block + sizeof(float), cudaMemcpyDeviceToHost, g->q));
-        } else {
-            if (out_bytes) CU_TRY(cudaMemcpyAsync(b->hin, b->dout, out_bytes, cudaMemcpyDeviceToHost, g->q));
-            CU_TRY(cudaMemcpyAsync(b->hin + b->host_block, b->maxv, sizeof(float), cudaMemcpyDeviceToHost, g->q));
-        }
+        if (out_bytes) CU_TRY(cudaMemcpyAsync(b->hin, b->dout, out_bytes, cudaMemcpyDeviceToHost, q));
+        CU_TRY(cudaMemcpyAsync(b->hin + b->host_block, b->maxv, sizeof(float), cudaMemcpyDeviceToHost, q));
+        b->seq_src = s->seq;
+        CU_TRY(cudaMemcpyAsync(stream_done_word(b), &b->seq_src, sizeof(unsigned), cudaMemcpyHostToHost, q));
     }
-    (void)N;
-    CU_TRY(cudaEventRecord(g->done, g->q));
-    if (g->has_block) CU_TRY(cudaEventRecord(g->done_block, g->q));
-    if (c->trace) g->host_launch_us = now_us() - h0;
     return 0;
 }
 
-// With the mutex held: start groups while there is queued work and a free launch slot.
-static void combiner_pump(FcvCombiner *c, std::unique_lock<std::mutex> &lk) {
-    while (!c->pending.empty() && c->inflight < c->depth) {
-        FcvGroup *g = combiner_take_group(c);
-        if (!g) {   // no CUDA stream / event to be had: everything queued fails
-            for (fcv_stream *s : c->pending) {
-                s->rc = FCV_E_CUDA;
-                s->err = "cannot create a CUDA stream for the launch group";
-                s->group = nullptr;
-                s->state = fcv_stream::DONE;
+static void dispatcher_main(FcvCombiner *c) {
+    cudaSetDevice(c->f->device);
+    std::vector<fcv_stream *> take, group;
+    int idle_polls = 0;
+    for (;;) {
+        // poll the queue while calls keep coming; sleep after a while without work
+        if (c->npending.load(std::memory_order_acquire) == 0) {
+            if (++idle_polls < 4000) {
+                cpu_relax();
+                if ((idle_polls & 63) == 0) {
+                    std::unique_lock<std::mutex> lk(c->mu);
+                    if (c->quit) return;
+                }
+                continue;
             }
-            c->pending.clear();
-            combiner_notify(c);
-            return;
-        }
-        // everything queued with the wire formats of the oldest request, oldest first
-        const fcv_batch *b0 = c->pending.front()->b;
-        g->n = 0;
-        for (auto it = c->pending.begin(); it != c->pending.end() && g->n < c->group_max;) {
-            fcv_stream *s = *it;
-            if (s->b->in_fmt == b0->in_fmt && s->b->out_fmt == b0->out_fmt) {
-                g->m[g->n++] = s;
-                s->state = fcv_stream::LAUNCHING;
-                s->group = g;
-                it = c->pending.erase(it);
-            } else {
-                ++it;
+            std::unique_lock<std::mutex> lk(c->mu);
+            if (c->quit && c->pending.empty()) return;
+            if (c->pending.empty()) {
+                c->sleeping = true;
+                c->cv.wait(lk, [c] { return c->quit || !c->pending.empty(); });
+                c->sleeping = false;
+                if (c->quit && c->pending.empty()) return;
             }
         }
-        g->members_left = g->n;
-        g->retired = false;
-        g->launched = false;
-        g->gen++;
-        c->inflight++;
-        g->busy_at_launch = c->inflight;
-        g->has_block = combiner_crowded(c);
-        c->flying.push_back(g);
-        lk.unlock();
-        const int rc = launch_group(c, g);
-        const std::string err = rc ? g_err : std::string();
-        lk.lock();
-        for (int i = 0; i < g->n; i++) {
-            g->m[i]->rc = rc;
-            g->m[i]->err = err;
-            g->m[i]->state = fcv_stream::INFLIGHT;   // on failure the event wait below returns at once or fails too
+        idle_polls = 0;
+        {
+            std::unique_lock<std::mutex> lk(c->mu);
+            take.swap(c->pending);
+            c->npending.store(0, std::memory_order_release);
         }
-        g->launched = true;
-        combiner_notify(c);
-    }
-}
-
-// With the mutex held: wait (unlocked) for the completion event of a launched group and, if nobody
-// else did meanwhile, give its launch slot back and mark its members done.
-static void combiner_finish(FcvCombiner *c, FcvGroup *g, std::unique_lock<std::mutex> &lk) {
-    const unsigned long long gen = g->gen;
-    cudaEvent_t ev = g->has_block && combiner_crowded(c) ? g->done_block : g->done;
-    lk.unlock();
-    cudaError_t e = cudaSetDevice(c->f->device);
-    if (e == cudaSuccess) e = cudaEventSynchronize(ev);
-    lk.lock();
-    if (g->gen != gen || g->retired) return;   // somebody else saw it complete (the object may be in use again)
-    g->retired = true;
-    c->inflight--;
-    if (c->trace) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, g->t0, g->done) == cudaSuccess) c->tr_gpu_us += 1e3 * ms;
-        const double t = now_us();
-        c->tr_groups++;
-        c->tr_streams += (unsigned long long)g->n;
-        c->tr_launch_us += g->host_launch_us;
-        for (int i = 0; i < g->n; i++) {
-            c->tr_queue_us += g->m[i]->t_launch - g->m[i]->t_submit;
-            c->tr_total_us += t - g->m[i]->t_submit;
+        const double t_take = c->trace ? now_us() : 0;
+        // everything queued, oldest first, in groups of equal wire formats
+        while (!take.empty()) {
+            const fcv_batch *b0 = take.front()->b;
+            group.clear();
+            for (auto it = take.begin(); it != take.end() && (int)group.size() < c->group_max;) {
+                if ((*it)->b->in_fmt == b0->in_fmt && (*it)->b->out_fmt == b0->out_fmt) {
+                    group.push_back(*it);
+                    it = take.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            if (!c->q[c->next_q] &&
+                cudaStreamCreateWithFlags(&c->q[c->next_q], cudaStreamNonBlocking) != cudaSuccess) {
+                for (fcv_stream *s : group) {
+                    s->rc = FCV_E_CUDA;
+                    s->err = "cannot create a CUDA stream for the launch group";
+                    s->state.store(fcv_stream::FAILED, std::memory_order_release);
+                }
+                continue;
+            }
+            cudaStream_t q = c->q[c->next_q];
+            c->next_q = (c->next_q + 1) % FcvCombiner::NQ;
+            const double h0 = c->trace ? now_us() : 0;
+            const int rc = launch_group(c, group.data(), (int)group.size(), q);
+            if (c->trace) {
+                std::unique_lock<std::mutex> lk(c->mu);
+                c->tr_launch_us += now_us() - h0;
+                c->tr_groups++;
+                c->tr_streams += group.size();
+                for (fcv_stream *s : group) c->tr_queue_us += t_take - s->t_submit;
+            }
+            for (fcv_stream *s : group) {
+                if (rc) {
+                    s->rc = rc;
+                    s->err = fcv_last_error();
+                    s->state.store(fcv_stream::FAILED, std::memory_order_release);
+                } else {
+                    s->launched_on = q;
+                    s->state.store(fcv_stream::LAUNCHED, std::memory_order_release);
+                }
+            }
         }
     }
-    for (auto it = c->flying.begin(); it != c->flying.end(); ++it)
-        if (*it == g) { c->flying.erase(it); break; }
-    for (int i = 0; i < g->n; i++) {
-        fcv_stream *m = g->m[i];
-        if (e != cudaSuccess && m->rc == 0) {
-            m->rc = FCV_E_CUDA;
-            m->err = std::string("convolution failed: ") + cudaGetErrorString(e);
-        }
-        m->state = fcv_stream::DONE;
-    }
-    combiner_notify(c);   // members pick up their result
-    // The thread that saw the group complete is awake and holds a free launch slot: it sends off
-    // whatever queued up meanwhile before it returns to its own caller (a queued caller asleep on
-    // the condition variable would take tens of microseconds to get there, with the GPU idle).
-    combiner_pump(c, lk);
 }
 
 extern "C" fcv_stream *fcv_stream_create_fmt(fcv_filter *f, int in_format, int out_format) {
@@ -1335,19 +1263,62 @@ extern "C" int fcv_stream_submit(fcv_stream *s, int frames_valid) {
     fcv_batch *b = s->b;
     const fcv_filter *f = b->f;
     if (frames_valid < 0 || frames_valid > f->fragm) return fail(FCV_E_PARAM, "frames_valid out of range");
+    if (s->state.load(std::memory_order_acquire) != fcv_stream::IDLE)
+        return fail(FCV_E_STATE, "stream has a block in flight: call fcv_stream_await first");
     FcvCombiner *c = f->combiner;
     // the unread rest of the input block is silence (sound-processor.cc:99-103)
     const size_t in_bytes = (size_t)frames_valid * f->ninp * pcm_bytes(b->in_fmt);
     if (in_bytes < b->in_block) memset(b->hin + in_bytes, 0, b->in_block - in_bytes);
-    std::unique_lock<std::mutex> lk(c->mu);
-    if (s->state != fcv_stream::IDLE) return fail(FCV_E_STATE, "stream has a block in flight: call fcv_stream_await first");
     s->frames_valid = frames_valid;
     s->rc = 0;
+    // ring slot and sequence number are the caller's (one block per stream in flight): the
+    // sequence number is never the value the completion word holds now
+    s->pt = (int)(b->step % (unsigned long long)b->R);
+    b->step++;
+    s->seq = (unsigned)b->step;
     if (c->trace) s->t_submit = now_us();
-    c->active++;
-    s->state = fcv_stream::PENDING;
-    c->pending.push_back(s);
-    combiner_pump(c, lk);
+    if (c->active.fetch_add(1, std::memory_order_acq_rel) == 0 && c->group_max > 0) {
+        // Nobody else has a block in flight: this caller launches its own group of one, right here,
+        // on the stream's own CUDA stream -- no hand-over to the dispatcher thread (3 us less on the
+        // lone-stream block latency).
+        if (cudaSetDevice(f->device) != cudaSuccess) {
+            c->active.fetch_sub(1, std::memory_order_relaxed);
+            return fail(FCV_E_CUDA, "cudaSetDevice failed");
+        }
+        const double h0 = c->trace ? now_us() : 0;
+        const int rc = launch_group(c, &s, 1, b->q[0]);
+        if (rc) {
+            c->active.fetch_sub(1, std::memory_order_relaxed);
+            return rc;
+        }
+        if (c->trace) {
+            std::unique_lock<std::mutex> lk(c->mu);
+            c->tr_launch_us += now_us() - h0;
+            c->tr_groups++;
+            c->tr_streams++;
+        }
+        s->launched_on = b->q[0];
+        s->state.store(fcv_stream::LAUNCHED, std::memory_order_release);
+        return 0;
+    }
+    s->state.store(fcv_stream::QUEUED, std::memory_order_release);
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        if (!c->started) {
+            c->started = true;
+            try {
+                c->th = std::thread(dispatcher_main, c);
+            } catch (...) {
+                c->started = false;
+                s->state.store(fcv_stream::IDLE, std::memory_order_release);
+                c->active.fetch_sub(1, std::memory_order_relaxed);
+                return fail(FCV_E_ALLOC, "cannot start the dispatcher thread");
+            }
+        }
+        c->pending.push_back(s);
+        c->npending.fetch_add(1, std::memory_order_release);
+        if (c->sleeping) c->cv.notify_one();
+    }
     return 0;
 }
 
@@ -1355,50 +1326,43 @@ extern "C" int fcv_stream_await(fcv_stream *s, float *max_inout) {
     if (!s) return fail(FCV_E_PARAM, "null stream");
     fcv_batch *b = s->b;
     FcvCombiner *c = b->f->combiner;
-    std::unique_lock<std::mutex> lk(c->mu);
-    for (;;) {
-        switch (s->state) {
-            case fcv_stream::IDLE:
-                return fail(FCV_E_STATE, "no block was submitted");
-            case fcv_stream::PENDING: {
-                combiner_pump(c, lk);
-                if (s->state != fcv_stream::PENDING) break;
-                // every launch slot is taken: see the oldest group in flight through (its members
-                // may all belong to this very thread, waiting to be awaited later) ...
-                FcvGroup *oldest = nullptr;
-                for (FcvGroup *g : c->flying)
-                    if (g->launched && !g->retired) { oldest = g; break; }
-                if (oldest) combiner_finish(c, oldest, lk);
-                else combiner_wait(c, lk);   // ... or wait for the leader that is launching right now
+    if (s->state.load(std::memory_order_acquire) == fcv_stream::IDLE) return fail(FCV_E_STATE, "no block was submitted");
+    volatile unsigned *done = stream_done_word(b);
+    // Wait for the GPU to publish this block's sequence number in the pinned block.  With more
+    // callers than CPUs the wait yields its time slice, otherwise it just polls the cache line.
+    int rc = 0;
+    const bool crowded = c->active.load(std::memory_order_relaxed) + 1 > c->ncpu;   // + the dispatcher
+    for (unsigned long spins = 1;; spins++) {
+        if (*done == s->seq) break;
+        const int st = s->state.load(std::memory_order_acquire);
+        if (st == fcv_stream::FAILED) {
+            rc = s->rc ? s->rc : FCV_E_CUDA;
+            break;
+        }
+        if (crowded) sched_yield();
+        else cpu_relax();
+        if ((spins & 0xfffff) == 0 && st == fcv_stream::LAUNCHED) {
+            // a long wait: has the launch itself failed on the device?
+            cudaError_t e = cudaSetDevice(b->f->device);
+            if (e == cudaSuccess) e = cudaStreamQuery(s->launched_on);
+            if (e != cudaSuccess && e != cudaErrorNotReady) {
+                s->err = std::string("convolution failed: ") + cudaGetErrorString(e);
+                rc = FCV_E_CUDA;
                 break;
-            }
-            case fcv_stream::LAUNCHING:
-                combiner_wait(c, lk);
-                break;
-            case fcv_stream::INFLIGHT:
-                combiner_finish(c, s->group, lk);
-                break;
-            case fcv_stream::DONE: {
-                FcvGroup *g = s->group;
-                s->group = nullptr;
-                s->state = fcv_stream::IDLE;
-                c->active--;
-                if (g && --g->members_left == 0) {
-                    c->free_groups.push_back(g);
-                    combiner_notify(c);
-                }
-                const int rc = s->rc;
-                if (rc) return fail(rc, "%s", s->err.c_str());
-                lk.unlock();
-                if (max_inout) {
-                    float m;
-                    memcpy(&m, b->hin + b->host_block, sizeof(float));
-                    if (m > *max_inout) *max_inout = m;
-                }
-                return 0;
             }
         }
     }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (c->trace) c->tr_total_ns += (unsigned long long)(1e3 * (now_us() - s->t_submit));
+    s->state.store(fcv_stream::IDLE, std::memory_order_release);
+    c->active.fetch_sub(1, std::memory_order_relaxed);
+    if (rc) return fail(rc, "%s", s->err.c_str());
+    if (max_inout) {
+        float m;
+        memcpy(&m, b->hin + b->host_block, sizeof(float));
+        if (m > *max_inout) *max_inout = m;
+    }
+    return 0;
 }
 
 extern "C" int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_inout) {
@@ -1407,14 +1371,12 @@ extern "C" int fcv_stream_process(fcv_stream *s, int frames_valid, float *max_in
     return fcv_stream_await(s, max_inout);
 }
 
-static int stream_idle(fcv_stream *s) {
-    std::unique_lock<std::mutex> lk(s->b->f->combiner->mu);
-    return s->state == fcv_stream::IDLE;
-}
+static int stream_idle(fcv_stream *s) { return s->state.load(std::memory_order_acquire) == fcv_stream::IDLE; }
 
 extern "C" void fcv_stream_destroy(fcv_stream *s) {
     if (!s) return;
     if (!stream_idle(s)) fcv_stream_await(s, nullptr);
+    // the block's last kernel may still be finishing OTHER streams of its group; cudaFree below waits for it
     batch_free(s->b);
     delete s;
 }

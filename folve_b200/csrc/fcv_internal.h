@@ -89,6 +89,7 @@ struct fcv_batch {
     const void *hin_dev = nullptr;       // device address of hin in that case
     size_t host_block = 0;               // single-stream mode: bytes of the shared in/out host block (max mirror behind it)
     bool copy_only = false;              // diagnostic: submit moves the PCM but launches no kernel
+    unsigned seq_src = 0;                // single-stream staged mode: source of the completion word's host-to-host copy
     int last_path = 0;                   // which entry point enqueued last (device loop / submit): see enter_path
     // device
     unsigned char *dmem = nullptr;       // one slab

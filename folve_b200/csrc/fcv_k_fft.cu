@@ -156,7 +156,7 @@ inv_stream_kernel(const __grid_constant__ SEL sel, FftTables tb, int nout, int T
     }
     if (SEL::kSingle && s.hout) {
         const int fr = fvb < 0 ? 0 : (fvb > N ? N : fvb);
-        host_copy_out(s, nout, (size_t)fr * nout * (out_fmt == PCM_S16 ? 2 : 4), tid, NT);
+        host_copy_out(s, nout, (size_t)fr * nout * (out_fmt == PCM_S16 ? 2 : 4), sel.seq(b), tid, NT);
     }
 }
 

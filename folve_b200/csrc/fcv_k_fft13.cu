@@ -127,7 +127,7 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
     }
     if (SEL::kSingle && s.hout) {
         const int fr = fvb < 0 ? 0 : (fvb > N ? N : fvb);
-        host_copy_out(s, nout, (size_t)fr * nout * wire, tid, NT);
+        host_copy_out(s, nout, (size_t)fr * nout * wire, sel.seq(b), tid, NT);
     }
 }
 

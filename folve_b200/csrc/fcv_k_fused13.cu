@@ -7,8 +7,14 @@
 // is computed differently: the phases call the very device functions of fcv_fft13.cuh and
 // fcv_mac.cuh that the separate kernels call, so results are bit-identical to the three-launch
 // path (tests/test_coalesce_gpu.py).  What changes is the cost of getting a group onto the GPU:
-// one launch instead of three (a launch costs ~8 us of host time in the VMs this was measured
-// on, profiles/r02_experiments.md) and no launch gaps between the phases.
+// one launch instead of three and no launch gaps between the phases.
+//
+// MEASURED (profiles/r02_experiments.md): host time per group 27 -> 13 us when many threads launch
+// (6 us from the single dispatcher thread), but a lone block takes 58 instead of 51 us (two
+// grid-wide barriers, 15 of 17 CTAs idle in the first and last phase), and under load concurrent
+// cooperative grids overlap worse than chained ordinary launches: 16 callers reach 20-22 k x realtime
+// against 24 k.  It is therefore OFF by default (FCV_FUSED=1 turns it on); kept because the
+// equivalence is tested and the measurement answers the question what one launch per block buys.
 //
 // Covered shape: fragm = 8192, stereo in and out (what folve feeds it); everything else keeps
 // the three-launch path.
@@ -137,7 +143,7 @@ fused13_stereo_kernel(const __grid_constant__ GroupSel sel, int n, f13::Tables t
                 }
             }
         }
-        if (s.hout) host_copy_out(s, 2, (size_t)frames * 2 * (FOUT == PCM_S16 ? 2 : 4), tid, FUSED_NT);
+        if (s.hout) host_copy_out(s, 2, (size_t)frames * 2 * (FOUT == PCM_S16 ? 2 : 4), sel.seq(b), tid, FUSED_NT);
         __syncthreads();   // shared memory (and `red`) are reused by the next item
     }
 }
@@ -170,8 +176,7 @@ static bool prepare(int device, FusedCtx &c) {
 
 // Whether a group of this filter can take the one-launch path on `device` (decided once per device).
 bool fcv::fused13_available(const fcv_filter *f, int in_fmt, int out_fmt) {
-    static const bool off = getenv("FCV_FUSED") && atoi(getenv("FCV_FUSED")) == 0;
-    if (off || !f->k13 || f->ninp != 2 || f->nout != 2 || f->group_no != 2 || f->ngroups != 1) return false;
+    if (!f->k13 || f->ninp != 2 || f->nout != 2 || f->group_no != 2 || f->ngroups != 1) return false;
     if (in_fmt != out_fmt) return false;   // instantiated for equal wire formats only
     std::lock_guard<std::mutex> l(g_mu);
     FusedCtx &c = g_ctx[f->device];

@@ -36,6 +36,7 @@ struct StreamDev {
     // of the block maximum behind it, and the count of output-channel CTAs that have finished
     void *hout;
     float *hmax;
+    unsigned *hdone;     // completion word in the pinned block: the block's sequence number once hout / hmax are complete
     unsigned *arrive;
 };
 
@@ -48,6 +49,7 @@ struct BatchSel {
     __device__ __forceinline__ StreamDev stream(int b) const { return st[b]; }
     __device__ __forceinline__ int frames(int b) const { return fv ? fv[b] : fv_all; }
     __device__ __forceinline__ int slot(int) const { return pt; }
+    __device__ __forceinline__ unsigned seq(int) const { return 0u; }
 };
 
 // Single-stream path: the output-channel CTA of a stream that finishes LAST copies the stream's
@@ -55,9 +57,12 @@ struct BatchSel {
 // block maximum into the caller's pinned host block -- coalesced 16-byte stores over the link
 // instead of one device->host copy operation (a driver call and a copy-engine transaction) per
 // stream and block.  Only the first out_bytes of the block are written, as the reference writes
-// back only the frames it read (sound-processor.cc:116-125).  Call with all threads of the CTA,
+// back only the frames it read (sound-processor.cc:116-125).  Last of all it publishes the block's
+// sequence number in the pinned block: the caller waits for that word, not for a CUDA event, so
+// a finished block costs its caller no driver call at all.  Call with all threads of the CTA,
 // after the CTA's last store to s.dout and its update of s.maxv.
-__device__ __forceinline__ void host_copy_out(const StreamDev &s, int nctas, size_t out_bytes, int tid, int nt) {
+__device__ __forceinline__ void host_copy_out(const StreamDev &s, int nctas, size_t out_bytes, unsigned seq, int tid,
+                                              int nt) {
     __shared__ int is_last;
     __syncthreads();
     if (tid == 0) {
@@ -73,9 +78,13 @@ __device__ __forceinline__ void host_copy_out(const StreamDev &s, int nctas, siz
     for (size_t i = tid; i < n16; i += nt) dst[i] = __ldcg(src + i);
     for (size_t i = n16 * 16 + tid; i < out_bytes; i += nt)
         reinterpret_cast<unsigned char *>(s.hout)[i] = __ldcg(reinterpret_cast<const unsigned char *>(s.dout) + i);
+    __threadfence_system();   // every thread's part of the block before ...
+    __syncthreads();
     if (tid == 0) {
         *s.hmax = __ldcg(s.maxv);
-        *s.arrive = 0u;    // ready for the stream's next block (ordered by the kernel boundary)
+        *s.arrive = 0u;    // ready for the stream's next block (the caller submits it only after this one)
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned *>(s.hdone) = seq;   // ... the word the caller is waiting for
     }
 }
 
@@ -85,9 +94,11 @@ struct GroupSel {
     const StreamDev *st[GROUP_MAX];
     int fv[GROUP_MAX];
     int pt[GROUP_MAX];
+    unsigned sq[GROUP_MAX];   // sequence number of each stream's block (published by host_copy_out)
     __device__ __forceinline__ StreamDev stream(int b) const { return *st[b]; }
     __device__ __forceinline__ int frames(int b) const { return fv[b]; }
     __device__ __forceinline__ int slot(int b) const { return pt[b]; }
+    __device__ __forceinline__ unsigned seq(int b) const { return sq[b]; }
 };
 
 }  // namespace fcv

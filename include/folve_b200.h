@@ -263,10 +263,12 @@ int fcv_filter_get_spectrum(fcv_filter *f, int inp, int out, int j, float *dst);
  * a link (dst receives the source pair's data), <0 on error. */
 int fcv_filter_get_impulse(fcv_filter *f, int inp, int out, float *dst, int capacity);
 int fcv_stream_get_input_spectrum(fcv_stream *s, int inp, int age, float *dst);
-/* Process-wide switch between the two implementations of a single-stream group: one cooperative
- * launch (default where the shape is covered) or three launches.  Results are identical; the
- * tests use it to show that. */
+/* Process-wide switch between the two implementations of a single-stream group: three chained
+ * launches (default) or one cooperative launch where the shape is covered (fragm 8192, stereo;
+ * also FCV_FUSED=1).  Results are identical; the tests use it to show that, and count the
+ * cooperative launches that really happened. */
 void fcv_debug_set_fused(int on);
+unsigned long long fcv_debug_fused_launches(void);
 
 #ifdef __cplusplus
 }

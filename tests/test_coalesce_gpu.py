@@ -182,14 +182,14 @@ def test_one_launch_group_equals_three_launches(fmt):
             [s.close() for s in streams]
             return [np.concatenate(o) for o in outs], mx
         finally:
-            L.fcv_debug_set_fused(1)
+            L.fcv_debug_set_fused(0)
 
-    n0 = L.fcv_kernel_launches()
+    c0 = L.fcv_debug_fused_launches()
     y3, m3 = run(False)
-    n1 = L.fcv_kernel_launches()
+    c1 = L.fcv_debug_fused_launches()
     y1, m1 = run(True)
-    n2 = L.fcv_kernel_launches()
-    assert (n2 - n1) < (n1 - n0)               # groups of several streams (and busy times) take one launch instead of three
+    c2 = L.fcv_debug_fused_launches()
+    assert c1 == c0 and c2 - c1 >= 5           # the cooperative kernel really ran in the second pass only
     for a, b in zip(y3, y1):
         assert a.shape == b.shape and np.array_equal(a, b)
     assert m3 == m1
