@@ -14,7 +14,7 @@ for tool in racecheck synccheck; do
   echo "$tool engine rc=$?" | tee -a $OUT/san_summary.txt
   grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard" $OUT/san_$tool.log | tail -5 | tee -a $OUT/san_summary.txt
 done
-timeout 900 $CS --tool racecheck python -m pytest tests/test_coalesce_gpu.py -x -q --timeout 800 -k "concurrent_threads or integer_wire" > $OUT/san_racecheck_single.log 2>&1
+timeout 900 $CS --tool racecheck python -m pytest tests/test_coalesce_gpu.py -x -q --timeout 800 -k "concurrent_threads or integer_wire or one_launch_group" > $OUT/san_racecheck_single.log 2>&1
 echo "racecheck single-stream path rc=$?" | tee -a $OUT/san_summary.txt
 grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|hazard" $OUT/san_racecheck_single.log | tail -5 | tee -a $OUT/san_summary.txt
 # ---- ThreadSanitizer
@@ -23,7 +23,7 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 --expt-relaxed-co
      -c -o /tmp/fcv_engine_tsan.o $S/fcv_engine.cu > $OUT/tsan_build.log 2>&1 &&
 g++ -fsanitize=thread -O1 -g -std=c++17 -I$H -I$H/sndfile_shim -Iinclude -o /tmp/tsan_host tools/tsan_host.cc \
     $H/sound-processor.cc $H/filter-config.cc $H/processor-pool.cc $H/batch-convolver.cc $H/sndfile_shim/sndfile_shim.cc \
-    /tmp/fcv_engine_tsan.o $S/fcv_k_fft.o $S/fcv_k_fft13.o $S/fcv_k_mac.o $S/fcv_k_mac_tma.o \
+    /tmp/fcv_engine_tsan.o $S/fcv_k_fft.o $S/fcv_k_fft13.o $S/fcv_k_mac.o $S/fcv_k_mac_tma.o $S/fcv_k_fused13.o \
     -L/usr/local/cuda/lib64 -lcudart -lpthread >> $OUT/tsan_build.log 2>&1
 if [ -x /tmp/tsan_host ]; then
   TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4" timeout 600 /tmp/tsan_host > $OUT/tsan_run.log 2>&1
