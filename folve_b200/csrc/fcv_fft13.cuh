@@ -64,6 +64,27 @@ __device__ __forceinline__ float2 w32(int j) {
     return make_float2(C[j], -S[j]);
 }
 
+#ifndef F13_TWU_FACTORED
+#define F13_TWU_FACTORED 0
+#endif
+// Unpack / repack twiddle exp(-i pi k / M) of entry 256 k2 + c of half H (bin k = 2 (256 k2 + c) + H):
+//   exp(-i pi (2c + H) / M) * exp(-i pi k2 / 16)  =  base[H][c] * w_32^k2.
+// -DF13_TWU_FACTORED=1 (experiment, OFF): only the 512 base values are read from memory (4 KB
+// instead of the 64 KB table) and the 15 other twiddles of a run are one multiplication by a
+// compile-time constant each, so that the twiddle tables of an SM shrink from 128 KB -- which cycle
+// through ~100 KB of L1 and miss it three times out of four (ncu, profiles/r02b_kernels.md) -- to
+// 68 KB.  Measured on one box, alternating builds (profiles/r02_experiments.md): forward 0.4084 ->
+// 0.4357 ms, inverse 0.5672 -> 0.5710 ms: the 30 extra packed multiplies per run cost more than
+// the L2 round trips they save (the kernels are as sensitive to their math / issue slots as to
+// load latency); parity unchanged (SNR vs float64 132.4 against 132.8 dB).
+__device__ __forceinline__ c2 ldg_c2(const float2 *p);
+#if F13_TWU_FACTORED
+#define F13_W(twu, k2, c, base) twu_of(base, k2)
+#else
+#define F13_W(twu, k2, c, base) ldg_c2((twu) + 256 * (k2) + (c))
+#endif
+__device__ __forceinline__ c2 twu_of(c2 base, int k2) { return k2 == 0 ? base : c2_cmul(base, c2_pack(w32(k2))); }
+
 __device__ __forceinline__ c2 ldg_c2(const float2 *p) {
     const float2 v = __ldg(p);
     return c2_pack(v.x, v.y);
@@ -196,9 +217,16 @@ __device__ __forceinline__ void unpack_pair(c2 zk, c2 zp, c2 w, c2 &xk, c2 &xp) 
 template <int H>
 __device__ __forceinline__ void fwd_pass_c(const c2 *sm, const Tables &tb, float2 *__restrict__ row, int t) {
     c2 *out = reinterpret_cast<c2 *>(row) + H * Q;
+#if F13_TWU_FACTORED
+    const float2 *twu = tb.twU + H * 256;   // base values exp(-i pi (2c + H) / M), c = 0..255
+#else
     const float2 *twu = tb.twU + H * Q;
+#endif
     if (H == 0 && t == 0) {
         // runs c = 0 and c = 128 hold their own partners: k2 <-> 16 - k2 and k2 <-> 15 - k2
+#if F13_TWU_FACTORED
+        const c2 b0 = ldg_c2(twu), b128 = ldg_c2(twu + 128);
+#endif
         c2 v1[16], v2[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -214,20 +242,23 @@ __device__ __forceinline__ void fwd_pass_c(const c2 *sm, const Tables &tb, float
 #pragma unroll
         for (int k2 = 1; k2 <= 8; k2++) {
             c2 xk, xp;
-            unpack_pair(v1[reg16(k2)], v1[reg16(16 - k2)], ldg_c2(twu + 256 * k2), xk, xp);
+            unpack_pair(v1[reg16(k2)], v1[reg16(16 - k2)], F13_W(twu, k2, 0, b0), xk, xp);
             out[256 * k2] = xk;
             if (k2 != 8) out[256 * (16 - k2)] = xp;
         }
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) {
             c2 xk, xp;
-            unpack_pair(v2[reg16(k2)], v2[reg16(15 - k2)], ldg_c2(twu + 256 * k2 + 128), xk, xp);
+            unpack_pair(v2[reg16(k2)], v2[reg16(15 - k2)], F13_W(twu, k2, 128, b128), xk, xp);
             out[256 * k2 + 128] = xk;
             out[256 * (15 - k2) + 128] = xp;
         }
         return;
     }
     const int c = t, cc = H == 0 ? 256 - t : 255 - t;
+#if F13_TWU_FACTORED
+    const c2 bc = ldg_c2(twu + c);
+#endif
     c2 v1[16], v2[16];
     {
         const c2 *p1 = sm + (c & 15) * ROW + (c >> 4) * 16;
@@ -243,7 +274,7 @@ __device__ __forceinline__ void fwd_pass_c(const c2 *sm, const Tables &tb, float
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) {
         c2 xk, xp;
-        unpack_pair(v1[reg16(k2)], v2[reg16(15 - k2)], ldg_c2(twu + 256 * k2 + c), xk, xp);
+        unpack_pair(v1[reg16(k2)], v2[reg16(15 - k2)], F13_W(twu, k2, c, bc), xk, xp);
         out[256 * k2 + c] = xk;
         out[256 * (15 - k2) + cc] = xp;
     }
@@ -280,8 +311,15 @@ __device__ __forceinline__ void repack_pair(c2 yk, c2 yp, c2 w, c2 &zk, c2 &zp) 
 template <int H>
 __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float2 *__restrict__ yrow, c2 zc0, int t) {
     const float2 *y = yrow + H * Q;
+#if F13_TWU_FACTORED
+    const float2 *twu = tb.twU + H * 256;
+#else
     const float2 *twu = tb.twU + H * Q;
+#endif
     if (H == 0 && t == 0) {
+#if F13_TWU_FACTORED
+        const c2 b0 = ldg_c2(twu), b128 = ldg_c2(twu + 128);
+#endif
         c2 y1[16], y2[16], v1[16], v2[16];
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
@@ -292,14 +330,14 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
 #pragma unroll
         for (int k2 = 1; k2 <= 8; k2++) {
             c2 zk, zp;
-            repack_pair(y1[k2], y1[16 - k2], ldg_c2(twu + 256 * k2), zk, zp);
+            repack_pair(y1[k2], y1[16 - k2], F13_W(twu, k2, 0, b0), zk, zp);
             v1[k2] = zk;
             if (k2 != 8) v1[16 - k2] = zp;
         }
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) {
             c2 zk, zp;
-            repack_pair(y2[k2], y2[15 - k2], ldg_c2(twu + 256 * k2 + 128), zk, zp);
+            repack_pair(y2[k2], y2[15 - k2], F13_W(twu, k2, 128, b128), zk, zp);
             v2[k2] = zk;
             v2[15 - k2] = zp;
         }
@@ -313,6 +351,9 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
         return;
     }
     const int c = t, cc = H == 0 ? 256 - t : 255 - t;
+#if F13_TWU_FACTORED
+    const c2 bc = ldg_c2(twu + c);
+#endif
     c2 v1[16], v2[16];
     {
         c2 y1[16], y2[16], w[16];
@@ -320,7 +361,7 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
         for (int k2 = 0; k2 < 16; k2++) {
             y1[k2] = ldg_stream_c2(y + 256 * k2 + c);
             y2[k2] = ldg_stream_c2(y + 256 * k2 + cc);
-            w[k2] = ldg_c2(twu + 256 * k2 + c);
+            w[k2] = F13_W(twu, k2, c, bc);
         }
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) repack_pair(y1[k2], y2[15 - k2], w[k2], v1[k2], v2[15 - k2]);

@@ -172,10 +172,16 @@ int fcv::fft13_tables(int device, f13::Tables *out) {
             for (int u = 0; u < 256; u++) h[o1 + (size_t)k0 * 256 + u] = unit((double)(u * (2 * k0 + 1) % M) / M);
         for (int n0 = 0; n0 < 16; n0++)
             for (int k1 = 0; k1 < 16; k1++) h[oB + (size_t)n0 * 16 + k1] = unit((double)(n0 * k1) / 256.0);
+#if F13_TWU_FACTORED
+        // base values of the unpack / repack twiddles: exp(-i pi (2c + h) / M), h = 0, 1, c = 0..255
+        for (int hh = 0; hh < 2; hh++)
+            for (int cc = 0; cc < 256; cc++) h[oU + (size_t)hh * 256 + cc] = unit((double)(2 * cc + hh) / (2.0 * M));
+#else
         for (int e = 0; e < 2 * Q; e++) {
             const int k = 2 * (e & (Q - 1)) + (e >> (f13::LOG2N - 1));
             h[oU + e] = unit((double)k / (2.0 * M));
         }
+#endif
         float2 *d = nullptr;
         CU_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
         CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));

@@ -19,7 +19,7 @@ struct Tables {
     const float2 *twA0;  // [15][256]  w_M^(2 u k0),      k0 = 1..15   (half 0, pass A)
     const float2 *twA1;  // [16][256]  w_M^(u (2 k0 + 1)), k0 = 0..15   (half 1, pass A, premultiply folded in)
     const float2 *twB;   // [16][16]   w_256^(n0 k1)
-    const float2 *twU;   // [2 Q]      exp(-i pi k / M) for the bin at entry e
+    const float2 *twU;   // [2][256]   exp(-i pi (2c + h) / M): base of the unpack / repack twiddles (fcv_fft13.cuh)
 };
 }  // namespace f13
 
