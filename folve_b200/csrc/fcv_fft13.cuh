@@ -204,6 +204,36 @@ __device__ __forceinline__ void pass_b(c2 *sm, const Tables &tb) {
     }
 }
 
+// Pass B of ONE half by NTH threads (ht = 0 .. NTH-1): the two halves of an inverse transform are
+// independent up to pass A^-1, so each half's 128 threads can run C^-1 -> B behind a barrier of
+// their own (inverse kernel, F13_INV_SPLIT).
+template <int DIR, int NTH>
+__device__ __forceinline__ void pass_b_one(c2 *sm, const Tables &tb, int ht) {
+    const int k0 = ht & 15;
+#pragma unroll 1
+    for (int n0 = ht >> 4; n0 < 16; n0 += NTH / 16) {
+        c2 w[16];
+#pragma unroll
+        for (int k1 = 1; k1 < 16; k1++) w[k1] = ldg_c2(tb.twB + n0 * 16 + k1);
+        c2 *p = sm + k0 * ROW + n0;
+        c2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = p[16 * j];
+        if (DIR > 0) {
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++) v[k1] = c2_cmulconj(v[k1], w[k1]);
+        }
+        Bfly<16>::template run<DIR>(v);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int k = out16(r);
+            c2 x = v[r];
+            if (DIR < 0 && k > 0) x = c2_cmul(x, w[k]);
+            p[16 * k] = x;
+        }
+    }
+}
+
 // X[k] = E - i w D and X[M-k] = conj(E + i w D) from Z[k] (zk) and Z[M-k] (zp)
 __device__ __forceinline__ void unpack_pair(c2 zk, c2 zp, c2 w, c2 &xk, c2 &xp) {
     const c2 e = c2_scale(c2_add(zk, c2_conj(zp)), 0.5f);

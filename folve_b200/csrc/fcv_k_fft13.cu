@@ -11,6 +11,12 @@
 
 using namespace fcv;
 
+#ifndef F13_INV_SPLIT
+#define F13_INV_SPLIT 0   // experiment: per-half barriers between passes C^-1 and B of the inverse kernel
+#endif
+#ifndef F13_INV_PFTW
+#define F13_INV_PFTW 0    // experiment (with F13_INV_SPLIT): L1 prefetch of the pass-A twiddles
+#endif
 #ifndef F13_INV_NT
 #define F13_INV_NT 256   // threads of the inverse kernel: 256 (2 CTAs/SM, <= 128 registers) or 128 (3 CTAs/SM)
 #endif
@@ -102,6 +108,27 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
             for (int i = 0; i < (M * 8 / 128) / NT; i++)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + M + (size_t)(tid + i * NT) * 16));
         }
+#if F13_INV_SPLIT
+        static_assert(NT == 256, "two halves of 128 threads");
+        {   // each half: C^-1 -> own 128-thread barrier -> B; only pass A^-1 needs both halves
+            const int half = tid >> 7, ht = tid & 127;
+            if (half == 0) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), ht);
+            else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, ht);
+#if F13_INV_PFTW
+            // the 31 pass-A twiddles of this thread's column: into L1 while passes C and B run
+            if ((tid & 15) == 0) {
+#pragma unroll
+                for (int k0 = 1; k0 < 16; k0++) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.twA0 + (k0 - 1) * 256 + tid));
+#pragma unroll
+                for (int k0 = 0; k0 < 16; k0++) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.twA1 + k0 * 256 + tid));
+            }
+#endif
+            if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            f13::pass_b_one<+1, 128>(sm + half * f13::HALF_ELEMS, tb, ht);
+        }
+        __syncthreads();
+#else
 #pragma unroll 1
         for (int j = tid; j < 256; j += NT) {
             if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), j);
@@ -110,6 +137,7 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
         __syncthreads();
         f13::pass_b<+1, 2, NT>(sm, tb);
         __syncthreads();
+#endif
         void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * nout * wire;
         const float m = f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames);
         lmax = fmaxf(lmax, m);
