@@ -10,7 +10,7 @@ LIB  = folve_b200/libfolve_b200.so
 all: $(LIB)
 
 # one object per kernel family (they compile in parallel: `make -j`), ptxas -v output kept per object
-CU_SRCS = fcv_engine fcv_k_fft fcv_k_fft13 fcv_k_mac fcv_k_mac_tma fcv_k_fused13
+CU_SRCS = fcv_engine fcv_nonuniform fcv_k_fft fcv_k_fft13 fcv_k_mac fcv_k_mac_tma fcv_k_fused13
 CU_OBJS = $(CU_SRCS:%=$(CSRC)/%.o)
 CU_HDRS = $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/folve_b200.h
 

@@ -617,6 +617,28 @@ def main():
                "what": "fcv_stream_process, one stream: pinned block read by the forward kernel over the link, "
                        "3 kernels, output written to the pinned block by the inverse kernel"}
         st.close()
+        # the same filter with non-uniform partitions (fcv_nustream: head partitions of 1024 frames, tail
+        # partitions of fragm): a block of 1024 frames = 23 ms of audio instead of 186 ms
+        if N == 8192:
+            q = 1024
+            nuf = wl.load(capi.NuFilter(wl.ninp, wl.nout, wl.size, q, N)).commit(local_rank)
+            nus = capi.NuStream(nuf)
+            nus.buffer[: q * wl.ninp] = m.x[0, :q].reshape(-1)
+            ts = []
+            for k in range(8 * 300):
+                t1 = time.perf_counter()
+                L.fcv_nustream_process(nus._h, q, C.byref(mx))
+                ts.append(time.perf_counter() - t1)
+            ts = np.array(ts[8 * 50:]) * 1e6
+            per_big = ts.reshape(-1, 8).sum(axis=1)
+            lat["nonuniform_q1024"] = {
+                "median": float(np.median(ts)), "p99": float(np.percentile(ts, 99)),
+                "median_of_tail_calls": float(np.median(ts.reshape(-1, 8)[:, 7])),
+                "us_per_8192_frames": float(np.median(per_big)), "calls": int(ts.size),
+                "what": "fcv_nustream_process, one stream, blocks of 1024 frames: 8 head partitions of 1024 + tail "
+                        "partitions of 8192; every 8th call also evaluates the tail level for the next large block"}
+            nus.close()
+            nuf.close()
     ctx.barrier()
 
     # ---- device resident: PCM already in HBM (left there by the steps above)

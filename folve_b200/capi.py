@@ -73,6 +73,20 @@ def lib() -> C.CDLL:
         "fcv_stream_await": (i, [vp, fp]),
         "fcv_batch_set_copy_only": (i, [vp, i]),
         "fcv_stream_filter": (vp, [vp]),
+        "fcv_nufilter_begin": (vp, [i, i, u, u, u]),
+        "fcv_nufilter_add": (i, [vp, i, i, i, fp, i, i]),
+        "fcv_nufilter_link": (i, [vp, i, i, i, i]),
+        "fcv_nufilter_commit": (i, [vp, i]),
+        "fcv_nufilter_ref": (None, [vp]),
+        "fcv_nufilter_unref": (None, [vp]),
+        "fcv_nufilter_quantum": (i, [vp]),
+        "fcv_nufilter_head_partitions": (i, [vp]),
+        "fcv_nufilter_tail_partitions": (i, [vp]),
+        "fcv_nustream_create": (vp, [vp]),
+        "fcv_nustream_destroy": (None, [vp]),
+        "fcv_nustream_reset": (i, [vp]),
+        "fcv_nustream_buffer": (fp, [vp]),
+        "fcv_nustream_process": (i, [vp, i, fp]),
         "fcv_batch_create": (vp, [vp, i, i, i]),
         "fcv_batch_create_tiled": (vp, [vp, i, i, i, i]),
         "fcv_batch_blocks_per_step": (i, [vp]),
@@ -227,6 +241,81 @@ class Stream:
     def close(self):
         if self._h:
             lib().fcv_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NuFilter:
+    """Non-uniform partitioning (Convproc::configure with quantum = minpart < maxpart)."""
+
+    def __init__(self, ninp: int, nout: int, size: int, quantum: int, maxpart: int):
+        self._h = lib().fcv_nufilter_begin(ninp, nout, size, quantum, maxpart)
+        if not self._h:
+            raise FcvError(lib().fcv_last_error().decode())
+        self.ninp, self.nout, self.size, self.quantum, self.maxpart = ninp, nout, size, quantum, maxpart
+        self.fragm = quantum     # block size of the streams (what run_blocks steps by)
+
+    def add(self, inp, out, data, ind0, step=1, ind1=None):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        if ind1 is None:
+            ind1 = ind0 + (len(data) + step - 1) // step
+        _check(lib().fcv_nufilter_add(self._h, inp, out, step, _fp(data), ind0, ind1))
+
+    def link(self, inp1, out1, inp2, out2):
+        _check(lib().fcv_nufilter_link(self._h, inp1, out1, inp2, out2))
+
+    def commit(self, device: int = 0):
+        _check(lib().fcv_nufilter_commit(self._h, device))
+        return self
+
+    @property
+    def head_partitions(self): return lib().fcv_nufilter_head_partitions(self._h)
+    @property
+    def tail_partitions(self): return lib().fcv_nufilter_tail_partitions(self._h)
+
+    def close(self):
+        if self._h:
+            lib().fcv_nufilter_unref(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NuStream:
+    def __init__(self, flt: NuFilter):
+        self.flt = flt
+        self._h = lib().fcv_nustream_create(flt._h)
+        if not self._h:
+            raise FcvError(lib().fcv_last_error().decode())
+        n = flt.quantum * max(flt.ninp, flt.nout)
+        self.buffer = np.ctypeslib.as_array(lib().fcv_nustream_buffer(self._h), shape=(n,))
+        self.max_value = 0.0
+
+    def process(self, block: np.ndarray) -> np.ndarray:
+        frames = block.shape[0]
+        f = self.flt
+        self.buffer[: frames * f.ninp] = np.ascontiguousarray(block, np.float32).reshape(-1)
+        m = C.c_float(self.max_value)
+        _check(lib().fcv_nustream_process(self._h, frames, C.byref(m)))
+        self.max_value = m.value
+        return self.buffer[: frames * f.nout].reshape(frames, f.nout).copy()
+
+    def reset(self):
+        _check(lib().fcv_nustream_reset(self._h))
+        self.max_value = 0.0
+
+    def close(self):
+        if self._h:
+            lib().fcv_nustream_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -163,6 +163,35 @@ int fcv_stream_await(fcv_stream *s, float *max_inout);
 
 fcv_filter *fcv_stream_filter(fcv_stream *s);
 
+/* ---- non-uniform partitioning ------------------------------------------------
+ * Convproc::configure(ninp, nout, maxsize, quantum, minpart, maxpart) with quantum = minpart <
+ * maxpart: zita-convolver's non-uniform mode.  folve itself always configures uniform partitions
+ * (quantum = minpart = maxpart = fragm, zita-fconfig.cc:74-93); a caller that wants a smaller block
+ * than fragm -- lower latency -- uses these.  Two levels: the first `maxpart` taps as partitions of
+ * `quantum` frames, evaluated for every block of `quantum` frames; the rest as partitions of
+ * `maxpart` frames, evaluated once per `maxpart` frames and always one large block ahead of where its
+ * output is needed.  Output == the uniform engine's with fragm = maxpart (same truncation, additive
+ * impulses, links), up to float32 rounding.  float32 PCM only. */
+typedef struct fcv_nufilter fcv_nufilter;
+typedef struct fcv_nustream fcv_nustream;
+fcv_nufilter *fcv_nufilter_begin(int ninp, int nout, unsigned size, unsigned quantum, unsigned maxpart);
+int fcv_nufilter_add(fcv_nufilter *f, int inp, int out, int step, const float *data, int ind0, int ind1);
+int fcv_nufilter_link(fcv_nufilter *f, int inp1, int out1, int inp2, int out2);
+int fcv_nufilter_commit(fcv_nufilter *f, int device);
+void fcv_nufilter_ref(fcv_nufilter *f);
+void fcv_nufilter_unref(fcv_nufilter *f);
+int fcv_nufilter_quantum(const fcv_nufilter *f);
+int fcv_nufilter_head_partitions(const fcv_nufilter *f);
+int fcv_nufilter_tail_partitions(const fcv_nufilter *f);
+fcv_nustream *fcv_nustream_create(fcv_nufilter *f);
+void fcv_nustream_destroy(fcv_nustream *s);
+int fcv_nustream_reset(fcv_nustream *s);
+/* Pinned block of quantum * max(ninp, nout) floats: interleaved input frames in, processed frames out. */
+float *fcv_nustream_buffer(fcv_nustream *s);
+/* One block of up to `quantum` frames, synchronous, like fcv_stream_process.  A block shorter than
+ * `quantum` ends the stream (reset before the next file). */
+int fcv_nustream_process(fcv_nustream *s, int frames_valid, float *max_inout);
+
 /* ---- batch: many streams of one filter, one launch per stage ------------- */
 
 /* Creates `nstreams` fresh streams that share `f` and are advanced together.
