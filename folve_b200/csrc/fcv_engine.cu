@@ -984,6 +984,7 @@ struct fcv_stream {
     int rc = 0;
     std::string err;
     double t_submit = 0;              // tracing only
+    const float *mix = nullptr;       // device frames added to the next block's output (fcv_nonuniform.cu), or null
 };
 
 // Dispatcher ("group commit") of the synchronous per-file path.  folve convolves every open file
@@ -1126,6 +1127,7 @@ static int launch_group(FcvCombiner *c, fcv_stream *const *m, int n, cudaStream_
         sel.fv[i] = s->frames_valid;
         sel.pt[i] = s->pt;
         sel.sq[i] = s->seq;
+        sel.mx[i] = s->mix;
         if (s->frames_valid > 0 && !b->in_zero_copy)
             CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)s->frames_valid * f->ninp * pcm_bytes(b->in_fmt),
                                    cudaMemcpyHostToDevice, q));
@@ -1386,6 +1388,15 @@ extern "C" int fcv_stream_reset(fcv_stream *s) {
     if (!stream_idle(s)) return fail(FCV_E_STATE, "stream has a block in flight: call fcv_stream_await first");
     return fcv_batch_reset_slot(s->b, 0);
 }
+
+// internal (fcv_nonuniform.cu): device frames [fragm][nout] float added to the output of the blocks
+// submitted from now on (any-size kernels only: fragm < 8192), and the stream's device output block
+int fcv::stream_set_mix(fcv_stream *s, const float *device_frames) {
+    if (device_frames && s->b->f->k13) return fail(FCV_E_STATE, "mixing is not available for fragm = 8192 streams");
+    s->mix = device_frames;
+    return 0;
+}
+const float *fcv::stream_device_out(const fcv_stream *s) { return reinterpret_cast<const float *>(s->b->dout); }
 
 extern "C" float *fcv_stream_buffer(fcv_stream *s) { return s ? (float *)s->b->hin : nullptr; }
 extern "C" size_t fcv_stream_buffer_bytes(const fcv_stream *s) { return s ? s->b->host_block : 0; }

@@ -162,6 +162,10 @@ void launch_mac_tt(const StepArgs &a, int newest, cudaStream_t q);      // T = 2
 bool launch_mac_tma(const StepArgs &a, int newest, cudaStream_t q);     // T = 4, 8; false: shape not covered
 void launch_dcny(const StepArgs &a, cudaStream_t q);                    // T > 1
 
+// fcv_engine.cu, for fcv_nonuniform.cu
+int stream_set_mix(fcv_stream *s, const float *device_frames);
+const float *stream_device_out(const fcv_stream *s);
+
 // fcv_k_fused13.cu: the three kernels of a single-stream group as one cooperative launch
 bool fused13_available(const fcv_filter *f, int in_fmt, int out_fmt);
 bool launch_fused13(const StepArgs &a, cudaStream_t q);   // false: not launched, take the three-launch path

@@ -72,9 +72,10 @@ fwd_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, FftTable
 
 // Overlap-add, tail save, re-interleave, float/int conversion and signed maximum
 // of one output channel; returns this thread's maximum over the valid frames.
-template <int LOG2N, int FMT>
+// MIX: add mix[frame * nout + o] (the tail level of a non-uniformly partitioned filter) to every sample.
+template <int LOG2N, int FMT, bool MIX>
 __device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables &tb, float2 *__restrict__ tail,
-                                              void *dout, int nout, int o, int frames) {
+                                              void *dout, int nout, int o, int frames, const float *__restrict__ mix) {
     constexpr int N = 1 << LOG2N, Q = N / 2;
     constexpr int NT = fft_threads(LOG2N);
     constexpr int CH = (Q / NT) < 8 ? (Q / NT) : 8;
@@ -94,10 +95,14 @@ __device__ __forceinline__ float inv_epilogue(const float2 *sm, const FftTables 
             const int n = tid + (c + i) * NT;
             const float2 a = sm[smem_pad(n)];
             const float2 t = cmulconj(sm[smem_pad(Q + n)], w[i]);
-            const float y0 = a.x + t.x + tl[i].x;
-            const float y1 = a.y + t.y + tl[i].y;
+            float y0 = a.x + t.x + tl[i].x;
+            float y1 = a.y + t.y + tl[i].y;
             tail[n] = make_float2(a.x - t.x, a.y - t.y);
             const int f0 = 2 * n;
+            if (MIX && mix) {
+                y0 += mix[(size_t)f0 * nout + o];
+                y1 += mix[(size_t)(f0 + 1) * nout + o];
+            }
             pcm_store<FMT>(dout, (size_t)f0 * nout + o, y0);
             pcm_store<FMT>(dout, (size_t)(f0 + 1) * nout + o, y1);
             if (f0 < frames) lmax = fmaxf(lmax, y0);
@@ -138,9 +143,10 @@ inv_stream_kernel(const __grid_constant__ SEL sel, FftTables tb, int nout, int T
 
         const size_t boff = (size_t)bt * N * nout;
         float m;
-        if (out_fmt == PCM_F32) m = inv_epilogue<LOG2N, PCM_F32>(sm, tb, tail, (float *)s.dout + boff, nout, o, frames);
-        else if (out_fmt == PCM_S16) m = inv_epilogue<LOG2N, PCM_S16>(sm, tb, tail, (short *)s.dout + boff, nout, o, frames);
-        else m = inv_epilogue<LOG2N, PCM_S24>(sm, tb, tail, (int *)s.dout + boff, nout, o, frames);
+        const float *mix = sel.mix(b);
+        if (out_fmt == PCM_F32) m = inv_epilogue<LOG2N, PCM_F32, SEL::kSingle>(sm, tb, tail, (float *)s.dout + boff, nout, o, frames, mix);
+        else if (out_fmt == PCM_S16) m = inv_epilogue<LOG2N, PCM_S16, SEL::kSingle>(sm, tb, tail, (short *)s.dout + boff, nout, o, frames, mix);
+        else m = inv_epilogue<LOG2N, PCM_S24, SEL::kSingle>(sm, tb, tail, (int *)s.dout + boff, nout, o, frames, mix);
         lmax = fmaxf(lmax, m);
         block_max_update(s.bmax + bt, m);
         if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block

@@ -6,8 +6,10 @@
 // quantum = minpart = maxpart = fragm (/root/reference/zita-fconfig.cc:74-93), i.e. uniform
 // partitions and a block of fragm frames; this file is what a caller with a smaller block would use.
 //
-// Two levels, built from the engine's own filters and streams (host-side composition over the C ABI;
-// every multiply-accumulate and every transform still runs in the CUDA kernels):
+// Two levels, built from the engine's own filters and streams (a composition over the C ABI: every
+// transform, multiply-accumulate AND the sum of the two levels run in the CUDA kernels -- the tail
+// level's output block stays on the device and the head level's inverse transform adds it in
+// its epilogue, before PCM conversion and maximum; the host only moves PCM):
 //   head : the first `maxpart` taps as maxpart / quantum partitions of `quantum` frames, evaluated for
 //          every block of `quantum` frames                            -> latency of one small block
 //   tail : the taps from `maxpart` on as partitions of `maxpart` frames, evaluated once per `maxpart`
@@ -40,8 +42,7 @@ struct fcv_nustream {
     fcv_stream *a = nullptr, *b = nullptr;
     float *abuf = nullptr, *bbuf = nullptr;
     int pos = 0;                   // frames of the current large block seen so far
-    bool have_tail = false;        // tail_out holds the tail's output for the current large block
-    std::vector<float> tail_out;   // [maxpart][nout]
+    bool have_tail = false;        // the tail stream's device output block holds the tail's share of the current large block
 };
 
 static bool pow2_in(unsigned v, unsigned lo, unsigned hi) { return v >= lo && v <= hi && !(v & (v - 1)); }
@@ -59,9 +60,10 @@ extern "C" fcv_nufilter *fcv_nufilter_begin(int ninp, int nout, unsigned size, u
     f->size = size;
     f->quantum = (int)quantum;
     f->maxpart = (int)maxpart;
-    const unsigned head_size = size < maxpart ? size : maxpart;
+    // quantum == maxpart is the uniform engine: one level
+    const unsigned head_size = (size < maxpart || quantum == maxpart) ? size : maxpart;
     f->head = fcv_filter_begin(ninp, nout, head_size, quantum);
-    if (f->head && size > maxpart) {
+    if (f->head && size > maxpart && quantum < maxpart) {
         f->tail = fcv_filter_begin(ninp, nout, size - maxpart, maxpart);
         if (!f->tail) { fcv_filter_unref(f->head); f->head = nullptr; }
     }
@@ -145,16 +147,7 @@ extern "C" fcv_nustream *fcv_nustream_create(fcv_nufilter *f) {
     if (s->a && f->tail) s->b = fcv_stream_create(f->tail);
     if (!s->a || (f->tail && !s->b)) { fcv_nustream_destroy(s); return nullptr; }
     s->abuf = fcv_stream_buffer(s->a);
-    if (s->b) {
-        s->bbuf = fcv_stream_buffer(s->b);
-        try {
-            s->tail_out.assign((size_t)f->maxpart * f->nout, 0.0f);
-        } catch (...) {
-            fcv_nustream_destroy(s);
-            fail(FCV_E_ALLOC, "out of memory");
-            return nullptr;
-        }
-    }
+    if (s->b) s->bbuf = fcv_stream_buffer(s->b);
     return s;
 }
 
@@ -177,23 +170,15 @@ extern "C" int fcv_nustream_process(fcv_nustream *s, int frames_valid, float *ma
     if (frames_valid < 0 || frames_valid > f->quantum) return fail(FCV_E_PARAM, "frames_valid out of range");
     if (s->b && frames_valid > 0)   // the tail level collects its large block from the same input
         memcpy(s->bbuf + (size_t)s->pos * f->ninp, s->abuf, (size_t)frames_valid * f->ninp * sizeof(float));
-    int rc = fcv_stream_process(s->a, frames_valid, nullptr);   // head level: this block, now
+    // head level: this block, now -- plus, in the inverse transform's epilogue, the tail level's
+    // output for these frames (computed one large block ago, still in the tail stream's device block)
+    int rc = stream_set_mix(s->a, s->have_tail ? stream_device_out(s->b) + (size_t)s->pos * f->nout : nullptr);
+    if (!rc) rc = fcv_stream_process(s->a, frames_valid, max_inout);
     if (rc) return rc;
-    const size_t n = (size_t)frames_valid * f->nout;
-    if (s->have_tail) {             // + the tail level's output for these frames (computed one large block ago)
-        const float *t = s->tail_out.data() + (size_t)s->pos * f->nout;
-        for (size_t i = 0; i < n; i++) s->abuf[i] += t[i];
-    }
-    if (max_inout) {                // signed maximum of the block (sound-processor.cc:120-123)
-        float m = *max_inout;
-        for (size_t i = 0; i < n; i++) m = s->abuf[i] > m ? s->abuf[i] : m;
-        *max_inout = m;
-    }
     s->pos += frames_valid;
     if (s->b && s->pos == f->maxpart) {   // a large block is complete: the tail level convolves it for the NEXT one
         rc = fcv_stream_process(s->b, f->maxpart, nullptr);
         if (rc) return rc;
-        memcpy(s->tail_out.data(), s->bbuf, s->tail_out.size() * sizeof(float));
         s->have_tail = true;
         s->pos = 0;
     }

@@ -50,6 +50,7 @@ struct BatchSel {
     __device__ __forceinline__ int frames(int b) const { return fv ? fv[b] : fv_all; }
     __device__ __forceinline__ int slot(int) const { return pt; }
     __device__ __forceinline__ unsigned seq(int) const { return 0u; }
+    __device__ __forceinline__ const float *mix(int) const { return nullptr; }
 };
 
 // Single-stream path: the output-channel CTA of a stream that finishes LAST copies the stream's
@@ -95,10 +96,15 @@ struct GroupSel {
     int fv[GROUP_MAX];
     int pt[GROUP_MAX];
     unsigned sq[GROUP_MAX];   // sequence number of each stream's block (published by host_copy_out)
+    // Optional second addend of the block's output, interleaved float frames on the device (or null):
+    // the tail level of a non-uniformly partitioned filter (fcv_nonuniform.cu), added in the inverse
+    // transform's epilogue before PCM conversion and maximum.  Any-size kernels (fcv_k_fft.cu) only.
+    const float *mx[GROUP_MAX];
     __device__ __forceinline__ StreamDev stream(int b) const { return *st[b]; }
     __device__ __forceinline__ int frames(int b) const { return fv[b]; }
     __device__ __forceinline__ int slot(int b) const { return pt[b]; }
     __device__ __forceinline__ unsigned seq(int b) const { return sq[b]; }
+    __device__ __forceinline__ const float *mix(int b) const { return mx[b]; }
 };
 
 }  // namespace fcv

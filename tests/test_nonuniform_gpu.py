@@ -29,7 +29,10 @@ def test_nonuniform_equals_uniform_and_truth(quantum):
     spec = _spec(quantum)
     x = np.random.default_rng(1).uniform(-0.25, 0.25, (3 * 8192 + 5 * quantum + 77, 2)).astype(np.float32)
     nu = spec.load(capi.NuFilter(2, 2, spec.size, quantum, 8192)).commit(0)
-    assert nu.head_partitions == 8192 // quantum and nu.tail_partitions == (spec.size - 8192 + 8191) // 8192
+    if quantum < 8192:
+        assert nu.head_partitions == 8192 // quantum and nu.tail_partitions == (spec.size - 8192 + 8191) // 8192
+    else:   # quantum == maxpart is the uniform engine: one level
+        assert nu.head_partitions == (spec.size + 8191) // 8192 and nu.tail_partitions == 0
     s = capi.NuStream(nu)
     y = run_blocks(s, x, quantum)
     uf = spec.load(capi.Filter(2, 2, spec.size, 8192)).commit(0)
