@@ -449,7 +449,7 @@ static void batch_free(fcv_batch *b) {
     if (b->f && b->f->device >= 0) cudaSetDevice(b->f->device);
     for (auto e : b->ev) cudaEventDestroy(e);
     for (int i = 0; i < 16; i++) if (b->sw[i]) cudaEventDestroy(b->sw[i]);
-    for (int i = 0; i < 5; i++) if (b->fj[i]) cudaEventDestroy(b->fj[i]);
+    for (int i = 0; i < 9; i++) if (b->fj[i]) cudaEventDestroy(b->fj[i]);
     for (int i = 0; i < fcv_batch::NQ; i++)
         if (b->q[i]) { cudaStreamSynchronize(b->q[i]); cudaStreamDestroy(b->q[i]); }
     if (b->dmem) cudaFree(b->dmem);
@@ -462,7 +462,7 @@ static void batch_free(fcv_batch *b) {
     if (b->dfv1) cudaFree(b->dfv1);
     for (int k = 0; k < 2; k++) if (b->hbmax[k]) cudaFreeHost(b->hbmax[k]);
     for (int k = 0; k < 2; k++)
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 8; i++)
             if (b->slot_done[k][i]) cudaEventDestroy(b->slot_done[k][i]);
     if (b->f) fcv_filter_unref(b->f);
     delete b;

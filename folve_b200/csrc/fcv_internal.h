@@ -110,12 +110,15 @@ struct fcv_batch {
     unsigned char *hin1 = nullptr, *hout1 = nullptr;
     int *dfv1 = nullptr, *hfv1 = nullptr;
     float *hbmax[2] = {nullptr, nullptr};   // [B][T] block maxima of the step submitted from each host slot
-    cudaEvent_t slot_done[2][4] = {};
+    cudaEvent_t slot_done[2][8] = {};
     bool slot_busy[2] = {false, false};
     // streams
-    static const int NQ = 4;
+#ifndef FCV_BATCH_NQ
+#define FCV_BATCH_NQ 4
+#endif
+    static const int NQ = FCV_BATCH_NQ;   // CUDA streams the chunks of a submit rotate over (<= 8)
     cudaStream_t q[NQ] = {};
-    cudaEvent_t fj[5] = {};  // fork/join events of the chunked device path
+    cudaEvent_t fj[9] = {};  // fork/join events of the chunked device path
     // stopwatch
     cudaEvent_t sw[16] = {};
     // profiling
