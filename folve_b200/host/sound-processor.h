@@ -54,6 +54,8 @@ public:
 
   // Reset processor for re-use: state identical to a freshly created one.
   void Reset();
+  // The name BASELINE.json's north star uses for the same call (this checkout of folve spells it Reset()).
+  void ResetBuffer() { Reset(); }
 
   // Largest (signed) output sample observed (>= 0.0).
   float max_output_value() const { return peak_seen_; }
