@@ -1120,9 +1120,11 @@ static int launch_group(FcvCombiner *c, fcv_stream *const *m, int n, cudaStream_
     const fcv_filter *f = c->f;
     const fcv_batch *b0 = m[0]->b;
     GroupSel sel;
+    bool staged[GROUP_MAX];
     for (int i = 0; i < n; i++) {
         fcv_stream *s = m[i];
         fcv_batch *b = s->b;
+        staged[i] = !b->in_zero_copy;
         sel.st[i] = b->dst;
         sel.fv[i] = s->frames_valid;
         sel.pt[i] = s->pt;
@@ -1155,13 +1157,15 @@ static int launch_group(FcvCombiner *c, fcv_stream *const *m, int n, cudaStream_
         int rc = launch_step(a, q, nullptr);
         if (rc) return rc;
     }
+    // From here on a zero-copy stream must not be touched any more: its block may complete -- and its
+    // caller return, resubmit or destroy the stream -- at any moment.
     for (int i = 0; i < n; i++) {
+        if (!staged[i]) continue;   // the inverse kernel writes output, maximum and completion word itself
         fcv_stream *s = m[i];
         fcv_batch *b = s->b;
-        if (b->in_zero_copy) continue;   // the inverse kernel writes output, maximum and completion word itself
         // Staged variant (FCV_STREAM_ZEROCOPY=0): the first frames_valid output frames go back into
         // the block (sound-processor.cc:116-125), then the maximum, then -- in stream order -- the
-        // completion word.
+        // completion word (until that copy has run the caller is still waiting: safe to touch).
         const size_t out_bytes = (size_t)s->frames_valid * f->nout * pcm_bytes(b->out_fmt);
         if (out_bytes) CU_TRY(cudaMemcpyAsync(b->hin, b->dout, out_bytes, cudaMemcpyDeviceToHost, q));
         CU_TRY(cudaMemcpyAsync(b->hin + b->host_block, b->maxv, sizeof(float), cudaMemcpyDeviceToHost, q));
@@ -1225,23 +1229,31 @@ static void dispatcher_main(FcvCombiner *c) {
             }
             cudaStream_t q = c->q[c->next_q];
             c->next_q = (c->next_q + 1) % FcvCombiner::NQ;
+            // Everything that touches the streams happens BEFORE the launch: once the kernels are
+            // enqueued a block may complete and its caller return, resubmit or destroy the stream while
+            // this thread is still on its way out of the launch call.
+            double queued_us = 0;
+            for (fcv_stream *s : group) {
+                if (c->trace) queued_us += t_take - s->t_submit;
+                s->launched_on = q;
+                s->state.store(fcv_stream::LAUNCHED, std::memory_order_release);
+            }
+            const size_t gn = group.size();
             const double h0 = c->trace ? now_us() : 0;
-            const int rc = launch_group(c, group.data(), (int)group.size(), q);
+            const int rc = launch_group(c, group.data(), (int)gn, q);
             if (c->trace) {
                 std::unique_lock<std::mutex> lk(c->mu);
                 c->tr_launch_us += now_us() - h0;
                 c->tr_groups++;
-                c->tr_streams += group.size();
-                for (fcv_stream *s : group) c->tr_queue_us += t_take - s->t_submit;
+                c->tr_streams += gn;
+                c->tr_queue_us += queued_us;
             }
-            for (fcv_stream *s : group) {
-                if (rc) {
+            if (rc) {   // nothing was (completely) enqueued: the callers are still waiting, tell them
+                const std::string err = fcv_last_error();
+                for (fcv_stream *s : group) {
                     s->rc = rc;
-                    s->err = fcv_last_error();
+                    s->err = err;
                     s->state.store(fcv_stream::FAILED, std::memory_order_release);
-                } else {
-                    s->launched_on = q;
-                    s->state.store(fcv_stream::LAUNCHED, std::memory_order_release);
                 }
             }
         }
