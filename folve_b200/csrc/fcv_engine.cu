@@ -625,6 +625,10 @@ static int run_kernels(fcv_batch *b, int off, int cnt, const int *fv_base, cudaS
     a.bsel.st = b->dst + off;
     a.bsel.fv = fv_base ? fv_base + off : nullptr;
     a.bsel.fv_all = b->T * f->fragm;
+    a.bsel.xring_stride = (size_t)f->ninp * b->R * f->fragm;
+    a.bsel.xring0 = b->xring + (size_t)off * a.bsel.xring_stride;
+    a.bsel.din_stride = b->in_zero_copy ? 0 : b->in_block;
+    a.bsel.din0 = b->in_zero_copy ? (const char *)b->hin_dev : (const char *)b->din + (size_t)off * b->in_block;
     // the step's first block goes to ring slot (step * T) mod R
     a.bsel.pt = (int)((b->step * (unsigned long long)b->T) % (unsigned long long)b->R);
     a.Y = b->Y + (size_t)off * f->nout * b->T * f->fragm;

@@ -25,6 +25,8 @@ constexpr int f13_min_ctas(int nt) { return nt >= 256 ? 2 : 3; }
 // Forward transform of the current block: one CTA = one half (blockIdx.x & 1) of the
 // spectra of C consecutive input channels (blockIdx.x >> 1 = channel group) of one
 // (stream, block): PCM and twiddles are fetched once for C transforms.
+// (One CTA computing both halves one after the other -- half as many CTAs, the second half's PCM
+// loads served by L1 / L2 -- was measured 20 % slower, profiles/r02_experiments.md.)
 template <class SEL, int FMT, int NCH, int C>
 __global__ void __launch_bounds__(128 * C, f13_min_ctas(128 * C))
 fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, int R, int T, int reset_max) {
@@ -34,17 +36,20 @@ fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, i
     pdl_trigger();
     pdl_wait();
     const int h = blockIdx.x & 1, ch0 = (blockIdx.x >> 1) * C, b = blockIdx.y, bt = blockIdx.z;
-    const StreamDev s = sel.stream(b);
     int frames = sel.frames(b) - bt * N;
     frames = frames < 0 ? 0 : (frames > N ? N : frames);
     int slot = sel.slot(b) + bt;
     if (slot >= R) slot -= R;
+    float2 *const xring = sel.xring(b);
     float2 *rows[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) rows[c] = s.xring + (size_t)((ch0 + c) * R + slot) * N;
-    // per-block maximum mode: the inverse kernel of this block starts from zero
-    if (reset_max && blockIdx.x == 0 && bt == 0 && threadIdx.x == 0) *s.maxv = 0.0f;
-    if (blockIdx.x == 0 && threadIdx.x == 0) s.bmax[bt] = 0.0f;  // this block's maximum starts from zero
+    for (int c = 0; c < C; c++) rows[c] = xring + (size_t)((ch0 + c) * R + slot) * N;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // the only thread that needs the stream's descriptor
+        const StreamDev s = sel.stream(b);
+        // per-block maximum mode: the inverse kernel of this block starts from zero
+        if (reset_max && bt == 0) *s.maxv = 0.0f;
+        s.bmax[bt] = 0.0f;  // this block's maximum starts from zero
+    }
     if (frames == 0) {  // silence: its spectrum is zero
 #pragma unroll
         for (int c = 0; c < C; c++)
@@ -52,7 +57,7 @@ fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, i
         return;
     }
     const size_t wire = FMT == PCM_S16 ? 2 : 4;
-    const void *in = reinterpret_cast<const char *>(s.din) + (size_t)bt * N * ninp * wire;
+    const void *in = reinterpret_cast<const char *>(sel.din(b)) + (size_t)bt * N * ninp * wire;
     if (h == 0) f13::fwd_half<0, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
     else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
 }

@@ -24,7 +24,7 @@ static bool launch_tma(const StepArgs &a, int newest, cudaStream_t q) {
     if (persist > 0 && a.num_sms * persist < nitems) grid = a.num_sms * persist;
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(a.Y);
-    tma::mac_tma_kernel<T, S, NS, MC><<<grid, tma::THREADS, smem, q>>>(a.bsel.st, a.cnt, f->dpairs, f->dpair_off,
+    tma::mac_tma_kernel<T, S, NS, MC><<<grid, tma::THREADS, smem, q>>>(a.bsel.xring0, a.bsel.xring_stride, a.cnt, f->dpairs, f->dpair_off,
                                                                      f->dtt_rows, H, Y, M4, f->ring, a.R, newest,
                                                                      f->nout, f->nrows, ntiles, ngroups, nitems);
     return true;

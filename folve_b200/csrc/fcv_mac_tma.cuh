@@ -115,7 +115,7 @@ __host__ __device__ constexpr int min_ctas(int T, int S) { return T * S >= 16 ? 
 
 template <int T, int S, int NS, int MC = min_ctas(T, S)>
 __global__ void __launch_bounds__(THREADS, MC)
-mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__restrict__ pairs,
+mac_tma_kernel(const float2 *__restrict__ xring0, size_t xring_stride, int nstreams, const TTPair *__restrict__ pairs,
                const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
                const float4 *__restrict__ H, float4 *__restrict__ Y, int M4, int P, int R, int newest_slot,
                int nout, int zero_row, int ntiles, int ngroups, int nitems) {
@@ -156,7 +156,8 @@ mac_tma_kernel(const StreamDev *__restrict__ st, int nstreams, const TTPair *__r
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 const int b = min(b0 + s, nstreams - 1);
-                xbase[s] = reinterpret_cast<const unsigned char *>(st[b].xring) + (size_t)tile * TILE_BYTES;
+                // the streams of a batch lie in one slab: no descriptor load in front of the first copies
+                xbase[s] = reinterpret_cast<const unsigned char *>(xring0 + (size_t)b * xring_stride) + (size_t)tile * TILE_BYTES;
             }
             const unsigned char *hbase = reinterpret_cast<const unsigned char *>(H) + (size_t)tile * TILE_BYTES;
             for (int p = p0; p < p1; p++) {

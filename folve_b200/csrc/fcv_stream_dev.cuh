@@ -46,6 +46,15 @@ struct BatchSel {
     const int *fv;   // valid frames per stream, or nullptr: fv_all for every stream
     int fv_all;
     int pt;          // ring slot of the first block of the step
+    // The streams of a batch live in slabs with a fixed stride: the forward kernel computes the two
+    // addresses it needs from these instead of loading the descriptor first (a dependent load in
+    // front of every CTA's PCM loads: 8 % of that kernel's stall samples, profiles/r02b_kernels.md).
+    float2 *xring0;       // input-spectra ring of stream 0 of the launch
+    size_t xring_stride;  // in float2 elements
+    const char *din0;     // PCM in of stream 0 of the launch
+    size_t din_stride;    // in bytes
+    __device__ __forceinline__ float2 *xring(int b) const { return xring0 + (size_t)b * xring_stride; }
+    __device__ __forceinline__ const void *din(int b) const { return din0 + (size_t)b * din_stride; }
     __device__ __forceinline__ StreamDev stream(int b) const { return st[b]; }
     __device__ __forceinline__ int frames(int b) const { return fv ? fv[b] : fv_all; }
     __device__ __forceinline__ int slot(int) const { return pt; }
@@ -100,6 +109,8 @@ struct GroupSel {
     // the tail level of a non-uniformly partitioned filter (fcv_nonuniform.cu), added in the inverse
     // transform's epilogue before PCM conversion and maximum.  Any-size kernels (fcv_k_fft.cu) only.
     const float *mx[GROUP_MAX];
+    __device__ __forceinline__ float2 *xring(int b) const { return st[b]->xring; }
+    __device__ __forceinline__ const void *din(int b) const { return st[b]->din; }
     __device__ __forceinline__ StreamDev stream(int b) const { return *st[b]; }
     __device__ __forceinline__ int frames(int b) const { return fv[b]; }
     __device__ __forceinline__ int slot(int b) const { return pt[b]; }
