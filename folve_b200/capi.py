@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
         "fcv_filter_get_impulse": (i, [vp, i, i, fp, i]),
         "fcv_debug_set_fused": (None, [i]),
         "fcv_debug_fused_launches": (C.c_ulonglong, []),
+        "fcv_debug_set_inv_pair": (None, [i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

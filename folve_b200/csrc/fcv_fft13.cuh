@@ -338,7 +338,10 @@ __device__ __forceinline__ void repack_pair(c2 yk, c2 yp, c2 w, c2 &zk, c2 &zp) 
 
 // Pass C^-1 of half H: global spectrum row -> registers (Hermitian repack) -> shared.
 // zc0 = the value of entry 0 (from the two real bins), used by thread 0 of half 0 only.
-template <int H>
+// CWAIT (stereo-pair kernel): the second cluster barrier of the previous block is waited for here, just
+// before the first write to shared memory, instead of at the end of that block.
+__device__ __forceinline__ void cluster_wait_divergent() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+template <int H, bool CWAIT = false>
 __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float2 *__restrict__ yrow, c2 zc0, int t) {
     const float2 *y = yrow + H * Q;
 #if F13_TWU_FACTORED
@@ -373,6 +376,7 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
         }
         Bfly<16>::template run<+1>(v1);
         Bfly<16>::template run<+1>(v2);
+        if (CWAIT) cluster_wait_divergent();
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             sm[out16(r)] = v1[r];
@@ -400,6 +404,7 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
     Bfly<16>::template run<+1>(v2);
     c2 *p1 = sm + (c & 15) * ROW + (c >> 4) * 16;
     c2 *p2 = sm + (cc & 15) * ROW + (cc >> 4) * 16;
+    if (CWAIT) cluster_wait_divergent();
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         p1[out16(r)] = v1[r];
@@ -447,6 +452,111 @@ __device__ __forceinline__ float inv_pass_a(const c2 *sm, const Tables &tb, floa
         }
     }
     return lmax;
+}
+
+
+// ---- stereo pair: the two output channels of a stream as a cluster of two CTAs -------------
+// A CTA owns ONE channel of an interleaved block, so on its own it can only store 2- or 4-byte
+// scalars, every 32-byte sector of the block being written four times (timing-only ablation,
+// profiles/r02_experiments.md: the inverse kernel without its PCM stores runs 20 % faster).
+// Here the two CTAs (cluster rank = channel) put their converted samples into their own shared
+// memory -- the transform buffers are free once pass A^-1 has them in registers -- and after a
+// cluster barrier each writes HALF of the block's frames with both channels, as 16-byte vectors,
+// reading the other channel through distributed shared memory.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t peer_smem(const void *p, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_cluster_u2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared::cluster.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t pcm_word(float v) {   // pcm_store's conversions, as a register value
+    if (FMT == PCM_F32) return __float_as_uint(v);
+    if (FMT == PCM_S16) return (uint32_t)__float2int_rn(v * 32767.0f) & 0xffffu;
+    return (uint32_t)__float2int_rn(v * 8388607.0f);
+}
+
+// Pass A^-1 + overlap-add + tail save + maximum as inv_pass_a, PCM through the pair exchange.
+// o = this CTA's channel = its rank in the cluster; the block has exactly two channels.
+// sm is read (transform result) and then reused as the exchange buffer; the caller must keep both
+// CTAs from writing sm again until the second cluster barrier (inside) has been passed.
+template <int FMT, class BETWEEN>
+__device__ __forceinline__ float inv_pass_a_pair(c2 *sm, const Tables &tb, float2 *__restrict__ tail, void *dout, int o,
+                                                 int frames, float &lmax_out, BETWEEN between) {
+    float &lmax = lmax_out;
+    lmax = 0.0f;
+    const int u = threadIdx.x;   // 256 threads: one column each
+    c2 va[16], vb[16];
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0++) {
+        va[k0] = sm[k0 * ROW + u];
+        vb[k0] = sm[HALF_ELEMS + k0 * ROW + u];
+    }
+    __syncthreads();   // the transform buffers are in registers everywhere: they become the exchange buffer
+#pragma unroll
+    for (int k0 = 1; k0 < 16; k0++) va[k0] = c2_cmulconj(va[k0], ldg_c2(tb.twA0 + (k0 - 1) * 256 + u));
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0++) vb[k0] = c2_cmulconj(vb[k0], ldg_c2(tb.twA1 + k0 * 256 + u));
+    Bfly<16>::template run<+1>(va);
+    Bfly<16>::template run<+1>(vb);
+    float2 tl[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) tl[r] = __ldcg(&tail[u + 256 * out16(r)]);  // L2 only: read once per block
+    uint32_t *x32 = reinterpret_cast<uint32_t *>(sm);   // 16-bit: one word per n (frames 2n, 2n+1 of this channel)
+    uint2 *x64 = reinterpret_cast<uint2 *>(sm);         // 32-bit formats: two words per n
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int n2 = out16(r), n = u + 256 * n2;
+        const c2 b = n2 == 0 ? vb[r] : c2_cmulconj(vb[r], c2_pack(w32(n2)));
+        const float2 s = c2_unpack(c2_add(va[r], b));
+        const float2 d = c2_unpack(c2_sub(va[r], b));
+        const float y0 = s.x + tl[r].x, y1 = s.y + tl[r].y;
+        tail[n] = d;
+        const int f0 = 2 * n;
+        if (FMT == PCM_S16) x32[n] = pcm_word<FMT>(y0) | (pcm_word<FMT>(y1) << 16);
+        else x64[n] = make_uint2(pcm_word<FMT>(y0), pcm_word<FMT>(y1));
+        if (f0 < frames) lmax = fmaxf(lmax, y0);
+        if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
+    }
+    cluster_arrive();
+    between();        // work that needs neither buffer (the block maximum)
+    cluster_wait();   // both channels' samples are in place
+    const uint32_t peer = peer_smem(sm, (uint32_t)(o ^ 1));
+    uint4 *out = reinterpret_cast<uint4 *>(dout);
+    if (FMT == PCM_S16) {
+        // 16 bytes = frames 2n .. 2n+3 = columns n, n+1 of both channels
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int n = o * (Q / 2) + i * 512 + 2 * u;
+            const uint2 own = *reinterpret_cast<const uint2 *>(x32 + n);
+            const uint2 oth = ld_cluster_u2(peer + n * 4);
+            const uint2 c0 = o == 0 ? own : oth, c1 = o == 0 ? oth : own;
+            uint4 v;
+            v.x = __byte_perm(c0.x, c1.x, 0x5410);
+            v.y = __byte_perm(c0.x, c1.x, 0x7632);
+            v.z = __byte_perm(c0.y, c1.y, 0x5410);
+            v.w = __byte_perm(c0.y, c1.y, 0x7632);
+            out[n / 2] = v;
+        }
+    } else {
+        // 16 bytes = frames 2n, 2n+1 = column n of both channels
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int n = o * (Q / 2) + i * 256 + u;
+            const uint2 own = x64[n];
+            const uint2 oth = ld_cluster_u2(peer + n * 8);
+            const uint2 c0 = o == 0 ? own : oth, c1 = o == 0 ? oth : own;
+            out[n] = make_uint4(c0.x, c1.x, c0.y, c1.y);
+        }
+    }
+    cluster_arrive();   // this CTA has read the other's exchange buffer; the matching wait comes before the
+    return lmax;        // next write to shared memory (inv_pass_c<.., true>) or before the CTA exits
 }
 
 }  // namespace f13

@@ -165,6 +165,62 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
 }
 
 // ---- tables ---------------------------------------------------------------------------------
+// The same for blocks of exactly two output channels: the two channels' CTAs form a cluster and
+// write the interleaved PCM together (f13::inv_pass_a_pair).  256 threads.
+template <class SEL, int FMT, bool PF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2)
+inv13_pair_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    constexpr int NT = 256;
+    __shared__ float red[NT / 32];
+    constexpr int N = f13::N, M = N;
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int o = blockIdx.x, b = blockIdx.y;   // gridDim.x == 2: o is the rank in the cluster
+    const StreamDev s = sel.stream(b);
+    const int fvb = sel.frames(b);
+    float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    float lmax = 0.0f;
+
+    for (int bt = 0; bt < T; bt++) {
+        int frames = fvb - bt * N;
+        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+        const float2 z0 = tid == 0 ? s.zc0[(size_t)o * T + bt] : make_float2(0.f, 0.f);
+        const float2 *yrow = s.Y + ((size_t)o * T + bt) * M;
+        if (PF && bt + 1 < T) {  // the next block's spectrum row (64 KB) is requested into L2 now
+#pragma unroll
+            for (int i = 0; i < (M * 8 / 128) / NT; i++)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + M + (size_t)(tid + i * NT) * 16));
+        }
+        if (bt == 0) {
+            if (tid < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), tid);
+            else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, tid - 128);
+        } else {   // waits for the pair's second barrier of the previous block before writing shared memory
+            if (tid < 128) f13::inv_pass_c<0, true>(sm, tb, yrow, c2_pack(z0.x, z0.y), tid);
+            else f13::inv_pass_c<1, true>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, tid - 128);
+        }
+        __syncthreads();
+        f13::pass_b<+1, 2, NT>(sm, tb);
+        __syncthreads();
+        void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * 2 * wire;
+        float m;
+        f13::inv_pass_a_pair<FMT>(sm, tb, tail, dout, o, frames, m, [&]() { block_max_update13(s.bmax + bt, m); });
+        lmax = fmaxf(lmax, m);
+    }
+    f13::cluster_wait_divergent();   // the other CTA is done with this CTA's shared memory
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+    if ((tid & 31) == 0) red[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; w++) lmax = fmaxf(lmax, red[w]);
+        if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
+    }
+}
+
 template <class SEL, int FMT>
 static int set_attrs13() {
     const int one = (int)f13::HALF_BYTES, two = 2 * (int)f13::HALF_BYTES;
@@ -174,6 +230,10 @@ static int set_attrs13() {
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    if constexpr (!SEL::kSingle) {
+        CU_TRY(cudaFuncSetAttribute(inv13_pair_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+        CU_TRY(cudaFuncSetAttribute(inv13_pair_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    }
     return 0;
 }
 
@@ -271,11 +331,24 @@ void fcv::launch_fwd13(const StepArgs &a, cudaStream_t q) {
     else launch_fwd13_sel<BatchSel>(a, a.bsel, q);
 }
 
+static std::atomic<bool> g_inv_pair{getenv("FCV_INV_PAIR") && atoi(getenv("FCV_INV_PAIR")) != 0};
+extern "C" void fcv_debug_set_inv_pair(int on) { g_inv_pair.store(on != 0); }
+
 template <class SEL, int FMT>
 static void launch_inv13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) {
     const dim3 grid(a.f->nout, a.cnt);
     const size_t smem = 2 * f13::HALF_BYTES;
     static const bool pf = !(getenv("FCV_INV_PF") && atoi(getenv("FCV_INV_PF")) == 0);
+    // Stereo blocks of a batch, experiment (OFF: measured 4 % slower, profiles/r02_experiments.md): the two
+    // channels' CTAs as a cluster that writes whole interleaved frames.  FCV_INV_PAIR=1 / fcv_debug_set_inv_pair(1).
+    const bool pair = g_inv_pair.load(std::memory_order_relaxed);
+    if (pair && !SEL::kSingle && a.f->nout == 2 && F13_INV_NT == 256) {
+        if constexpr (!SEL::kSingle) {
+            if (pf && a.T > 1) inv13_pair_kernel<SEL, FMT, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.T);
+            else inv13_pair_kernel<SEL, FMT, false><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.T);
+        }
+        return;
+    }
     if (pf && a.T > 1) inv13_stream_kernel<SEL, FMT, true><<<grid, F13_INV_NT, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
     else launch_k(inv13_stream_kernel<SEL, FMT, false>, grid, dim3(F13_INV_NT), smem, q, a.pdl, sel, a.f->tb13, a.f->nout, a.T);
 }

@@ -292,6 +292,45 @@ def test_time_tiled_batch_equals_block_by_block(T):
     f.close()
 
 
+@pytest.mark.parametrize("fmt", ["f32", "s16", "s24"])
+def test_stereo_pair_inverse_kernel_is_bit_identical(fmt):
+    """The inverse transform of a stereo batch with the two channels' CTAs as a cluster that writes whole
+    interleaved frames (fcv_debug_set_inv_pair; an experiment that stays off) gives the same bits as the
+    default kernel: block contents, running maximum, per-block maxima; T = 1 and T = 8, short steps."""
+    r = _rng(77)
+    spec = FilterSpec(2, 2, 40000)
+    spec.add(0, 0, r.standard_normal(40000) * 0.004, 100).add(1, 1, r.standard_normal(30000) * 0.004, 0)
+    spec.add(1, 0, r.standard_normal(5000) * 0.004, 9000)
+    f = _engine(spec)
+    N, B = spec.fragm, 7
+    pcm = {"f32": capi.PCM_F32, "s16": capi.PCM_S16, "s24": capi.PCM_S24}[fmt]
+    L = capi.lib()
+    for T in (1, 8):
+        x = r.uniform(-0.3, 0.3, (3, B, T * N, 2))
+        xin = (x.astype(np.float32) if fmt == "f32" else
+               np.rint(x * (20000 if fmt == "s16" else 5000000)).astype(np.int16 if fmt == "s16" else np.int32))
+        fv = np.array([T * N, 1, N - 1, N, T * N - 3, 0, 5000][:B], np.int32)
+        outs = []
+        for pair in (0, 1):
+            L.fcv_debug_set_inv_pair(pair)
+            try:
+                bt = capi.Batch(f, B, pcm, pcm, blocks_per_step=T)
+                got = []
+                for k in range(3):
+                    bt.host_in[:] = xin[k]
+                    bt.process(fv if k == 2 else None)
+                    got.append(bt.host_out.copy())
+                got.append(bt.get_max().copy())
+                got.append(bt.get_block_max().copy())
+                bt.close()
+                outs.append(got)
+            finally:
+                L.fcv_debug_set_inv_pair(0)
+        for a, c in zip(*outs):
+            assert np.array_equal(a, c)
+    f.close()
+
+
 @pytest.mark.parametrize("nin,nout,T,size", [(1, 1, 4, 30000), (3, 2, 4, 30000), (1, 2, 8, 30000), (6, 6, 2, 30000),
                                              (3, 2, 8, 30000), (6, 6, 8, 30000), (2, 2, 8, 110000), (2, 3, 4, 110000)])
 def test_time_tiled_other_channel_counts_and_s24(nin, nout, T, size):
