@@ -199,6 +199,13 @@ def fft_calibration(n=16384, reps=300):
     return res
 
 
+def real_libraries():
+    """the real libzita-convolver / libfftw3f are looked for at run time.  They are in neither
+    this image nor the GPU box's; the record says what was found, so that the arm cannot be mistaken for them."""
+    import ctypes.util
+    return {n: ctypes.util.find_library(n) for n in ("zita-convolver", "fftw3f", "sndfile")}
+
+
 def cpu_baseline(wl, filter_dir, target_s=12.0):
     cores = len(os.sched_getaffinity(0))
     kind, run, what = cpu_arm(wl, filter_dir)
@@ -221,6 +228,7 @@ def cpu_baseline(wl, filter_dir, target_s=12.0):
         "sample": f"{cores} files x {nb} blocks of {wl.fragm} frames ({wl.name}), one SoundProcessor/Convproc per "
                   f"file, one file per thread, {wall:.1f} s wall; {what}",
         "fft_calibration_one_core": cal,
+        "real_libraries_found": real_libraries(),
     }
 
 
