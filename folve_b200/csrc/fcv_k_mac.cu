@@ -45,8 +45,29 @@ static void launch_mac1(const StepArgs &a, const SEL &sel, cudaStream_t q) {
 #undef FCV_MAC1_ARGS
 }
 
+// The launch groups of the per-file path: one CTA per (tile, output, stream) -- mac_group_kernel.
+template <class SEL>
+static void launch_mac_group(const StepArgs &a, const SEL &sel, cudaStream_t q) {
+    const fcv_filter *f = a.f;
+    const int M4 = f->fragm / 2;
+    const int TPB = M4 >= 128 ? 128 : M4;
+    dim3 grid(M4 / TPB + 1, f->nout, a.cnt);
+    const float4 *H = reinterpret_cast<const float4 *>(f->dH);
+#define FCV_MACG_ARGS sel, H, M4, a.R, f->dpairs, f->dpair_off, f->dtt_rows, f->ring
+    if (TPB == 128) launch_k(mac_group_kernel<SEL, 128>, grid, dim3(128), 0, q, a.pdl, FCV_MACG_ARGS);
+    else if (TPB == 64) launch_k(mac_group_kernel<SEL, 64>, grid, dim3(64), 0, q, a.pdl, FCV_MACG_ARGS);
+    else launch_k(mac_group_kernel<SEL, 32>, grid, dim3(32), 0, q, a.pdl, FCV_MACG_ARGS);
+#undef FCV_MACG_ARGS
+}
+
 template <class SEL>
 static void launch_mac_t1_sel(const StepArgs &a, const SEL &sel, cudaStream_t q) {
+    // FCV_MAC_GROUP=0: the step-table kernel for launch groups too (A/B)
+    static const bool group_kernel = !(getenv("FCV_MAC_GROUP") && atoi(getenv("FCV_MAC_GROUP")) == 0);
+    if (SEL::kSingle && group_kernel && a.cnt <= 65535) {
+        launch_mac_group<SEL>(a, sel, q);
+        return;
+    }
     const int S = a.cnt >= 4 ? 4 : (a.cnt >= 2 ? 2 : 1);
     switch (a.f->group_no) {
         case 1: if (S == 4) launch_mac1<SEL, 1, 4>(a, sel, q); else if (S == 2) launch_mac1<SEL, 1, 2>(a, sel, q); else launch_mac1<SEL, 1, 1>(a, sel, q); break;

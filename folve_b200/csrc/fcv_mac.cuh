@@ -209,6 +209,63 @@ mac_kernel(const __grid_constant__ SEL sel, int nstreams, const MacStep *__restr
     }
 }
 
+// ---- the launch groups of the per-file path ------------------------------------------------
+// One CTA per (spectrum tile, OUTPUT, stream): a thread walks only the partitions of the inputs that
+// feed its output -- X row, filter row, 4 FFMA2 per step, addresses by increments -- instead of the
+// step table shared by the outputs of a group.  A lone stream is bound by the length of one warp's
+// instruction stream (one warp per scheduler: ~10 cycles per instruction; mac_kernel<.., 2, 1, 128>
+// executes 3000 instructions per warp for SantaLucia, 15 us): here it is ~600, on twice as many SMs.
+// Per output the additions happen in the order of mac_kernel's step table (inputs ascending,
+// partitions ascending, absent rows skipped), so the results are bit-identical.
+// grid: x = M/2/TPB tiles + 1 DC/Nyquist column, y = outputs, z = streams of the launch.
+template <class SEL, int TPB>
+__global__ void __launch_bounds__(TPB)
+mac_group_kernel(const __grid_constant__ SEL sel, const float4 *__restrict__ H, int M4, int R, const TTPair *__restrict__ pairs,
+                 const int *__restrict__ pair_off, const int *__restrict__ tt_rows, int Pfilt) {
+    pdl_trigger();
+    pdl_wait();
+    const int o = blockIdx.y, b = blockIdx.z;
+    const StreamDev sd = sel.stream(b);
+    const int pt = sel.slot(b);
+    if (blockIdx.x == gridDim.x - 1) {   // DC / Nyquist products of this (stream, output)
+        if (threadIdx.x < 32) {
+            const float2 z = dcny_warp(sd.xring, pairs, pair_off, tt_rows, reinterpret_cast<const float2 *>(H), o, Pfilt, R,
+                                       pt, 2 * M4, threadIdx.x);
+            if (threadIdx.x == 0) sd.zc0[o] = z;
+        }
+        return;
+    }
+    const int e4 = blockIdx.x * TPB + threadIdx.x;
+    const float4 *hb = H + e4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 12;   // rows in flight together: SantaLucia's 22 partitions in two round trips
+    const int p1 = pair_off[o + 1];
+    for (int p = pair_off[o]; p < p1; p++) {
+        const int *rows = tt_rows + __ldg(&pairs[p].rowbase);
+        const float4 *xin = reinterpret_cast<const float4 *>(sd.xring) + (size_t)__ldg(&pairs[p].inp) * R * (size_t)M4 + e4;
+#pragma unroll 1
+        for (int j0 = 0; j0 < Pfilt; j0 += U) {
+            int row[U];
+            float4 x[U], h[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) row[u] = j0 + u < Pfilt ? __ldg(rows + j0 + u) : -1;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                int slot = pt - (j0 + u);
+                if (slot < 0) slot += R;
+                if (row[u] >= 0) {
+                    x[u] = ld_stream(xin + (size_t)slot * (size_t)M4);
+                    h[u] = ld_keep(hb + (size_t)row[u] * (size_t)M4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (row[u] >= 0) cmac2(acc, x[u], h[u]);
+        }
+    }
+    __stcs(reinterpret_cast<float4 *>(sd.Y) + (size_t)o * (size_t)M4 + e4, acc);
+}
+
 // ---- time-tiled variant ------------------------------------------------------------
 // When T consecutive blocks of a stream are available at once (prebuffered files),
 // output block t0+t needs ring slots t0+t-j, j < P: the T outputs share all but

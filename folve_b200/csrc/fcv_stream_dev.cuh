@@ -88,13 +88,16 @@ __device__ __forceinline__ void host_copy_out(const StreamDev &s, int nctas, siz
     for (size_t i = tid; i < n16; i += nt) dst[i] = __ldcg(src + i);
     for (size_t i = n16 * 16 + tid; i < out_bytes; i += nt)
         reinterpret_cast<unsigned char *>(s.hout)[i] = __ldcg(reinterpret_cast<const unsigned char *>(s.dout) + i);
-    __threadfence_system();   // every thread's part of the block before ...
+    // One system-scope fence, by the thread that publishes the word, behind the CTA barrier: fences are
+    // cumulative, so every thread's part of the block (ordered before the barrier) is visible to the host
+    // before the word is -- the barrier / fence / flag idiom of NCCL's primitives.  A second fence by all
+    // 256 threads in front of the barrier cost 2-4 us per block (tools/hostlink_probe.cu).
     __syncthreads();
     if (tid == 0) {
         *s.hmax = __ldcg(s.maxv);
         *s.arrive = 0u;    // ready for the stream's next block (the caller submits it only after this one)
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned *>(s.hdone) = seq;   // ... the word the caller is waiting for
+        *reinterpret_cast<volatile unsigned *>(s.hdone) = seq;   // the word the caller is waiting for
     }
 }
 
