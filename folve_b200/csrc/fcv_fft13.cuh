@@ -486,9 +486,11 @@ __device__ __forceinline__ uint32_t pcm_word(float v) {   // pcm_store's convers
 // o = this CTA's channel = its rank in the cluster; the block has exactly two channels.
 // sm is read (transform result) and then reused as the exchange buffer; the caller must keep both
 // CTAs from writing sm again until the second cluster barrier (inside) has been passed.
+// hout (or null): the caller's pinned block (per-file path); it receives the same vectors as dout, but only the
+// first `frames` frames (the reference writes back only the frames it read, sound-processor.cc:116-125).
 template <int FMT, class BETWEEN>
-__device__ __forceinline__ float inv_pass_a_pair(c2 *sm, const Tables &tb, float2 *__restrict__ tail, void *dout, int o,
-                                                 int frames, float &lmax_out, BETWEEN between) {
+__device__ __forceinline__ float inv_pass_a_pair(c2 *sm, const Tables &tb, float2 *__restrict__ tail, void *dout, void *hout,
+                                                 int o, int frames, float &lmax_out, BETWEEN between) {
     float &lmax = lmax_out;
     lmax = 0.0f;
     const int u = threadIdx.x;   // 256 threads: one column each
@@ -543,6 +545,16 @@ __device__ __forceinline__ float inv_pass_a_pair(c2 *sm, const Tables &tb, float
             v.z = __byte_perm(c0.y, c1.y, 0x5410);
             v.w = __byte_perm(c0.y, c1.y, 0x7632);
             out[n / 2] = v;
+            if (hout) {   // frames 2n .. 2n+3
+                const int f0 = 2 * n;
+                if (f0 + 4 <= frames) reinterpret_cast<uint4 *>(hout)[n / 2] = v;
+                else {
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (f0 + k < frames) reinterpret_cast<uint32_t *>(hout)[f0 + k] = w[k];
+                }
+            }
         }
     } else {
         // 16 bytes = frames 2n, 2n+1 = column n of both channels
@@ -552,7 +564,13 @@ __device__ __forceinline__ float inv_pass_a_pair(c2 *sm, const Tables &tb, float
             const uint2 own = x64[n];
             const uint2 oth = ld_cluster_u2(peer + n * 8);
             const uint2 c0 = o == 0 ? own : oth, c1 = o == 0 ? oth : own;
-            out[n] = make_uint4(c0.x, c1.x, c0.y, c1.y);
+            const uint4 v = make_uint4(c0.x, c1.x, c0.y, c1.y);
+            out[n] = v;
+            if (hout) {   // frames 2n, 2n+1
+                const int f0 = 2 * n;
+                if (f0 + 2 <= frames) reinterpret_cast<uint4 *>(hout)[n] = v;
+                else if (f0 < frames) reinterpret_cast<uint2 *>(hout)[f0] = make_uint2(v.x, v.y);
+            }
         }
     }
     cluster_arrive();   // this CTA has read the other's exchange buffer; the matching wait comes before the

@@ -207,10 +207,10 @@ inv13_pair_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int T) {
         __syncthreads();
         void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * 2 * wire;
         float m;
-        f13::inv_pass_a_pair<FMT>(sm, tb, tail, dout, o, frames, m, [&]() { block_max_update13(s.bmax + bt, m); });
+        void *hout = SEL::kSingle ? s.hout : nullptr;   // per-file path: the vectors go to the caller's block as well
+        f13::inv_pass_a_pair<FMT>(sm, tb, tail, dout, hout, o, frames, m, [&]() { block_max_update13(s.bmax + bt, m); });
         lmax = fmaxf(lmax, m);
     }
-    f13::cluster_wait_divergent();   // the other CTA is done with this CTA's shared memory
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
     if ((tid & 31) == 0) red[tid >> 5] = lmax;
@@ -218,6 +218,19 @@ inv13_pair_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int T) {
     if (tid == 0) {
         for (int w = 1; w < NT / 32; w++) lmax = fmaxf(lmax, red[w]);
         if (lmax > 0.0f) atomicMax(reinterpret_cast<int *>(s.maxv), __float_as_int(lmax));
+    }
+    // The pair's last barrier: the other CTA is done with this CTA's shared memory -- and, on the per-file
+    // path, both CTAs' stores to the caller's block and both maxima are ordered before what follows.
+    f13::cluster_wait_divergent();
+    if (SEL::kSingle && s.hout) {
+        // one more rendezvous behind the maximum's atomics (the wait above belongs to the arrive inside the epilogue)
+        f13::cluster_arrive();
+        f13::cluster_wait();
+        if (o == 0 && tid == 0) {
+            *s.hmax = __ldcg(s.maxv);
+            __threadfence_system();   // cumulative: every store of both CTAs before the word (see host_copy_out)
+            *reinterpret_cast<volatile unsigned *>(s.hdone) = sel.seq(b);
+        }
     }
 }
 
@@ -230,7 +243,7 @@ static int set_attrs13() {
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
-    if constexpr (!SEL::kSingle) {
+    {
         CU_TRY(cudaFuncSetAttribute(inv13_pair_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
         CU_TRY(cudaFuncSetAttribute(inv13_pair_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     }
@@ -332,21 +345,27 @@ void fcv::launch_fwd13(const StepArgs &a, cudaStream_t q) {
 }
 
 static std::atomic<bool> g_inv_pair{getenv("FCV_INV_PAIR") && atoi(getenv("FCV_INV_PAIR")) != 0};
-extern "C" void fcv_debug_set_inv_pair(int on) { g_inv_pair.store(on != 0); }
+static std::atomic<bool> g_inv_pair_single{getenv("FCV_INV_PAIR_SINGLE") && atoi(getenv("FCV_INV_PAIR_SINGLE")) != 0};
+extern "C" void fcv_debug_set_inv_pair(int mask) {   // bit 0: batches, bit 1: the per-file path
+    g_inv_pair.store((mask & 1) != 0);
+    g_inv_pair_single.store((mask & 2) != 0);
+}
 
 template <class SEL, int FMT>
 static void launch_inv13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) {
     const dim3 grid(a.f->nout, a.cnt);
     const size_t smem = 2 * f13::HALF_BYTES;
     static const bool pf = !(getenv("FCV_INV_PF") && atoi(getenv("FCV_INV_PF")) == 0);
-    // Stereo blocks of a batch, experiment (OFF: measured 4 % slower, profiles/r02_experiments.md): the two
-    // channels' CTAs as a cluster that writes whole interleaved frames.  FCV_INV_PAIR=1 / fcv_debug_set_inv_pair(1).
-    const bool pair = g_inv_pair.load(std::memory_order_relaxed);
-    if (pair && !SEL::kSingle && a.f->nout == 2 && F13_INV_NT == 256) {
-        if constexpr (!SEL::kSingle) {
-            if (pf && a.T > 1) inv13_pair_kernel<SEL, FMT, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.T);
-            else inv13_pair_kernel<SEL, FMT, false><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.T);
-        }
+    // Stereo blocks: the two channels' CTAs as a cluster that writes whole interleaved frames.
+    // An experiment that stays OFF on both paths (profiles/r02_experiments.md):
+    //   batches (FCV_INV_PAIR=1 / fcv_debug_set_inv_pair(1)): 4 % slower;
+    //   per-file path (FCV_INV_PAIR_SINGLE=1 / fcv_debug_set_inv_pair(2)): the frames go straight to the caller's
+    //     pinned block from both CTAs, no second pass by the last CTA: 14.6 -> 14.0 us for a lone block, but
+    //     16 / 32 concurrent callers lose 5-10 % (clusters of concurrent groups are harder to place).
+    const bool pair = (SEL::kSingle ? g_inv_pair_single : g_inv_pair).load(std::memory_order_relaxed);
+    if (pair && a.f->nout == 2 && F13_INV_NT == 256) {
+        if (pf && a.T > 1) inv13_pair_kernel<SEL, FMT, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.T);
+        else launch_k(inv13_pair_kernel<SEL, FMT, false>, grid, dim3(256), smem, q, a.pdl, sel, a.f->tb13, a.T);
         return;
     }
     if (pf && a.T > 1) inv13_stream_kernel<SEL, FMT, true><<<grid, F13_INV_NT, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);

@@ -298,11 +298,13 @@ int fcv_stream_get_input_spectrum(fcv_stream *s, int inp, int age, float *dst);
  * cooperative launches that really happened. */
 void fcv_debug_set_fused(int on);
 unsigned long long fcv_debug_fused_launches(void);
-/* Process-wide switch of the batch path's inverse transform for stereo blocks of fragm 8192: one CTA
- * per output channel storing its samples on its own (default), or the two channels' CTAs as a thread
- * block cluster that exchanges the converted samples through distributed shared memory and writes
- * whole interleaved frames (also FCV_INV_PAIR=1).  Results are identical, the pair is slower. */
-void fcv_debug_set_inv_pair(int on);
+/* Process-wide switch of the inverse transform for stereo blocks of fragm 8192: one CTA per output
+ * channel storing its samples on its own (default), or the two channels' CTAs as a thread block cluster
+ * that exchanges the converted samples through distributed shared memory and writes whole interleaved
+ * frames.  mask bit 0: batches (also FCV_INV_PAIR=1), bit 1: the per-file path, where the frames then
+ * go straight to the caller's pinned block (also FCV_INV_PAIR_SINGLE=1).  Results are identical; the
+ * pair is not faster on either path. */
+void fcv_debug_set_inv_pair(int mask);
 
 #ifdef __cplusplus
 }

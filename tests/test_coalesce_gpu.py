@@ -149,7 +149,8 @@ def test_short_block_leaves_the_rest_of_the_buffer_zero():
 def test_one_launch_group_equals_three_launches(fmt):
     """a group of single-stream blocks as ONE cooperative launch (fcv_k_fused13.cu) gives bit for bit
     what the forward / MAC / inverse launches give: lone streams, short last blocks, silence,
-    many streams per group, every wire format"""
+    many streams per group, every wire format -- and so does the inverse transform as a cluster pair that
+    writes the frames straight into the callers' pinned blocks (fcv_debug_set_inv_pair(2))"""
     spec = _spec(7)
     f = _engine(spec)
     N = spec.fragm
@@ -184,13 +185,23 @@ def test_one_launch_group_equals_three_launches(fmt):
         finally:
             L.fcv_debug_set_fused(0)
 
+    def run_pair():
+        # the inverse transform as a cluster pair writing the frames straight into the callers' blocks
+        L.fcv_debug_set_inv_pair(2)
+        try:
+            return run(False)
+        finally:
+            L.fcv_debug_set_inv_pair(0)
+
+    yp, mp = run_pair()
     c0 = L.fcv_debug_fused_launches()
     y3, m3 = run(False)
     c1 = L.fcv_debug_fused_launches()
     y1, m1 = run(True)
     c2 = L.fcv_debug_fused_launches()
     assert c1 == c0 and c2 - c1 >= 5           # the cooperative kernel really ran in the second pass only
-    for a, b in zip(y3, y1):
+    for a, b, c in zip(y3, y1, yp):
         assert a.shape == b.shape and np.array_equal(a, b)
-    assert m3 == m1
+        assert a.shape == c.shape and np.array_equal(a, c)
+    assert m3 == m1 and m3 == mp
     f.close()
