@@ -1013,8 +1013,10 @@ struct FcvCombiner {
     std::condition_variable cv;
     std::vector<fcv_stream *> pending;      // guarded by mu
     std::atomic<int> npending{0};
-    bool sleeping = false, quit = false, started = false;   // guarded by mu
-    std::thread th;
+    bool quit = false, started = false;     // guarded by mu
+    int sleeping = 0;                       // dispatcher threads waiting on cv (guarded by mu)
+    std::vector<std::thread> ths;           // FCV_DISPATCHERS of them (default 1)
+    int nthreads = 1;
     static const int NQ = 8;
     cudaStream_t q[NQ] = {};
     int next_q = 0;
@@ -1065,6 +1067,8 @@ static FcvCombiner *combiner_create(fcv_filter *f) {
     c->f = f;
     // FCV_COMBINE_MAX: streams per group (default and maximum 32; 1 = one launch group per block)
     if (const char *v = getenv("FCV_COMBINE_MAX")) c->group_max = atoi(v) > 0 && atoi(v) <= GROUP_MAX ? atoi(v) : GROUP_MAX;
+    // FCV_DISPATCHERS: launching threads per (filter, device); whichever is free takes what has queued up meanwhile
+    if (const char *v = getenv("FCV_DISPATCHERS")) c->nthreads = atoi(v) >= 1 && atoi(v) <= 8 ? atoi(v) : 1;
     {
         cpu_set_t set;
         CPU_ZERO(&set);
@@ -1087,7 +1091,8 @@ static void combiner_destroy(FcvCombiner *c) {
         c->quit = true;
         c->cv.notify_all();
     }
-    if (c->th.joinable()) c->th.join();
+    for (std::thread &t : c->ths)
+        if (t.joinable()) t.join();
     if (c->trace) {
         combiner_report(c);
         std::lock_guard<std::mutex> l(g_trace_mu);
@@ -1197,18 +1202,25 @@ static void dispatcher_main(FcvCombiner *c) {
             std::unique_lock<std::mutex> lk(c->mu);
             if (c->quit && c->pending.empty()) return;
             if (c->pending.empty()) {
-                c->sleeping = true;
+                c->sleeping++;
                 c->cv.wait(lk, [c] { return c->quit || !c->pending.empty(); });
-                c->sleeping = false;
+                c->sleeping--;
                 if (c->quit && c->pending.empty()) return;
             }
         }
         idle_polls = 0;
         {
             std::unique_lock<std::mutex> lk(c->mu);
-            take.swap(c->pending);
-            c->npending.store(0, std::memory_order_release);
+            if (c->nthreads == 1 || (int)c->pending.size() <= c->group_max) {
+                take.swap(c->pending);
+                c->npending.store(0, std::memory_order_release);
+            } else {   // several dispatchers: one group's worth, the rest is for the others
+                take.assign(c->pending.begin(), c->pending.begin() + c->group_max);
+                c->pending.erase(c->pending.begin(), c->pending.begin() + c->group_max);
+                c->npending.store((int)c->pending.size(), std::memory_order_release);
+            }
         }
+        if (take.empty()) continue;
         const double t_take = c->trace ? now_us() : 0;
         // everything queued, oldest first, in groups of equal wire formats
         while (!take.empty()) {
@@ -1222,8 +1234,15 @@ static void dispatcher_main(FcvCombiner *c) {
                     ++it;
                 }
             }
-            if (!c->q[c->next_q] &&
-                cudaStreamCreateWithFlags(&c->q[c->next_q], cudaStreamNonBlocking) != cudaSuccess) {
+            cudaStream_t q = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(c->mu);
+                if (!c->q[c->next_q]) cudaStreamCreateWithFlags(&c->q[c->next_q], cudaStreamNonBlocking);
+                q = c->q[c->next_q];
+                if (q) c->next_q = (c->next_q + 1) % FcvCombiner::NQ;
+            }
+            if (!q) {
+                cudaGetLastError();
                 for (fcv_stream *s : group) {
                     s->rc = FCV_E_CUDA;
                     s->err = "cannot create a CUDA stream for the launch group";
@@ -1231,8 +1250,6 @@ static void dispatcher_main(FcvCombiner *c) {
                 }
                 continue;
             }
-            cudaStream_t q = c->q[c->next_q];
-            c->next_q = (c->next_q + 1) % FcvCombiner::NQ;
             // Everything that touches the streams happens BEFORE the launch: once the kernels are
             // enqueued a block may complete and its caller return, resubmit or destroy the stream while
             // this thread is still on its way out of the launch call.
@@ -1325,17 +1342,19 @@ extern "C" int fcv_stream_submit(fcv_stream *s, int frames_valid) {
         if (!c->started) {
             c->started = true;
             try {
-                c->th = std::thread(dispatcher_main, c);
+                for (int i = 0; i < c->nthreads; i++) c->ths.emplace_back(dispatcher_main, c);
             } catch (...) {
+                if (!c->ths.empty()) goto started_some;   // fewer dispatchers than asked for will do
                 c->started = false;
                 s->state.store(fcv_stream::IDLE, std::memory_order_release);
                 c->active.fetch_sub(1, std::memory_order_relaxed);
                 return fail(FCV_E_ALLOC, "cannot start the dispatcher thread");
             }
+        started_some:;
         }
         c->pending.push_back(s);
         c->npending.fetch_add(1, std::memory_order_release);
-        if (c->sleeping) c->cv.notify_one();
+        if (c->sleeping > 0) c->cv.notify_one();
     }
     return 0;
 }
