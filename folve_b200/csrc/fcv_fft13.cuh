@@ -98,6 +98,24 @@ __device__ __forceinline__ c2 ldg_stream_c2(const float2 *p) {
     return v;
 }
 
+// Two stereo frames in wire format (frames 2n, 2n+1: 16 bytes as float32 / int24-in-int32, 8 bytes as int16, in
+// r.x, r.y) -> the pairs (x[2n], x[2n+1]) of the left and of the right channel, libsndfile's scaling.
+template <int FMT>
+__device__ __forceinline__ void raw_to_pairs(uint4 r, float2 &left, float2 &right) {
+    if (FMT == PCM_F32) {
+        left = make_float2(__uint_as_float(r.x), __uint_as_float(r.z));
+        right = make_float2(__uint_as_float(r.y), __uint_as_float(r.w));
+    } else if (FMT == PCM_S16) {
+        constexpr float K = 1.0f / 32768.0f;
+        left = make_float2((short)(r.x & 0xffffu) * K, (short)(r.y & 0xffffu) * K);
+        right = make_float2((short)(r.x >> 16) * K, (short)(r.y >> 16) * K);
+    } else {
+        constexpr float K = 1.0f / 8388608.0f;
+        left = make_float2((int)r.x * K, (int)r.z * K);
+        right = make_float2((int)r.y * K, (int)r.w * K);
+    }
+}
+
 // z[n] = (x[2n], x[2n+1]) of C consecutive channels starting at ch0, frames >= fv read as 0.
 // NCH = 2: stereo block and both channels wanted (one vector load); NCH = 1: mono block;
 // NCH = 0: any layout, scalar loads.
@@ -107,18 +125,13 @@ __device__ __forceinline__ void load_z(const void *in, int nchan, int ch0, int n
     if (NCH == 2 && C == 2) {
         if (FMT == PCM_F32) {
             const float4 t = __ldcs(reinterpret_cast<const float4 *>(in) + n);
-            v[0] = make_float2(t.x, t.z);
-            v[1] = make_float2(t.y, t.w);
+            raw_to_pairs<FMT>(make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w)), v[0], v[1]);
         } else if (FMT == PCM_S16) {
-            constexpr float K = 1.0f / 32768.0f;
-            const short4 t = __ldcs(reinterpret_cast<const short4 *>(in) + n);
-            v[0] = make_float2(t.x * K, t.z * K);
-            v[1] = make_float2(t.y * K, t.w * K);
+            const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(in) + n);
+            raw_to_pairs<FMT>(make_uint4(t.x, t.y, 0u, 0u), v[0], v[1]);
         } else {
-            constexpr float K = 1.0f / 8388608.0f;
             const int4 t = __ldcs(reinterpret_cast<const int4 *>(in) + n);
-            v[0] = make_float2(t.x * K, t.z * K);
-            v[1] = make_float2(t.y * K, t.w * K);
+            raw_to_pairs<FMT>(make_uint4((uint32_t)t.x, (uint32_t)t.y, (uint32_t)t.z, (uint32_t)t.w), v[0], v[1]);
         }
     } else {
 #pragma unroll
@@ -575,6 +588,109 @@ __device__ __forceinline__ float inv_pass_a_pair(c2 *sm, const Tables &tb, float
     }
     cluster_arrive();   // this CTA has read the other's exchange buffer; the matching wait comes before the
     return lmax;        // next write to shared memory (inv_pass_c<.., true>) or before the CTA exits
+}
+
+
+// ---- forward pair: the two halves' CTAs of a stereo block share ONE read of the PCM -----------
+// Each of the two CTAs (half 0 / half 1 of the spectrum) needs every frame of the block.  On the per-file
+// path the block lies in the caller's pinned host memory: read by both CTAs it crosses the link twice.
+// As a cluster, CTA r copies only frames [r N/2, (r+1) N/2) into its shared memory (wire format, as they
+// are), and pass A takes the first half of its inputs from CTA 0's copy and the second from CTA 1's
+// (ld.shared::cluster).  The arithmetic is that of fwd_pass_a: bit-identical spectra.
+template <int FMT>
+struct StageVec {   // two stereo frames in wire format
+    static constexpr int BYTES = FMT == PCM_S16 ? 8 : 16;
+};
+constexpr size_t STAGE_BYTES_MAX = (size_t)(N / 2) * 16;   // the whole block as float32 / int32 frames
+
+__device__ __forceinline__ uint4 ld_cluster_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+// CTA `rank` copies its half of the block (frames < fv only) from `in` to its staging buffer.
+template <int FMT>
+__device__ __forceinline__ void stage_half(unsigned char *stage, const void *in, int rank, int fv) {
+    constexpr int VB = StageVec<FMT>::BYTES;
+    const int n0 = rank * (Q / 2);
+#pragma unroll
+    for (int i = 0; i < (Q / 2) / 256; i++) {
+        const int n = n0 + i * 256 + threadIdx.x;
+        if (VB == 16) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (2 * n < fv) t = __ldcs(reinterpret_cast<const uint4 *>(in) + n);
+            reinterpret_cast<uint4 *>(stage)[n] = t;
+        } else {
+            uint2 t = make_uint2(0u, 0u);
+            if (2 * n < fv) t = __ldcs(reinterpret_cast<const uint2 *>(in) + n);
+            reinterpret_cast<uint2 *>(stage)[n] = t;
+        }
+    }
+}
+
+// fwd_pass_a for a stereo block (both channels, 256 threads) with the inputs taken from the pair's staging buffers.
+template <int H, int FMT>
+__device__ __forceinline__ void fwd_pass_a_staged(c2 *sm, const Tables &tb, uint32_t stage0, uint32_t stage1, int fv) {
+    constexpr int VB = StageVec<FMT>::BYTES;
+    const int u = threadIdx.x;
+    c2 v[2][16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int n = u + 256 * j;
+        const uint32_t a = (j < 8 ? stage0 : stage1) + (uint32_t)n * VB;
+        uint4 r;
+        if (VB == 16) r = ld_cluster_u4(a);
+        else {
+            const uint2 t = ld_cluster_u2(a);
+            r = make_uint4(t.x, t.y, 0u, 0u);
+        }
+        float2 p[2];
+        raw_to_pairs<FMT>(r, p[0], p[1]);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (2 * n >= fv) p[c].x = 0.0f;
+            if (2 * n + 1 >= fv) p[c].y = 0.0f;
+            v[c][j] = c2_pack(p[c].x, p[c].y);
+        }
+    }
+    c2 w[16];
+    if (H == 0) {
+#pragma unroll
+        for (int k0 = 1; k0 < 16; k0++) w[k0] = ldg_c2(tb.twA0 + (k0 - 1) * 256 + u);
+    } else {
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++) w[k0] = ldg_c2(tb.twA1 + k0 * 256 + u);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (H == 1) {
+#pragma unroll
+            for (int j = 1; j < 16; j++) v[c][j] = c2_cmul(v[c][j], c2_pack(w32(j)));
+        }
+        Bfly<16>::template run<-1>(v[c]);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int k0 = out16(r);
+            c2 x = v[c][r];
+            if (H == 1 || k0 > 0) x = c2_cmul(x, w[k0]);
+            sm[c * HALF_ELEMS + k0 * ROW + u] = x;
+        }
+    }
+}
+
+// One half of both channels' transforms, inputs from the staging buffers (the rest is fwd_half).
+template <int H, int FMT>
+__device__ __forceinline__ void fwd_half_staged(c2 *sm, const Tables &tb, uint32_t stage0, uint32_t stage1, int fv,
+                                                float2 *const (&rows)[2]) {
+    fwd_pass_a_staged<H, FMT>(sm, tb, stage0, stage1, fv);
+    cluster_arrive();   // this CTA has read the other's staging buffer (waited for before the CTA exits)
+    __syncthreads();
+    pass_b<-1, 2, 256>(sm, tb);
+    __syncthreads();
+    const int j = threadIdx.x, c = j >> 7;
+    fwd_pass_c<H>(sm + c * HALF_ELEMS, tb, c ? rows[1] : rows[0], j & 127);
+    cluster_wait();
 }
 
 }  // namespace f13

@@ -62,6 +62,45 @@ fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, i
     else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
 }
 
+// The same for the stereo blocks of the per-file path as a cluster of the two halves' CTAs that reads the
+// caller's block ONCE (f13::stage_half / fwd_pass_a_staged): half the bytes over the link.
+template <class SEL, int FMT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+fwd13_pair_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int R, int T, int reset_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    unsigned char *stage = smem_raw + 2 * f13::HALF_BYTES;
+    constexpr int N = f13::N;
+    pdl_trigger();
+    pdl_wait();
+    const int h = blockIdx.x, b = blockIdx.y, bt = blockIdx.z;   // gridDim.x == 2: h is the rank in the cluster
+    int frames = sel.frames(b) - bt * N;
+    frames = frames < 0 ? 0 : (frames > N ? N : frames);
+    int slot = sel.slot(b) + bt;
+    if (slot >= R) slot -= R;
+    float2 *const xring = sel.xring(b);
+    float2 *rows[2] = {xring + (size_t)(0 * R + slot) * N, xring + (size_t)(1 * R + slot) * N};
+    if (h == 0 && threadIdx.x == 0) {
+        const StreamDev s = sel.stream(b);
+        if (reset_max && bt == 0) *s.maxv = 0.0f;
+        s.bmax[bt] = 0.0f;
+    }
+    if (frames == 0) {  // silence (both CTAs of the pair): its spectrum is zero
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+            for (int e = threadIdx.x; e < f13::Q; e += 256) rows[c][h * f13::Q + e] = make_float2(0.f, 0.f);
+        return;
+    }
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    const void *in = reinterpret_cast<const char *>(sel.din(b)) + (size_t)bt * N * 2 * wire;
+    f13::stage_half<FMT>(stage, in, h, frames);
+    f13::cluster_arrive();
+    f13::cluster_wait();   // both halves of the block are staged
+    const uint32_t st0 = f13::peer_smem(stage, 0u), st1 = f13::peer_smem(stage, 1u);
+    if (h == 0) f13::fwd_half_staged<0, FMT>(sm, tb, st0, st1, frames, rows);
+    else f13::fwd_half_staged<1, FMT>(sm, tb, st0, st1, frames, rows);
+}
+
 // Filter preparation (K6): src[row][N] floats -> dst[row][N] spectra, one half per CTA.
 __global__ void __launch_bounds__(128, f13_min_ctas(128))
 fwd13_raw_kernel(const float *__restrict__ src, float2 *__restrict__ dst, f13::Tables tb) {
@@ -238,6 +277,9 @@ template <class SEL, int FMT>
 static int set_attrs13() {
     const int one = (int)f13::HALF_BYTES, two = 2 * (int)f13::HALF_BYTES;
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    if constexpr (SEL::kSingle)
+        CU_TRY(cudaFuncSetAttribute(fwd13_pair_kernel<SEL, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    two + (int)f13::STAGE_BYTES_MAX));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, one));
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
@@ -320,6 +362,15 @@ template <class SEL, int FMT>
 static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) {
     const fcv_filter *f = a.f;
     const int rm = a.per_block_max ? 1 : 0;
+    // per-file path, stereo: the two halves' CTAs as a cluster that reads the caller's block once (FCV_FWD_PAIR=0: off)
+    static const bool fwd_pair = !(getenv("FCV_FWD_PAIR") && atoi(getenv("FCV_FWD_PAIR")) == 0);
+    if constexpr (SEL::kSingle) {
+        if (f->ninp == 2 && fwd_pair) {
+            launch_k(fwd13_pair_kernel<SEL, FMT>, dim3(2, a.cnt, a.T), dim3(256), 2 * f13::HALF_BYTES + f13::STAGE_BYTES_MAX,
+                     q, a.pdl, sel, f->tb13, a.R, a.T, rm);
+            return;
+        }
+    }
     if (f->ninp == 2)
         launch_k(fwd13_stream_kernel<SEL, FMT, 2, 2>, dim3(2, a.cnt, a.T), dim3(256), 2 * f13::HALF_BYTES, q, a.pdl, sel,
                  f->tb13, f->ninp, a.R, a.T, rm);
