@@ -497,6 +497,9 @@ def album_library(ctx, wl, filter_dir, T, pcm16, in_process_gpus=0):
     threads = max(2, cores // max(1, ctx.world if in_process_gpus <= 1 else in_process_gpus))
     audio, chains = C.c_double(0), C.c_int(0)
     ctx.barrier()
+    # two BatchConvolvers per GPU (MultiDeviceConvolver's instances_per_device): four steps in flight instead of two;
+    # the small per-GPU batches of this config are bound by the latency of a step, not by the link
+    instances = int(os.environ.setdefault("FOLVE_B200_LIBRARY_INSTANCES", "2"))
     wall = L.fh_bench_albums(cfg.encode(), wl.fs, wl.ninp, nalbums, tracks, rank, world, in_process_gpus, T, threads,
                              1 if pcm16 else 0, C.byref(audio), C.byref(chains))
     if wall <= 0:
@@ -509,11 +512,12 @@ def album_library(ctx, wl, filter_dir, T, pcm16, in_process_gpus=0):
     return {"value": total_audio / max_wall, "unit": "x realtime (audio-s per wall-s)", "audio_seconds": total_audio,
             "wall_s": max_wall, "albums": nalbums, "tracks_per_album": tracks, "chains_per_gpu": chains.value
             if in_process_gpus <= 1 else nalbums // in_process_gpus,
-            "host_threads_per_gpu": threads, "wire_format": "s16" if pcm16 else "f32", "blocks_per_step": T,
+            "host_threads_per_gpu": threads, "batch_convolvers_per_gpu": instances,
+            "wire_format": "s16" if pcm16 else "f32", "blocks_per_step": T,
             "sharding": (f"one process, {in_process_gpus} GPUs (MultiDeviceConvolver)" if in_process_gpus > 1 else
                          f"{world} ranks, albums a = rank (mod {world}) (sharding.balanced_albums)"),
             "what": "BatchConvolver::Run over SNDFILE in / SNDFILE out: 128 gapless album chains x 8 tracks of "
-                    "U[120 s, 360 s] (seed 100 + album), all chains prebuffered at t = 0, two steps in flight"}
+                    "U[120 s, 360 s] (seed 100 + album), all chains prebuffered at t = 0, two steps in flight per BatchConvolver"}
 
 
 def parity_gate(wl, flt):

@@ -393,7 +393,7 @@ bool BatchConvolver::Run(const std::vector<Chain *> &chains, int threads) {
 MultiDeviceConvolver *MultiDeviceConvolver::Create(const std::string &config_file, int samplerate, int channels,
                                                    int slots_per_device, bool gapless,
                                                    const std::vector<int> &devices, int blocks_per_step,
-                                                   bool pcm16) {
+                                                   bool pcm16, int instances_per_device) {
     std::vector<int> ids = devices;
     if (ids.empty()) {
         const int n = fcv_device_count();
@@ -401,14 +401,18 @@ MultiDeviceConvolver *MultiDeviceConvolver::Create(const std::string &config_fil
     }
     if (ids.empty()) return nullptr;
     MultiDeviceConvolver *m = new MultiDeviceConvolver();
+    m->inst_ = instances_per_device > 1 ? instances_per_device : 1;
+    const int slots = (slots_per_device + m->inst_ - 1) / m->inst_;
     for (int d : ids) {
-        BatchConvolver *bc = BatchConvolver::Create(config_file, samplerate, channels, slots_per_device, gapless, d,
-                                                    blocks_per_step, pcm16);
-        if (!bc) {
-            delete m;
-            return nullptr;
+        for (int k = 0; k < m->inst_; k++) {
+            BatchConvolver *bc = BatchConvolver::Create(config_file, samplerate, channels, slots, gapless, d,
+                                                        blocks_per_step, pcm16);
+            if (!bc) {
+                delete m;
+                return nullptr;
+            }
+            m->parts_.push_back(bc);
         }
-        m->parts_.push_back(bc);
         m->device_ids_.push_back(d);
     }
     return m;
@@ -422,7 +426,7 @@ int MultiDeviceConvolver::fragment_size() const { return parts_.empty() ? 0 : pa
 int MultiDeviceConvolver::output_channels() const { return parts_.empty() ? 0 : parts_[0]->output_channels(); }
 
 int MultiDeviceConvolver::PlacementOf(const std::string &key) const {
-    return SoundProcessor::DeviceForKey(key, (int)parts_.size());
+    return SoundProcessor::DeviceForKey(key, (int)device_ids_.size());
 }
 
 long MultiDeviceConvolver::blocks_processed() const {
@@ -433,18 +437,22 @@ long MultiDeviceConvolver::blocks_processed() const {
 
 bool MultiDeviceConvolver::Run(const std::vector<Chain *> &chains, const std::vector<std::string> &keys,
                                int threads_per_device, std::vector<int> *assignment) {
-    const size_t nd = parts_.size();
-    std::vector<std::vector<Chain *> > shard(nd);
+    const size_t nd = device_ids_.size(), np = parts_.size();
+    std::vector<std::vector<Chain *> > shard(np);
+    std::vector<size_t> next(nd, 0);   // the chains of a device go round its instances
     if (assignment) assignment->assign(chains.size(), 0);
     for (size_t i = 0; i < chains.size(); i++) {
         const size_t d = keys.empty() ? i % nd : (size_t)PlacementOf(keys[i]);
-        shard[d].push_back(chains[i]);
+        shard[d * (size_t)inst_ + next[d]++ % (size_t)inst_].push_back(chains[i]);
         if (assignment) (*assignment)[i] = (int)d;
     }
-    std::vector<char> ok(nd, 1);
+    // every instance gets the device's full thread count: the instances of a device take turns -- one fills and
+    // drains while the others wait for their steps (measured: dividing the threads loses all of the gain)
+    const int threads = threads_per_device;
+    std::vector<char> ok(np, 1);
     std::vector<std::thread> th;
-    for (size_t d = 0; d < nd; d++)
-        th.emplace_back([&, d] { ok[d] = parts_[d]->Run(shard[d], threads_per_device) ? 1 : 0; });
+    for (size_t p = 0; p < np; p++)
+        th.emplace_back([&, p] { ok[p] = parts_[p]->Run(shard[p], threads) ? 1 : 0; });
     for (auto &t : th) t.join();
     bool all = true;
     for (char o : ok) all = all && o;

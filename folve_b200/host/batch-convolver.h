@@ -99,12 +99,17 @@ private:
 class MultiDeviceConvolver {
 public:
     // devices: CUDA device indices to use (empty: all usable ones).  NULL on failure.
+    // instances_per_device: BatchConvolvers per GPU, the chains of a device dealt out among them.  Each keeps two
+    // steps in flight, so k instances keep 2k: worth it for SMALL batches (a library of ~100 albums on one GPU),
+    // whose steps are bound by the latency of copy in -> kernels -> copy out rather than by the link (measured
+    // on the 128-album library of BASELINE config 5: +30 % with two instances).  slots_per_device is the total.
     static MultiDeviceConvolver *Create(const std::string &config_file, int samplerate, int channels,
                                         int slots_per_device, bool gapless, const std::vector<int> &devices,
-                                        int blocks_per_step = 1, bool pcm16 = false);
+                                        int blocks_per_step = 1, bool pcm16 = false, int instances_per_device = 1);
     ~MultiDeviceConvolver();
 
-    int devices() const { return (int)parts_.size(); }
+    int devices() const { return (int)device_ids_.size(); }
+    int instances_per_device() const { return inst_; }
     int fragment_size() const;
     int output_channels() const;
     // Position (0 .. devices()-1) of the device a chain with this key is placed on.
@@ -119,8 +124,9 @@ public:
 
 private:
     MultiDeviceConvolver() {}
-    std::vector<BatchConvolver *> parts_;
+    std::vector<BatchConvolver *> parts_;   // [device position][instance]
     std::vector<int> device_ids_;
+    int inst_ = 1;
 };
 
 }  // namespace folve_b200

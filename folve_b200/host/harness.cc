@@ -244,6 +244,7 @@ int fh_run_chain(const char *filter_dir, int samplerate, int channels, int bits,
 // chains over from this one process (0 = the single BatchConvolver on the default device).
 static std::vector<long> g_claimed_frames;
 static int g_library_devices = 0;
+static int g_library_instances = 1;
 static std::vector<int> g_last_assignment;
 
 static int RunLibrary(const char *config_file, int samplerate, int channels, int gapless, int slots, int threads,
@@ -252,15 +253,17 @@ static int RunLibrary(const char *config_file, int samplerate, int channels, int
                       long *steps_out, int blocks_per_step, int pcm16) {
     const std::vector<long> claimed = g_claimed_frames;
     g_claimed_frames.clear();
-    const int ndev = g_library_devices;
+    const int ndev = g_library_devices, inst = g_library_instances;
     g_library_devices = 0;
+    g_library_instances = 1;
     folve_b200::BatchConvolver *bc = nullptr;
     folve_b200::MultiDeviceConvolver *md = nullptr;
-    if (ndev > 0) {
+    if (ndev > 0 || inst > 1) {
         std::vector<int> ids;
-        for (int d = 0; d < ndev; d++) ids.push_back(d);
-        md = folve_b200::MultiDeviceConvolver::Create(config_file, samplerate, channels, slots, gapless != 0, ids,
-                                                      blocks_per_step, pcm16 != 0);
+        for (int d = 0; d < (ndev > 0 ? ndev : 1); d++)
+            ids.push_back(ndev > 0 ? d : (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()));
+        md = folve_b200::MultiDeviceConvolver::Create(config_file, samplerate, channels, slots + inst, gapless != 0, ids,
+                                                      blocks_per_step, pcm16 != 0, inst);
         if (!md) return -1;
     } else {
         bc = folve_b200::BatchConvolver::Create(config_file, samplerate, channels, slots, gapless != 0,
@@ -310,6 +313,7 @@ static int RunLibrary(const char *config_file, int samplerate, int channels, int
 
 void fh_set_claimed_frames(const long *claimed, int n) { g_claimed_frames.assign(claimed, claimed + n); }
 void fh_set_library_devices(int ndevices) { g_library_devices = ndevices; }
+void fh_set_library_instances(int instances) { g_library_instances = instances > 1 ? instances : 1; }
 // device position every chain of the last multi-device run was placed on; returns the chain count
 int fh_last_assignment(int *out, int capacity) {
     for (int i = 0; i < capacity && (size_t)i < g_last_assignment.size(); i++) out[i] = g_last_assignment[(size_t)i];
@@ -424,15 +428,18 @@ double fh_bench_albums(const char *config_file, int samplerate, int channels, in
     std::vector<int> mine;
     for (int a = rank; a < nalbums; a += world) mine.push_back(a);
     if (mine.empty()) return -1.0;
+    // FOLVE_B200_LIBRARY_INSTANCES=k: k BatchConvolvers per GPU (MultiDeviceConvolver's instances_per_device)
+    const int inst = getenv("FOLVE_B200_LIBRARY_INSTANCES") ? atoi(getenv("FOLVE_B200_LIBRARY_INSTANCES")) : 1;
     const int nd = ndevices > 1 ? ndevices : 1;
-    const int slots = ((int)mine.size() + nd - 1) / nd + (nd > 1 ? 2 : 0);   // room for an uneven placement
+    const int slots = ((int)mine.size() + nd - 1) / nd + (nd > 1 ? 2 : 0) + (inst > 1 ? inst : 0);   // room for an uneven placement
     folve_b200::BatchConvolver *bc = nullptr;
     folve_b200::MultiDeviceConvolver *md = nullptr;
-    if (nd > 1) {
+    if (nd > 1 || inst > 1) {
         std::vector<int> ids;
-        for (int d = 0; d < nd; d++) ids.push_back(d);
+        const int dev0 = SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device();
+        for (int d = 0; d < nd; d++) ids.push_back(nd > 1 ? d : dev0);
         md = folve_b200::MultiDeviceConvolver::Create(config_file, samplerate, channels, slots, true, ids,
-                                                      blocks_per_step, pcm16 != 0);
+                                                      blocks_per_step, pcm16 != 0, inst);
     } else {
         bc = folve_b200::BatchConvolver::Create(config_file, samplerate, channels, slots, true,
                                                 (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()),

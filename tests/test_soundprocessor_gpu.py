@@ -365,6 +365,27 @@ def test_one_process_many_gpus_equals_one_gpu(dirs):
     assert n == 8 and len(set(devs)) == min(ndev, 8)
 
 
+def test_several_batch_convolvers_per_gpu_equal_one(dirs):
+    """MultiDeviceConvolver's instances_per_device: the chains of ONE GPU dealt out to two / three
+    BatchConvolvers (4 / 6 steps in flight instead of 2) give every file what a single one gives it"""
+    P = H.product()
+    d, rate, ch, bits = dirs["crossfeed"]
+    conf = os.path.join(d, f"filter-{rate}.conf")
+    N = _fragm(d, rate, ch)["fragm"]
+    r = np.random.default_rng(6)
+    shapes = [[N + 1, 2 * N + 5, N + N // 3], [2 * N, N + 7], [N + 100, 50, 300], [3 * N + 17], [40], [N],
+              [N - 1, 1, 1, N + 2], [5 * N + 11, 2 * N, 3 * N + 3], [7], [2 * N + 1, N]]
+    chains = [[_noise(n, ch, 0.25, int(r.integers(1 << 30))) for n in lens] for lens in shapes]
+    one, mx1, fl1, _ = P.run_library(conf, rate, ch, chains, gapless=True, slots=10, threads=2)
+    for inst in (2, 3):
+        P.L.fh_set_library_instances(inst)
+        many, mxn, fln, _ = P.run_library(conf, rate, ch, chains, gapless=True, slots=10, threads=4)
+        for ci in range(len(chains)):
+            for fi in range(len(chains[ci])):
+                assert np.array_equal(one[ci][fi], many[ci][fi]), (inst, ci, fi)
+        assert fl1 == fln and mx1 == mxn
+
+
 DEMO_FIXTURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "demo-filters")
 
 
