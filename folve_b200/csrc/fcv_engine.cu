@@ -989,6 +989,11 @@ struct fcv_stream {
     std::string err;
     double t_submit = 0;              // tracing only
     const float *mix = nullptr;       // device frames added to the next block's output (fcv_nonuniform.cu), or null
+    // Sequence number of the last block whose request fields the dispatcher has finished reading.  The real
+    // ordering "dispatcher reads -> launch -> GPU -> completion word -> caller writes the next request" runs
+    // through the device; this release / acquire pair states it in terms the C++ memory model (and
+    // ThreadSanitizer) can see.
+    std::atomic<unsigned> read_done{0};
 };
 
 // Dispatcher ("group commit") of the synchronous per-file path.  folve convolves every open file
@@ -1143,6 +1148,8 @@ static int launch_group(FcvCombiner *c, fcv_stream *const *m, int n, cudaStream_
             CU_TRY(cudaMemcpyAsync(b->din, b->hin, (size_t)s->frames_valid * f->ninp * pcm_bytes(b->in_fmt),
                                    cudaMemcpyHostToDevice, q));
     }
+    for (int i = 0; i < n; i++)   // zero-copy streams are not touched after this (staged ones: see below)
+        if (!staged[i]) m[i]->read_done.store(sel.sq[i], std::memory_order_release);
     StepArgs a;
     a.f = f;
     a.T = 1;
@@ -1179,6 +1186,7 @@ static int launch_group(FcvCombiner *c, fcv_stream *const *m, int n, cudaStream_
         if (out_bytes) CU_TRY(cudaMemcpyAsync(b->hin, b->dout, out_bytes, cudaMemcpyDeviceToHost, q));
         CU_TRY(cudaMemcpyAsync(b->hin + b->host_block, b->maxv, sizeof(float), cudaMemcpyDeviceToHost, q));
         b->seq_src = s->seq;
+        s->read_done.store(s->seq, std::memory_order_release);   // last touch of the stream
         CU_TRY(cudaMemcpyAsync(stream_done_word(b), &b->seq_src, sizeof(unsigned), cudaMemcpyHostToHost, q));
     }
     return 0;
@@ -1390,6 +1398,9 @@ extern "C" int fcv_stream_await(fcv_stream *s, float *max_inout) {
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    // the dispatcher is done with this request's fields (always true by now: it read them before it launched)
+    if (!rc)
+        while (s->read_done.load(std::memory_order_acquire) != s->seq) cpu_relax();
     if (c->trace) c->tr_total_ns += (unsigned long long)(1e3 * (now_us() - s->t_submit));
     s->state.store(fcv_stream::IDLE, std::memory_order_release);
     c->active.fetch_sub(1, std::memory_order_relaxed);
