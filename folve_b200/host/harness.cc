@@ -373,10 +373,19 @@ static double NowSeconds() {
 double fh_bench_library(const char *config_file, int samplerate, int channels, int gapless, int nchains,
                         int files_per_chain, long frames_per_file, int blocks_per_step, int threads, int pcm16,
                         double *audio_seconds) {
-    folve_b200::BatchConvolver *bc = folve_b200::BatchConvolver::Create(
-        config_file, samplerate, channels, nchains, gapless != 0, (SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device()), blocks_per_step, pcm16 != 0);
-    if (!bc) return -1.0;
-    const int nout = bc->output_channels();
+    // FOLVE_B200_LIBRARY_INSTANCES=k: k BatchConvolvers on the GPU (MultiDeviceConvolver's instances_per_device)
+    const int inst = getenv("FOLVE_B200_LIBRARY_INSTANCES") ? atoi(getenv("FOLVE_B200_LIBRARY_INSTANCES")) : 1;
+    const int dev = SoundProcessor::Device() < 0 ? 0 : SoundProcessor::Device();
+    folve_b200::BatchConvolver *bc = nullptr;
+    folve_b200::MultiDeviceConvolver *md = nullptr;
+    if (inst > 1)
+        md = folve_b200::MultiDeviceConvolver::Create(config_file, samplerate, channels, nchains + inst, gapless != 0,
+                                                      std::vector<int>(1, dev), blocks_per_step, pcm16 != 0, inst);
+    else
+        bc = folve_b200::BatchConvolver::Create(config_file, samplerate, channels, nchains, gapless != 0, dev,
+                                                blocks_per_step, pcm16 != 0);
+    if (!bc && !md) return -1.0;
+    const int nout = bc ? bc->output_channels() : md->output_channels();
     const long longest = frames_per_file + 4099;
     std::vector<float> pcm((size_t)longest * (size_t)channels);
     std::vector<short> pcm_s16(pcm16 ? pcm.size() : 0);
@@ -402,7 +411,7 @@ double fh_bench_library(const char *config_file, int samplerate, int channels, i
     std::vector<folve_b200::Chain *> ptrs;
     for (auto &c : chains) ptrs.push_back(&c);
     const double t0 = NowSeconds();
-    const bool ok = bc->Run(ptrs, threads);
+    const bool ok = bc ? bc->Run(ptrs, threads) : md->Run(ptrs, std::vector<std::string>(), threads);
     const double wall = NowSeconds() - t0;
     for (auto &c : chains)
         for (auto &f : c) {
@@ -410,6 +419,7 @@ double fh_bench_library(const char *config_file, int samplerate, int channels, i
             sf_close(f.out);
         }
     delete bc;
+    delete md;
     if (audio_seconds) *audio_seconds = frames_total / (double)samplerate;
     return ok ? wall : -2.0;
 }
