@@ -6,14 +6,14 @@
 using namespace fcv;
 
 // Returns false when the shape is not covered.
-template <int T, int S, int NS, int MC = tma::min_ctas(T, S)>
+template <int T, int S, int NS, int G = NS, int MC = tma::min_ctas(T, S)>
 static bool launch_tma(const StepArgs &a, int newest, cudaStream_t q) {
     const fcv_filter *f = a.f;
     const int M4 = f->fragm / 2;
     if (M4 % tma::TPB != 0 || a.cnt < S) return false;
     const size_t smem = tma::smem_bytes(S, NS);
     // dynamic + static shared memory exceeds the 48 KB default; the attribute is per device
-    if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS, MC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return false;
     // one CTA per work item; FCV_MAC_PERSIST=n runs a persistent grid of n CTAs per SM instead
@@ -24,7 +24,7 @@ static bool launch_tma(const StepArgs &a, int newest, cudaStream_t q) {
     if (persist > 0 && a.num_sms * persist < nitems) grid = a.num_sms * persist;
     const float4 *H = reinterpret_cast<const float4 *>(f->dH);
     float4 *Y = reinterpret_cast<float4 *>(a.Y);
-    tma::mac_tma_kernel<T, S, NS, MC><<<grid, tma::THREADS, smem, q>>>(a.bsel.xring0, a.bsel.xring_stride, a.cnt, f->dpairs, f->dpair_off,
+    tma::mac_tma_kernel<T, S, NS, MC, G><<<grid, tma::THREADS, smem, q>>>(a.bsel.xring0, a.bsel.xring_stride, a.cnt, f->dpairs, f->dpair_off,
                                                                      f->dtt_rows, H, Y, M4, f->ring, a.R, newest,
                                                                      f->nout, f->nrows, ntiles, ngroups, nitems);
     return true;
@@ -38,7 +38,14 @@ bool fcv::launch_mac_tma(const StepArgs &a, int newest, cudaStream_t q) {
     static const int use_tma = getenv("FCV_MAC_TMA") ? atoi(getenv("FCV_MAC_TMA")) : 1;
     if (!use_tma) return false;
     if (a.T == 8 && use_tma == 3 && launch_tma<8, 1, 12>(a, newest, q)) return true;
-    if (a.T == 8 && launch_tma<8, 2, 8>(a, newest, q)) return true;
+    // FCV_MAC_G: rows per producer pass (fcv_mac_tma.cuh; 0 = in order, one lane at a time)
+    static const int g = getenv("FCV_MAC_G") ? atoi(getenv("FCV_MAC_G")) : 4;
+    if (a.T == 8 && g == 0 && launch_tma<8, 2, 8, 0>(a, newest, q)) return true;
+    if (a.T == 8 && g == 1 && launch_tma<8, 2, 8, 1>(a, newest, q)) return true;
+    if (a.T == 8 && g == 2 && launch_tma<8, 2, 8, 2>(a, newest, q)) return true;
+    if (a.T == 8 && g == 4 && launch_tma<8, 2, 8, 4>(a, newest, q)) return true;
+    if (a.T == 8 && g == 8 && launch_tma<8, 2, 8, 8>(a, newest, q)) return true;
+    if (a.T == 8 && launch_tma<8, 2, 8, 4>(a, newest, q)) return true;
     if (a.T == 4 && use_tma == 2 && launch_tma<4, 4, 6>(a, newest, q)) return true;
     if (a.T == 4 && launch_tma<4, 2, 8>(a, newest, q)) return true;
     return false;

@@ -113,7 +113,16 @@ __host__ __device__ constexpr size_t smem_bytes(int S, int NS) { return (size_t)
 // CTAs per SM the register allocation is held to (T * S accumulators + T window entries)
 __host__ __device__ constexpr int min_ctas(int T, int S) { return T * S >= 16 ? 3 : 4; }
 
-template <int T, int S, int NS, int MC = min_ctas(T, S)>
+// G: how the producer warp hands out the rows of the window.
+//   G > 0: passes of G rows, lane l of a pass takes row g0 + l (stage (g0 + l) % NS).  The lanes of
+//          a pass reconverge behind their waits (ptxas brackets the try_wait spin with BSSY /
+//          BSYNC), so a pass issues its copies when the LAST of its G stages has been released:
+//          with G = NS the ring is refilled only once it has drained completely (no copy of a CTA
+//          in flight while its consumers work); with G < NS the copies run NS - G rows ahead of
+//          the arithmetic at G-fold amortised address arithmetic.
+//   G = 0: the addresses of NS rows are computed lane-parallel, then the rows are issued in order,
+//          one lane at a time, each as soon as its own stage is released (NS - 1 rows ahead).
+template <int T, int S, int NS, int MC = min_ctas(T, S), int G = NS>
 __global__ void __launch_bounds__(THREADS, MC)
 mac_tma_kernel(const float2 *__restrict__ xring0, size_t xring_stride, int nstreams, const TTPair *__restrict__ pairs,
                const int *__restrict__ pair_off, const int *__restrict__ tt_rows,
@@ -148,7 +157,9 @@ mac_tma_kernel(const float2 *__restrict__ xring0, size_t xring_stride, int nstre
         // same stage and keeps that stage's phase bit; the consumers index the stages of a
         // T-row chunk with compile-time constants when NS divides T.
         static_assert(NS <= 32, "one lane per stage");
-        uint32_t ph = 0;   // parity of this lane's stage: flips with every row the lane issues
+        static_assert(G >= 0 && G <= NS && (G == 0 || NS % G == 0), "lanes per pass: a stage is always served by the same lane");
+        constexpr int GL = G > 0 ? G : NS;   // rows whose addresses one pass computes
+        uint32_t ph = 0;   // bit s: parity of the last fill of stage s (a lane only ever looks at the stages it serves)
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int o = item % nout, tile = (item / nout) % ntiles, b0 = item / (nout * ntiles) * S;
             const int p0 = pair_off[o], p1 = pair_off[o + 1];
@@ -163,22 +174,30 @@ mac_tma_kernel(const float2 *__restrict__ xring0, size_t xring_stride, int nstre
             for (int p = p0; p < p1; p++) {
                 const int inp = pairs[p].inp;
                 const int *rows = tt_rows + pairs[p].rowbase;
-                for (int g0 = 0; g0 < D; g0 += NS) {
+                for (int g0 = 0; g0 < D; g0 += GL) {
                     const int d = g0 + lane;
-                    if (lane < NS && d < D) {
-                        const int stage = lane;
-                        int slot = newest_slot - d;   // d < D = R: at most one wrap
-                        if (slot < 0) slot += R;
-                        int row = d < P ? rows[d] : 0;
-                        if (row < 0) row = zero_row;
-                        mbar_wait(&empty[stage], ph ^ 1);
-                        ph ^= 1;
-                        unsigned char *dst = stages + (size_t)stage * STAGE_BYTES;
+                    const bool has_row = lane < GL && d < D;
+                    const int stage = d % NS;
+                    int slot = newest_slot - d;   // d < D = R: at most one wrap
+                    if (slot < 0) slot += R;
+                    int row = (has_row && d < P) ? rows[d] : 0;
+                    if (row < 0) row = zero_row;
+                    unsigned char *dst = stages + (size_t)stage * STAGE_BYTES;
+                    const size_t xoff = ((size_t)inp * R + slot) * rowb;
+                    auto issue = [&]() {
+                        mbar_wait(&empty[stage], ((ph >> stage) & 1) ^ 1);
+                        ph ^= 1u << stage;
                         mbar_expect_tx(&full[stage], (uint32_t)((d < P ? S + 1 : S) * TILE_BYTES));
-                        const size_t xoff = ((size_t)inp * R + slot) * rowb;
 #pragma unroll
                         for (int s = 0; s < S; s++) bulk_g2s(dst + s * TILE_BYTES, xbase[s] + xoff, TILE_BYTES, &full[stage]);
                         if (d < P) bulk_g2s(dst + S * TILE_BYTES, hbase + (size_t)row * rowb, TILE_BYTES, &full[stage]);
+                    };
+                    if (G > 0) {
+                        if (has_row) issue();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NS; i++)
+                            if (lane == i && has_row) issue();
                     }
                     __syncwarp();
                 }
@@ -206,47 +225,58 @@ mac_tma_kernel(const float2 *__restrict__ xring0, size_t xring_stride, int nstre
         c2x2 hw[T];
 #pragma unroll
         for (int t = 0; t < T; t++) hw[t].a = hw[t].b = 0ull;
-        // T steps d0 .. d0+T-1; GUARD: the chunk contains steps where some outputs have no
-        // partition (j < 0 at the head of the window, j >= P at its tail)
-        auto chunk = [&](int d0, auto guard) {
-            constexpr bool GUARD = decltype(guard)::value;
+        // Rows d0 .. d0+NR-1 of the window (NR <= T, a compile-time count: straight-line code, one
+        // entry, one exit -- an early exit per row makes ptxas re-home every accumulator in front
+        // of each exit branch, ~90 MOVs per row).
+        // HEAD (d0 = 0): output t starts on partition 0 at row T-1-t, so row r feeds the outputs
+        // t >= T-1-r -- a compile-time staircase.  Otherwise every row feeds every output: the
+        // outputs whose partition index j = d-(T-1)+t has run past P-1 are NOT skipped, their window
+        // entries are the zeros that rows d >= P put there (h = 0 below), so they add x * 0 to an
+        // accumulator that is never -0 -- bit-identical to skipping them, and much cheaper than the
+        // per-output ISETP / BRA pairs that skipping costs (21 of SantaLucia's 29 rows were such
+        // guarded rows: 150 against 89 instructions of an unguarded row).
+        auto chunk = [&](int d0, auto head, auto nrows) {
+            constexpr bool HEAD = decltype(head)::value;
+            constexpr int NR = decltype(nrows)::value;
 #pragma unroll
-            for (int r = 0; r < T; r++) {
+            for (int r = 0; r < NR; r++) {
                 const int d = d0 + r;
-                if (!GUARD || d < D) {
-                    const int stage = FIXED ? r % NS : (d0 + r) % NS;
-                    mbar_wait_a(bar0 + 8 * stage, (phases >> stage) & 1);
-                    const uint32_t sp = mine + stage * STAGE_BYTES;
-                    c2x2 x[S];
+                const int stage = FIXED ? r % NS : (d0 + r) % NS;
+                mbar_wait_a(bar0 + 8 * stage, (phases >> stage) & 1);
+                const uint32_t sp = mine + stage * STAGE_BYTES;
+                c2x2 x[S];
 #pragma unroll
-                    for (int s = 0; s < S; s++) x[s] = lds_c2x2_a(sp + s * TILE_BYTES);
-                    c2x2 h;
-                    h.a = h.b = 0ull;
-                    if (!GUARD || d < P) h = lds_c2x2_a(sp + S * TILE_BYTES);
-                    hw[(T - 1 + r) % T] = h;  // H[d]: the newest output (t = T-1) starts on partition j = d
+                for (int s = 0; s < S; s++) x[s] = lds_c2x2_a(sp + s * TILE_BYTES);
+                c2x2 h;
+                h.a = h.b = 0ull;
+                if (d < P) h = lds_c2x2_a(sp + S * TILE_BYTES);
+                hw[(T - 1 + r) % T] = h;  // H[d]: the newest output (t = T-1) starts on partition j = d
 #pragma unroll
-                    for (int t = 0; t < T; t++) {
-                        const int j = d - (T - 1) + t;
-                        if (!GUARD || (j >= 0 && j < P)) {
-                            const c2x2 hh = hw[(t + r) % T];
+                for (int t = (HEAD ? T - 1 - r : 0); t < T; t++) {
+                    const c2x2 hh = hw[(t + r) % T];
 #pragma unroll
-                            for (int s = 0; s < S; s++) {
-                                acc[t][s][0] = c2_cmac(acc[t][s][0], x[s].a, hh.a);
-                                acc[t][s][1] = c2_cmac(acc[t][s][1], x[s].b, hh.b);
-                            }
-                        }
+                    for (int s = 0; s < S; s++) {
+                        acc[t][s][0] = c2_cmac(acc[t][s][0], x[s].a, hh.a);
+                        acc[t][s][1] = c2_cmac(acc[t][s][1], x[s].b, hh.b);
                     }
-                    mbar_arrive_elect_a(bar0 + 8 * (NS + stage));
-                    phases ^= 1u << stage;
                 }
+                mbar_arrive_elect_a(bar0 + 8 * (NS + stage));
+                phases ^= 1u << stage;
             }
         };
+        using IT = std::integral_constant<int, T>;
         int d0 = 0;
-        chunk(d0, std::true_type{});
+        chunk(d0, std::true_type{}, IT{});   // D = P+T-1 >= T: all T rows of the head exist
 #pragma unroll 1
-        for (d0 = T; d0 + T <= P; d0 += T) chunk(d0, std::false_type{});
-#pragma unroll 1
-        for (; d0 < D; d0 += T) chunk(d0, std::true_type{});
+        for (d0 = T; d0 + T <= D; d0 += T) chunk(d0, std::false_type{}, IT{});
+        // the last D % T rows, as one of T-1 straight-line bodies (one per launch: P is the filter's)
+        switch (D - d0) {
+#define FCV_TAIL(n) case n: if constexpr (n < T) chunk(d0, std::false_type{}, std::integral_constant<int, n>{}); break;
+            FCV_TAIL(1) FCV_TAIL(2) FCV_TAIL(3) FCV_TAIL(4) FCV_TAIL(5) FCV_TAIL(6) FCV_TAIL(7)
+#undef FCV_TAIL
+            default: break;
+        }
+        static_assert(T <= 8, "tail bodies");
     }
     const int e4 = tile * TPB + threadIdx.x;
 #pragma unroll
