@@ -468,6 +468,208 @@ __device__ __forceinline__ float inv_pass_a(const c2 *sm, const Tables &tb, floa
 }
 
 
+// ---- tensor memory as a per-thread scratch: what a thread needs again in every block ----------
+// The inverse kernel of a batch walks T blocks of one (stream, output).  In every block each thread
+// re-reads the SAME 47 twiddles (31 of pass A^-1, 16 of the repack in pass C^-1: 128 KB of tables per
+// SM cycling through ~100 KB of L1, hit rate 16 %, profiles/r02b_kernels.md) and reads back the 16
+// overlap values it stored itself one block earlier -- 79 of its ~145 global-memory instructions per
+// block.  B200's 256 KB of tensor memory per SM are idle in this kernel (no MMA): each CTA allocates
+// 256 columns (2 CTAs per SM = all 512), every thread owns 128 words of them -- its lane of the warp's
+// lane quarter, columns [128 (warp / 4), +128) -- and keeps there
+//   words   0 ..  31   the overlap tail (16 x float2), carried from block to block
+//   words  32 ..  95   pass A^-1 twiddles: slot k0 (1..15) = twA0[k0-1][u], slot 16 + k0 = twA1[k0][u]
+//   words  96 .. 127   repack twiddles of pass C^-1: slot k2 = twU[256 k2 + c]
+// tcgen05.ld / tcgen05.st (shape 32x32b: thread i <-> lane i, register j <-> column j) move 16 or 32
+// registers per instruction.  Same values, same arithmetic: bit-identical to the kernel without it.
+namespace tm {
+constexpr uint32_t COLS = 256;            // per CTA
+constexpr uint32_t TAIL = 0, TWA = 32, TWC = 96;
+__device__ __forceinline__ void alloc(uint32_t *slot, uint32_t ncols) {   // one whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dealloc(uint32_t addr, uint32_t ncols) {   // one whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// this thread's 128 words: lane quarter of its warp, column half of its warp's group of four
+__device__ __forceinline__ uint32_t thread_base(uint32_t cta_base) {
+    const uint32_t warp = threadIdx.x >> 5;
+    return cta_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 128u;
+}
+// NC2 packed complex values = 2 NC2 columns; the load waits for its data inside the same statement
+template <int NC2> __device__ __forceinline__ void tm_ld(uint32_t taddr, c2 *v);
+template <int NC2> __device__ __forceinline__ void tm_st(uint32_t taddr, const c2 *v);
+template <>
+__device__ __forceinline__ void tm_ld<8>(uint32_t taddr, c2 *v) {
+    asm volatile("{ .reg .b32 t<16>; tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15}, [%8]; tcgen05.wait::ld.sync.aligned; mov.b64 %0, {t0, t1}; mov.b64 %1, {t2, t3}; mov.b64 %2, {t4, t5}; mov.b64 %3, {t6, t7}; mov.b64 %4, {t8, t9}; mov.b64 %5, {t10, t11}; mov.b64 %6, {t12, t13}; mov.b64 %7, {t14, t15}; }"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]), "=l"(v[4]), "=l"(v[5]), "=l"(v[6]), "=l"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tm_ld<16>(uint32_t taddr, c2 *v) {
+    asm volatile("{ .reg .b32 t<32>; tcgen05.ld.sync.aligned.32x32b.x32.b32 {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18, t19, t20, t21, t22, t23, t24, t25, t26, t27, t28, t29, t30, t31}, [%16]; tcgen05.wait::ld.sync.aligned; mov.b64 %0, {t0, t1}; mov.b64 %1, {t2, t3}; mov.b64 %2, {t4, t5}; mov.b64 %3, {t6, t7}; mov.b64 %4, {t8, t9}; mov.b64 %5, {t10, t11}; mov.b64 %6, {t12, t13}; mov.b64 %7, {t14, t15}; mov.b64 %8, {t16, t17}; mov.b64 %9, {t18, t19}; mov.b64 %10, {t20, t21}; mov.b64 %11, {t22, t23}; mov.b64 %12, {t24, t25}; mov.b64 %13, {t26, t27}; mov.b64 %14, {t28, t29}; mov.b64 %15, {t30, t31}; }"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]), "=l"(v[4]), "=l"(v[5]), "=l"(v[6]), "=l"(v[7]), "=l"(v[8]), "=l"(v[9]), "=l"(v[10]), "=l"(v[11]), "=l"(v[12]), "=l"(v[13]), "=l"(v[14]), "=l"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void tm_st<16>(uint32_t taddr, const c2 *v) {
+    asm volatile("{ .reg .b32 t<32>; mov.b64 {t0, t1}, %1; mov.b64 {t2, t3}, %2; mov.b64 {t4, t5}, %3; mov.b64 {t6, t7}, %4; mov.b64 {t8, t9}, %5; mov.b64 {t10, t11}, %6; mov.b64 {t12, t13}, %7; mov.b64 {t14, t15}, %8; mov.b64 {t16, t17}, %9; mov.b64 {t18, t19}, %10; mov.b64 {t20, t21}, %11; mov.b64 {t22, t23}, %12; mov.b64 {t24, t25}, %13; mov.b64 {t26, t27}, %14; mov.b64 {t28, t29}, %15; mov.b64 {t30, t31}, %16; tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18, t19, t20, t21, t22, t23, t24, t25, t26, t27, t28, t29, t30, t31}; }"
+                 :
+                 : "r"(taddr), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]), "l"(v[4]), "l"(v[5]), "l"(v[6]), "l"(v[7]), "l"(v[8]), "l"(v[9]), "l"(v[10]), "l"(v[11]), "l"(v[12]), "l"(v[13]), "l"(v[14]), "l"(v[15])
+                 : "memory");
+}
+}  // namespace tm
+
+// Pass C^-1 as inv_pass_c with the repack twiddles handed in (w[k2] = twU[256 k2 + c]; the thread of entry 0,
+// t = 0 of half 0, finds those of its second run in the slots its first run leaves free: w[0] = twU[128],
+// w[8 + k2] = twU[256 k2 + 128], k2 = 1..7 -- inv_fill_twc).
+template <int H>
+__device__ __forceinline__ void inv_pass_c_w(c2 *sm, const float2 *__restrict__ yrow, c2 zc0, int t, const c2 (&w)[16]) {
+    const float2 *y = yrow + H * Q;
+    if (H == 0 && t == 0) {
+        c2 y1[16], y2[16], v1[16], v2[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) {
+            y1[k2] = ldg_stream_c2(y + 256 * k2);
+            y2[k2] = ldg_stream_c2(y + 256 * k2 + 128);
+        }
+        v1[0] = zc0;
+#pragma unroll
+        for (int k2 = 1; k2 <= 8; k2++) {
+            c2 zk, zp;
+            repack_pair(y1[k2], y1[16 - k2], w[k2], zk, zp);
+            v1[k2] = zk;
+            if (k2 != 8) v1[16 - k2] = zp;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            c2 zk, zp;
+            repack_pair(y2[k2], y2[15 - k2], k2 == 0 ? w[0] : w[8 + k2], zk, zp);
+            v2[k2] = zk;
+            v2[15 - k2] = zp;
+        }
+        Bfly<16>::template run<+1>(v1);
+        Bfly<16>::template run<+1>(v2);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            sm[out16(r)] = v1[r];
+            sm[16 * 8 + out16(r)] = v2[r];
+        }
+        return;
+    }
+    const int c = t, cc = H == 0 ? 256 - t : 255 - t;
+    c2 v1[16], v2[16];
+    {
+        c2 y1[16], y2[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) {
+            y1[k2] = ldg_stream_c2(y + 256 * k2 + c);
+            y2[k2] = ldg_stream_c2(y + 256 * k2 + cc);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) repack_pair(y1[k2], y2[15 - k2], w[k2], v1[k2], v2[15 - k2]);
+    }
+    Bfly<16>::template run<+1>(v1);
+    Bfly<16>::template run<+1>(v2);
+    c2 *p1 = sm + (c & 15) * ROW + (c >> 4) * 16;
+    c2 *p2 = sm + (cc & 15) * ROW + (cc >> 4) * 16;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        p1[out16(r)] = v1[r];
+        p2[out16(r)] = v2[r];
+    }
+}
+// the w[] of inv_pass_c_w for thread j (0..255: half j / 128, t = j % 128), from the table
+__device__ __forceinline__ void inv_fill_twc(const Tables &tb, int j, c2 (&w)[16]) {
+    const int H = j >> 7, t = j & 127;
+    const float2 *twu = tb.twU + H * Q;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) w[k2] = ldg_c2(twu + 256 * k2 + t);
+    if (j == 0) {
+        w[0] = ldg_c2(twu + 128);
+#pragma unroll
+        for (int k2 = 1; k2 < 8; k2++) w[8 + k2] = ldg_c2(twu + 256 * k2 + 128);
+    }
+}
+
+// Pass A^-1 as inv_pass_a (256 threads, one column each) with the twiddles and the overlap tail in the thread's
+// tensor-memory words: no table load, no tail load, no tail store.
+template <int FMT>
+__device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void *dout, int nout, int o, int frames) {
+    float lmax = 0.0f;
+    const int u = threadIdx.x;
+    c2 va[16], vb[16];
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0++) {
+        va[k0] = sm[k0 * ROW + u];
+        vb[k0] = sm[HALF_ELEMS + k0 * ROW + u];
+    }
+    {
+        c2 w[16];
+        tm::tm_ld<16>(tmem + tm::TWA, w);
+#pragma unroll
+        for (int k0 = 1; k0 < 16; k0++) va[k0] = c2_cmulconj(va[k0], w[k0]);
+        tm::tm_ld<16>(tmem + tm::TWA + 32, w);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++) vb[k0] = c2_cmulconj(vb[k0], w[k0]);
+    }
+    Bfly<16>::template run<+1>(va);
+    Bfly<16>::template run<+1>(vb);
+    c2 tl[16];
+    tm::tm_ld<16>(tmem + tm::TAIL, tl);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int n2 = out16(r), n = u + 256 * n2;
+        const c2 b = n2 == 0 ? vb[r] : c2_cmulconj(vb[r], c2_pack(w32(n2)));
+        const float2 s = c2_unpack(c2_add(va[r], b));
+        const float2 t = c2_unpack(tl[r]);
+        const float y0 = s.x + t.x, y1 = s.y + t.y;
+        tl[r] = c2_sub(va[r], b);
+        const int f0 = 2 * n;
+        pcm_store<FMT>(dout, (size_t)f0 * nout + o, y0);
+        pcm_store<FMT>(dout, (size_t)(f0 + 1) * nout + o, y1);
+        if (f0 < frames) lmax = fmaxf(lmax, y0);
+        if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
+    }
+    tm::tm_st<16>(tmem + tm::TAIL, tl);
+    tm::wait_st();
+    return lmax;
+}
+// the thread's words: tail from / to global memory (first / behind the last block), twiddles from the tables
+__device__ __forceinline__ void inv_tm_fill(uint32_t tmem, const Tables &tb, const float2 *__restrict__ tail) {
+    const int u = threadIdx.x;
+    c2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const float2 t = __ldcg(&tail[u + 256 * out16(r)]);
+        v[r] = c2_pack(t.x, t.y);
+    }
+    tm::tm_st<16>(tmem + tm::TAIL, v);
+    v[0] = 0ull;
+#pragma unroll
+    for (int k0 = 1; k0 < 16; k0++) v[k0] = ldg_c2(tb.twA0 + (k0 - 1) * 256 + u);
+    tm::tm_st<16>(tmem + tm::TWA, v);
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0++) v[k0] = ldg_c2(tb.twA1 + k0 * 256 + u);
+    tm::tm_st<16>(tmem + tm::TWA + 32, v);
+    inv_fill_twc(tb, u, v);
+    tm::tm_st<16>(tmem + tm::TWC, v);
+    tm::wait_st();
+}
+__device__ __forceinline__ void inv_tm_save_tail(uint32_t tmem, float2 *__restrict__ tail) {
+    const int u = threadIdx.x;
+    c2 v[16];
+    tm::tm_ld<16>(tmem + tm::TAIL, v);
+#pragma unroll
+    for (int r = 0; r < 16; r++) tail[u + 256 * out16(r)] = c2_unpack(v[r]);
+}
+
+
 // ---- stereo pair: the two output channels of a stream as a cluster of two CTAs -------------
 // A CTA owns ONE channel of an interleaved block, so on its own it can only store 2- or 4-byte
 // scalars, every 32-byte sector of the block being written four times (timing-only ablation,

@@ -123,13 +123,17 @@ __device__ __forceinline__ void block_max_update13(float *dst, float m) {
 // Inverse transform of every (stream, output channel), T blocks one after the other
 // (block t+1 overlap-adds the tail block t just saved), with overlap-add, tail save,
 // re-interleave, float -> PCM and the signed maximum of the valid frames fused in.
-template <class SEL, int FMT, bool PF>
+// TM (batches, T > 1, 256 threads): the thread's twiddles and the overlap tail live in tensor memory for
+// the T blocks (f13::tm, fcv_fft13.cuh); FCV_INV_TMEM=0 selects the kernel without it.
+template <class SEL, int FMT, bool PF, bool TM = false>
 __global__ void __launch_bounds__(F13_INV_NT, f13_min_ctas(F13_INV_NT))
 inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c2 *sm = reinterpret_cast<c2 *>(smem_raw);
     constexpr int NT = F13_INV_NT;
+    static_assert(!TM || NT == 256, "tensor-memory variant: one column per thread");
     __shared__ float red[NT / 32];
+    __shared__ uint32_t tm_slot;
     constexpr int N = f13::N, M = N;
     pdl_trigger();
     pdl_wait();
@@ -140,6 +144,15 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
     float2 *tail = reinterpret_cast<float2 *>(s.tail + (size_t)o * N);
     const size_t wire = FMT == PCM_S16 ? 2 : 4;
     float lmax = 0.0f;
+    uint32_t tmem = 0;
+    if (TM) {
+        if (tid < 32) f13::tm::alloc(&tm_slot, f13::tm::COLS);
+        f13::tm::fence_before_sync();
+        __syncthreads();
+        f13::tm::fence_after_sync();
+        tmem = f13::tm::thread_base(tm_slot);
+        f13::inv_tm_fill(tmem, tb, tail);
+    }
 
     for (int bt = 0; bt < T; bt++) {
         int frames = fvb - bt * N;
@@ -173,25 +186,39 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
         }
         __syncthreads();
 #else
+        if (TM) {
+            c2 w[16];
+            f13::tm::tm_ld<16>(tmem + f13::tm::TWC, w);   // whole warps, before the entry-0 thread takes its own path
+            if (tid < 128) f13::inv_pass_c_w<0>(sm, yrow, c2_pack(z0.x, z0.y), tid, w);
+            else f13::inv_pass_c_w<1>(sm + f13::HALF_ELEMS, yrow, 0ull, tid - 128, w);
+        } else {
 #pragma unroll 1
-        for (int j = tid; j < 256; j += NT) {
-            if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), j);
-            else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, j - 128);
+            for (int j = tid; j < 256; j += NT) {
+                if (j < 128) f13::inv_pass_c<0>(sm, tb, yrow, c2_pack(z0.x, z0.y), j);
+                else f13::inv_pass_c<1>(sm + f13::HALF_ELEMS, tb, yrow, 0ull, j - 128);
+            }
         }
         __syncthreads();
         f13::pass_b<+1, 2, NT>(sm, tb);
         __syncthreads();
 #endif
         void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * nout * wire;
-        const float m = f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames);
+        const float m = TM ? f13::inv_pass_a_tm<FMT>(sm, tmem, dout, nout, o, frames)
+                           : f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames);
         lmax = fmaxf(lmax, m);
         block_max_update13(s.bmax + bt, m);
         if (bt + 1 < T) __syncthreads();  // shared memory and the tail are reused by the next block
     }
+    if (TM) f13::inv_tm_save_tail(tmem, tail);   // the last block's tail: the next step starts from it
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
     if ((tid & 31) == 0) red[tid >> 5] = lmax;
+    if (TM) f13::tm::fence_before_sync();
     __syncthreads();
+    if (TM && tid < 32) {   // every warp's tensor-memory accesses are complete (their loads wait inside)
+        f13::tm::fence_after_sync();
+        f13::tm::dealloc(tm_slot, f13::tm::COLS);
+    }
     if (tid == 0) {
         for (int w = 1; w < NT / 32; w++) lmax = fmaxf(lmax, red[w]);
         // running maximum is >= 0, positive floats order like their bit patterns
@@ -285,6 +312,10 @@ static int set_attrs13() {
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    if constexpr (!SEL::kSingle && F13_INV_NT == 256) {
+        CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+        CU_TRY(cudaFuncSetAttribute(inv13_stream_kernel<SEL, FMT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    }
     {
         CU_TRY(cudaFuncSetAttribute(inv13_pair_kernel<SEL, FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
         CU_TRY(cudaFuncSetAttribute(inv13_pair_kernel<SEL, FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
@@ -418,6 +449,15 @@ static void launch_inv13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
         if (pf && a.T > 1) inv13_pair_kernel<SEL, FMT, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.T);
         else launch_k(inv13_pair_kernel<SEL, FMT, false>, grid, dim3(256), smem, q, a.pdl, sel, a.f->tb13, a.T);
         return;
+    }
+    // batches with several blocks per step: twiddles and overlap tail in tensor memory (FCV_INV_TMEM=0: off)
+    static const bool use_tm = !(getenv("FCV_INV_TMEM") && atoi(getenv("FCV_INV_TMEM")) == 0);
+    if constexpr (!SEL::kSingle && F13_INV_NT == 256) {
+        if (use_tm && a.T > 1) {
+            if (pf) inv13_stream_kernel<SEL, FMT, true, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
+            else inv13_stream_kernel<SEL, FMT, false, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
+            return;
+        }
     }
     if (pf && a.T > 1) inv13_stream_kernel<SEL, FMT, true><<<grid, F13_INV_NT, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
     else launch_k(inv13_stream_kernel<SEL, FMT, false>, grid, dim3(F13_INV_NT), smem, q, a.pdl, sel, a.f->tb13, a.f->nout, a.T);
