@@ -523,21 +523,49 @@ __device__ __forceinline__ void tm_st<16>(uint32_t taddr, const c2 *v) {
                  : "r"(taddr), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]), "l"(v[4]), "l"(v[5]), "l"(v[6]), "l"(v[7]), "l"(v[8]), "l"(v[9]), "l"(v[10]), "l"(v[11]), "l"(v[12]), "l"(v[13]), "l"(v[14]), "l"(v[15])
                  : "memory");
 }
+// Split form: the load is issued here and its 32 registers may only be touched behind ld_wait32, which names
+// them as read-write operands so that neither nvcc nor ptxas moves a use in front of the wait.
+__device__ __forceinline__ void ld_issue32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ c2 pair_of(const uint32_t (&r)[32], int i) {
+    c2 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(r[2 * i]), "r"(r[2 * i + 1]));
+    return v;
+}
 }  // namespace tm
 
-// Pass C^-1 as inv_pass_c with the repack twiddles handed in (w[k2] = twU[256 k2 + c]; the thread of entry 0,
-// t = 0 of half 0, finds those of its second run in the slots its first run leaves free: w[0] = twU[128],
-// w[8 + k2] = twU[256 k2 + 128], k2 = 1..7 -- inv_fill_twc).
+// Pass C^-1 as inv_pass_c with the repack twiddles coming from tensor memory: wr = the 32 registers of a load
+// issued by the caller (w[k2] = twU[256 k2 + c]; the thread of entry 0, t = 0 of half 0, finds those of its second
+// run in the slots its first run leaves free: w[0] = twU[128], w[8 + k2] = twU[256 k2 + 128], k2 = 1..7 --
+// fill_twc).  Every thread issues the same 32 spectrum loads (entry 0's thread with its own two columns) in front
+// of the wait, which all lanes of a warp must reach together; only then the entry-0 thread takes its own path.
 template <int H>
-__device__ __forceinline__ void inv_pass_c_w(c2 *sm, const float2 *__restrict__ yrow, c2 zc0, int t, const c2 (&w)[16]) {
+__device__ __forceinline__ void inv_pass_c_w(c2 *sm, const float2 *__restrict__ yrow, c2 zc0, int t, uint32_t (&wr)[32]) {
     const float2 *y = yrow + H * Q;
-    if (H == 0 && t == 0) {
-        c2 y1[16], y2[16], v1[16], v2[16];
+    const bool entry0 = H == 0 && t == 0;
+    const int c = t, cc = entry0 ? 128 : (H == 0 ? 256 - t : 255 - t);
+    c2 y1[16], y2[16];
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2++) {
-            y1[k2] = ldg_stream_c2(y + 256 * k2);
-            y2[k2] = ldg_stream_c2(y + 256 * k2 + 128);
-        }
+    for (int k2 = 0; k2 < 16; k2++) {
+        y1[k2] = ldg_stream_c2(y + 256 * k2 + c);
+        y2[k2] = ldg_stream_c2(y + 256 * k2 + cc);
+    }
+    tm::ld_wait32(wr);
+    c2 w[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) w[k2] = tm::pair_of(wr, k2);
+    if (entry0) {
+        c2 v1[16], v2[16];
         v1[0] = zc0;
 #pragma unroll
         for (int k2 = 1; k2 <= 8; k2++) {
@@ -562,18 +590,9 @@ __device__ __forceinline__ void inv_pass_c_w(c2 *sm, const float2 *__restrict__ 
         }
         return;
     }
-    const int c = t, cc = H == 0 ? 256 - t : 255 - t;
     c2 v1[16], v2[16];
-    {
-        c2 y1[16], y2[16];
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2++) {
-            y1[k2] = ldg_stream_c2(y + 256 * k2 + c);
-            y2[k2] = ldg_stream_c2(y + 256 * k2 + cc);
-        }
-#pragma unroll
-        for (int k2 = 0; k2 < 16; k2++) repack_pair(y1[k2], y2[15 - k2], w[k2], v1[k2], v2[15 - k2]);
-    }
+    for (int k2 = 0; k2 < 16; k2++) repack_pair(y1[k2], y2[15 - k2], w[k2], v1[k2], v2[15 - k2]);
     Bfly<16>::template run<+1>(v1);
     Bfly<16>::template run<+1>(v2);
     c2 *p1 = sm + (c & 15) * ROW + (c >> 4) * 16;
@@ -584,50 +603,54 @@ __device__ __forceinline__ void inv_pass_c_w(c2 *sm, const float2 *__restrict__ 
         p2[out16(r)] = v2[r];
     }
 }
-// the w[] of inv_pass_c_w for thread j (0..255: half j / 128, t = j % 128), from the table
-__device__ __forceinline__ void inv_fill_twc(const Tables &tb, int j, c2 (&w)[16]) {
-    const int H = j >> 7, t = j & 127;
+// the w[] of inv_pass_c_w / fwd_pass_c_w for run t (0..127) of half H, from the table
+__device__ __forceinline__ void fill_twc(const Tables &tb, int H, int t, c2 (&w)[16]) {
     const float2 *twu = tb.twU + H * Q;
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) w[k2] = ldg_c2(twu + 256 * k2 + t);
-    if (j == 0) {
+    if (H == 0 && t == 0) {
         w[0] = ldg_c2(twu + 128);
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w[8 + k2] = ldg_c2(twu + 256 * k2 + 128);
     }
 }
+__device__ __forceinline__ void inv_fill_twc(const Tables &tb, int j, c2 (&w)[16]) { fill_twc(tb, j >> 7, j & 127, w); }
 
 // Pass A^-1 as inv_pass_a (256 threads, one column each) with the twiddles and the overlap tail in the thread's
-// tensor-memory words: no table load, no tail load, no tail store.
+// tensor-memory words: no table load, no tail load, no tail store.  The tensor-memory loads are issued one
+// phase ahead of their use (the first twiddles while shared memory is read, the tail in front of the
+// butterflies); the tail store stays in flight until the next block's tail load (wait_st in front of it).
 template <int FMT>
 __device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void *dout, int nout, int o, int frames) {
     float lmax = 0.0f;
     const int u = threadIdx.x;
+    uint32_t wr[32];
+    tm::ld_issue32(tmem + tm::TWA, wr);
     c2 va[16], vb[16];
 #pragma unroll
     for (int k0 = 0; k0 < 16; k0++) {
         va[k0] = sm[k0 * ROW + u];
         vb[k0] = sm[HALF_ELEMS + k0 * ROW + u];
     }
-    {
-        c2 w[16];
-        tm::tm_ld<16>(tmem + tm::TWA, w);
+    tm::ld_wait32(wr);
 #pragma unroll
-        for (int k0 = 1; k0 < 16; k0++) va[k0] = c2_cmulconj(va[k0], w[k0]);
-        tm::tm_ld<16>(tmem + tm::TWA + 32, w);
+    for (int k0 = 1; k0 < 16; k0++) va[k0] = c2_cmulconj(va[k0], tm::pair_of(wr, k0));
+    tm::ld_issue32(tmem + tm::TWA + 32, wr);
+    tm::ld_wait32(wr);
 #pragma unroll
-        for (int k0 = 0; k0 < 16; k0++) vb[k0] = c2_cmulconj(vb[k0], w[k0]);
-    }
+    for (int k0 = 0; k0 < 16; k0++) vb[k0] = c2_cmulconj(vb[k0], tm::pair_of(wr, k0));
+    tm::wait_st();   // the previous block's tail store (or the fill)
+    tm::ld_issue32(tmem + tm::TAIL, wr);
     Bfly<16>::template run<+1>(va);
     Bfly<16>::template run<+1>(vb);
+    tm::ld_wait32(wr);
     c2 tl[16];
-    tm::tm_ld<16>(tmem + tm::TAIL, tl);
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const int n2 = out16(r), n = u + 256 * n2;
         const c2 b = n2 == 0 ? vb[r] : c2_cmulconj(vb[r], c2_pack(w32(n2)));
         const float2 s = c2_unpack(c2_add(va[r], b));
-        const float2 t = c2_unpack(tl[r]);
+        const float2 t = c2_unpack(tm::pair_of(wr, r));
         const float y0 = s.x + t.x, y1 = s.y + t.y;
         tl[r] = c2_sub(va[r], b);
         const int f0 = 2 * n;
@@ -637,7 +660,6 @@ __device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void
         if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
     }
     tm::tm_st<16>(tmem + tm::TAIL, tl);
-    tm::wait_st();
     return lmax;
 }
 // the thread's words: tail from / to global memory (first / behind the last block), twiddles from the tables
@@ -664,9 +686,151 @@ __device__ __forceinline__ void inv_tm_fill(uint32_t tmem, const Tables &tb, con
 __device__ __forceinline__ void inv_tm_save_tail(uint32_t tmem, float2 *__restrict__ tail) {
     const int u = threadIdx.x;
     c2 v[16];
+    tm::wait_st();
     tm::tm_ld<16>(tmem + tm::TAIL, v);
 #pragma unroll
     for (int r = 0; r < 16; r++) tail[u + 256 * out16(r)] = c2_unpack(v[r]);
+}
+
+
+// ---- forward transform with the thread's twiddles in tensor memory -----------------------------
+// Stereo blocks of a batch: one CTA = one half of both channels' spectra of ONE stream for the T blocks of
+// the step (the kernel without it: one CTA per block).  47 of a thread's 63 global loads per block are
+// twiddles that do not change from block to block: pass A 16 (slot k0), pass B 15 (slot k1), unpack 16
+// (slot k2, as in the inverse kernel) -- 96 words of the thread's 128.
+namespace tm {
+constexpr uint32_t F_TWA = 0, F_TWB = 32, F_TWC = 64;
+}
+template <int H>
+__device__ __forceinline__ void fwd_tm_fill(uint32_t tmem, const Tables &tb) {
+    const int u = threadIdx.x;
+    c2 v[16];
+    v[0] = 0ull;
+    if (H == 0) {
+#pragma unroll
+        for (int k0 = 1; k0 < 16; k0++) v[k0] = ldg_c2(tb.twA0 + (k0 - 1) * 256 + u);
+    } else {
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++) v[k0] = ldg_c2(tb.twA1 + k0 * 256 + u);
+    }
+    tm::tm_st<16>(tmem + tm::F_TWA, v);
+    v[0] = 0ull;
+#pragma unroll
+    for (int k1 = 1; k1 < 16; k1++) v[k1] = ldg_c2(tb.twB + (u >> 4) * 16 + k1);
+    tm::tm_st<16>(tmem + tm::F_TWB, v);
+    fill_twc(tb, H, u & 127, v);
+    tm::tm_st<16>(tmem + tm::F_TWC, v);
+    tm::wait_st();
+}
+// fwd_half<H, FMT, 2, 2, 256> with every table value from the thread's tensor-memory words
+template <int H, int FMT>
+__device__ __forceinline__ void fwd_half_tm(c2 *sm, uint32_t tmem, const void *in, int fv, float2 *const (&rows)[2]) {
+    const int u = threadIdx.x;
+    {   // pass A
+        c2 v[2][16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            c2 z[2];
+            load_z<FMT, 2, 2>(in, 2, 0, u + 256 * j, fv, z);
+            v[0][j] = z[0];
+            v[1][j] = z[1];
+        }
+        c2 w[16];
+        tm::tm_ld<16>(tmem + tm::F_TWA, w);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            if (H == 1) {
+#pragma unroll
+                for (int j = 1; j < 16; j++) v[c][j] = c2_cmul(v[c][j], c2_pack(w32(j)));
+            }
+            Bfly<16>::template run<-1>(v[c]);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k0 = out16(r);
+                c2 x = v[c][r];
+                if (H == 1 || k0 > 0) x = c2_cmul(x, w[k0]);
+                sm[c * HALF_ELEMS + k0 * ROW + u] = x;
+            }
+        }
+    }
+    __syncthreads();
+    {   // pass B
+        const int k0 = u & 15, n0 = u >> 4;
+        c2 w[16];
+        tm::tm_ld<16>(tmem + tm::F_TWB, w);
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            c2 *p = sm + a * HALF_ELEMS + k0 * ROW + n0;
+            c2 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = p[16 * j];
+            Bfly<16>::template run<-1>(v);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k = out16(r);
+                c2 x = v[r];
+                if (k > 0) x = c2_cmul(x, w[k]);
+                p[16 * k] = x;
+            }
+        }
+    }
+    __syncthreads();
+    {   // pass C + unpack: thread u = run t = u % 128 of channel u / 128
+        c2 w[16];
+        tm::tm_ld<16>(tmem + tm::F_TWC, w);   // whole warps, before the entry-0 threads take their own path
+        const c2 *smc = sm + (u >> 7) * HALF_ELEMS;
+        c2 *out = reinterpret_cast<c2 *>(rows[u >> 7]) + H * Q;
+        const int t = u & 127;
+        if (H == 0 && t == 0) {
+            c2 v1[16], v2[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                v1[j] = smc[j];
+                v2[j] = smc[16 * 8 + j];
+            }
+            Bfly<16>::template run<-1>(v1);
+            Bfly<16>::template run<-1>(v2);
+            {
+                const float2 z0 = c2_unpack(v1[reg16(0)]);
+                out[0] = c2_pack(z0.x + z0.y, z0.x - z0.y);  // DC, Nyquist
+            }
+#pragma unroll
+            for (int k2 = 1; k2 <= 8; k2++) {
+                c2 xk, xp;
+                unpack_pair(v1[reg16(k2)], v1[reg16(16 - k2)], w[k2], xk, xp);
+                out[256 * k2] = xk;
+                if (k2 != 8) out[256 * (16 - k2)] = xp;
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++) {
+                c2 xk, xp;
+                unpack_pair(v2[reg16(k2)], v2[reg16(15 - k2)], k2 == 0 ? w[0] : w[8 + k2], xk, xp);
+                out[256 * k2 + 128] = xk;
+                out[256 * (15 - k2) + 128] = xp;
+            }
+        } else {
+            const int c = t, cc = H == 0 ? 256 - t : 255 - t;
+            c2 v1[16], v2[16];
+            {
+                const c2 *p1 = smc + (c & 15) * ROW + (c >> 4) * 16;
+                const c2 *p2 = smc + (cc & 15) * ROW + (cc >> 4) * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    v1[j] = p1[j];
+                    v2[j] = p2[j];
+                }
+            }
+            Bfly<16>::template run<-1>(v1);
+            Bfly<16>::template run<-1>(v2);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                c2 xk, xp;
+                unpack_pair(v1[reg16(k2)], v2[reg16(15 - k2)], w[k2], xk, xp);
+                out[256 * k2 + c] = xk;
+                out[256 * (15 - k2) + cc] = xp;
+            }
+        }
+    }
 }
 
 

@@ -62,6 +62,60 @@ fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, i
     else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
 }
 
+// Stereo blocks of a batch with several blocks per step: one CTA = one half of both channels' spectra of one
+// stream for all T blocks, the thread's 47 twiddles in tensor memory (f13::fwd_half_tm).  Bit-identical and measured 6 % SLOWER than
+// one CTA per block (0.417 against 0.394 ms, profiles/r02_experiments.md): an experiment, FCV_FWD_TMEM=1 only.
+template <class SEL, int FMT>
+__global__ void __launch_bounds__(256, 2)
+fwd13_tm_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int R, int T, int reset_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c2 *sm = reinterpret_cast<c2 *>(smem_raw);
+    __shared__ uint32_t tm_slot;
+    constexpr int N = f13::N;
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int h = blockIdx.x, b = blockIdx.y;   // gridDim.x == 2
+    if (tid < 32) f13::tm::alloc(&tm_slot, f13::tm::COLS);
+    f13::tm::fence_before_sync();
+    __syncthreads();
+    f13::tm::fence_after_sync();
+    const uint32_t tmem = f13::tm::thread_base(tm_slot);
+    if (h == 0) f13::fwd_tm_fill<0>(tmem, tb);
+    else f13::fwd_tm_fill<1>(tmem, tb);
+    const int fvb = sel.frames(b), slot0 = sel.slot(b);
+    float2 *const xring = sel.xring(b);
+    const size_t wire = FMT == PCM_S16 ? 2 : 4;
+    if (h == 0 && tid == 0) {   // the only thread that needs the stream's descriptor
+        const StreamDev s = sel.stream(b);
+        if (reset_max) *s.maxv = 0.0f;   // per-block maximum mode: the inverse kernel of this step starts from zero
+        for (int bt = 0; bt < T; bt++) s.bmax[bt] = 0.0f;   // every block's maximum starts from zero
+    }
+    for (int bt = 0; bt < T; bt++) {
+        int frames = fvb - bt * N;
+        frames = frames < 0 ? 0 : (frames > N ? N : frames);
+        int slot = slot0 + bt;
+        if (slot >= R) slot -= R;
+        float2 *rows[2] = {xring + (size_t)(0 * R + slot) * N, xring + (size_t)(1 * R + slot) * N};
+        if (frames == 0) {  // silence: its spectrum is zero
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+                for (int e = tid; e < f13::Q; e += 256) rows[c][h * f13::Q + e] = make_float2(0.f, 0.f);
+            continue;
+        }
+        const void *in = reinterpret_cast<const char *>(sel.din(b)) + (size_t)bt * N * 2 * wire;
+        if (h == 0) f13::fwd_half_tm<0, FMT>(sm, tmem, in, frames, rows);
+        else f13::fwd_half_tm<1, FMT>(sm, tmem, in, frames, rows);
+        __syncthreads();   // shared memory is written again by the next block's pass A
+    }
+    f13::tm::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) {
+        f13::tm::fence_after_sync();
+        f13::tm::dealloc(tm_slot, f13::tm::COLS);
+    }
+}
+
 // The same for the stereo blocks of the per-file path as a cluster of the two halves' CTAs that reads the
 // caller's block ONCE (f13::stage_half / fwd_pass_a_staged): half the bytes over the link.
 template <class SEL, int FMT>
@@ -187,10 +241,10 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
         __syncthreads();
 #else
         if (TM) {
-            c2 w[16];
-            f13::tm::tm_ld<16>(tmem + f13::tm::TWC, w);   // whole warps, before the entry-0 thread takes its own path
-            if (tid < 128) f13::inv_pass_c_w<0>(sm, yrow, c2_pack(z0.x, z0.y), tid, w);
-            else f13::inv_pass_c_w<1>(sm + f13::HALF_ELEMS, yrow, 0ull, tid - 128, w);
+            uint32_t wr[32];
+            f13::tm::ld_issue32(tmem + f13::tm::TWC, wr);   // waited for inside, behind the spectrum loads
+            if (tid < 128) f13::inv_pass_c_w<0>(sm, yrow, c2_pack(z0.x, z0.y), tid, wr);
+            else f13::inv_pass_c_w<1>(sm + f13::HALF_ELEMS, yrow, 0ull, tid - 128, wr);
         } else {
 #pragma unroll 1
             for (int j = tid; j < 256; j += NT) {
@@ -304,6 +358,8 @@ template <class SEL, int FMT>
 static int set_attrs13() {
     const int one = (int)f13::HALF_BYTES, two = 2 * (int)f13::HALF_BYTES;
     CU_TRY(cudaFuncSetAttribute(fwd13_stream_kernel<SEL, FMT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+    if constexpr (!SEL::kSingle)
+        CU_TRY(cudaFuncSetAttribute(fwd13_tm_kernel<SEL, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
     if constexpr (SEL::kSingle)
         CU_TRY(cudaFuncSetAttribute(fwd13_pair_kernel<SEL, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     two + (int)f13::STAGE_BYTES_MAX));
@@ -399,6 +455,15 @@ static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
         if (f->ninp == 2 && fwd_pair) {
             launch_k(fwd13_pair_kernel<SEL, FMT>, dim3(2, a.cnt, a.T), dim3(256), 2 * f13::HALF_BYTES + f13::STAGE_BYTES_MAX,
                      q, a.pdl, sel, f->tb13, a.R, a.T, rm);
+            return;
+        }
+    }
+    // batches of stereo blocks with several blocks per step: one CTA per (half, stream), twiddles in tensor memory
+    // (experiment, off: slower)
+    static const bool fwd_tm = getenv("FCV_FWD_TMEM") && atoi(getenv("FCV_FWD_TMEM")) != 0;
+    if constexpr (!SEL::kSingle) {
+        if (f->ninp == 2 && a.T > 1 && fwd_tm) {
+            fwd13_tm_kernel<SEL, FMT><<<dim3(2, a.cnt), 256, 2 * f13::HALF_BYTES, q>>>(sel, f->tb13, a.R, a.T, rm);
             return;
         }
     }
