@@ -722,11 +722,14 @@ __device__ __forceinline__ void fwd_tm_fill(uint32_t tmem, const Tables &tb) {
     tm::tm_st<16>(tmem + tm::F_TWC, v);
     tm::wait_st();
 }
-// fwd_half<H, FMT, 2, 2, 256> with every table value from the thread's tensor-memory words
+// fwd_half<H, FMT, 2, 2, 256> with every table value from the thread's tensor-memory words; each load is issued
+// in front of the phase's global / shared loads and waited for behind them.
 template <int H, int FMT>
 __device__ __forceinline__ void fwd_half_tm(c2 *sm, uint32_t tmem, const void *in, int fv, float2 *const (&rows)[2]) {
     const int u = threadIdx.x;
+    uint32_t wr[32];
     {   // pass A
+        tm::ld_issue32(tmem + tm::F_TWA, wr);
         c2 v[2][16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -735,8 +738,7 @@ __device__ __forceinline__ void fwd_half_tm(c2 *sm, uint32_t tmem, const void *i
             v[0][j] = z[0];
             v[1][j] = z[1];
         }
-        c2 w[16];
-        tm::tm_ld<16>(tmem + tm::F_TWA, w);
+        tm::ld_wait32(wr);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             if (H == 1) {
@@ -748,48 +750,60 @@ __device__ __forceinline__ void fwd_half_tm(c2 *sm, uint32_t tmem, const void *i
             for (int r = 0; r < 16; r++) {
                 const int k0 = out16(r);
                 c2 x = v[c][r];
-                if (H == 1 || k0 > 0) x = c2_cmul(x, w[k0]);
+                if (H == 1 || k0 > 0) x = c2_cmul(x, tm::pair_of(wr, k0));
                 sm[c * HALF_ELEMS + k0 * ROW + u] = x;
             }
         }
     }
+    tm::ld_issue32(tmem + tm::F_TWB, wr);
     __syncthreads();
     {   // pass B
         const int k0 = u & 15, n0 = u >> 4;
-        c2 w[16];
-        tm::tm_ld<16>(tmem + tm::F_TWB, w);
+        c2 *p = sm + k0 * ROW + n0;
+        c2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = p[16 * j];
+        tm::ld_wait32(wr);
 #pragma unroll
         for (int a = 0; a < 2; a++) {
-            c2 *p = sm + a * HALF_ELEMS + k0 * ROW + n0;
-            c2 v[16];
+            if (a) {
+                p += HALF_ELEMS;
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = p[16 * j];
+                for (int j = 0; j < 16; j++) v[j] = p[16 * j];
+            }
             Bfly<16>::template run<-1>(v);
 #pragma unroll
             for (int r = 0; r < 16; r++) {
                 const int k = out16(r);
                 c2 x = v[r];
-                if (k > 0) x = c2_cmul(x, w[k]);
+                if (k > 0) x = c2_cmul(x, tm::pair_of(wr, k));
                 p[16 * k] = x;
             }
         }
     }
+    tm::ld_issue32(tmem + tm::F_TWC, wr);
     __syncthreads();
-    {   // pass C + unpack: thread u = run t = u % 128 of channel u / 128
-        c2 w[16];
-        tm::tm_ld<16>(tmem + tm::F_TWC, w);   // whole warps, before the entry-0 threads take their own path
+    {   // pass C + unpack: thread u = run t = u % 128 of channel u / 128; the entry-0 threads (t = 0 of half 0)
+        // read their own two runs with the same code and leave the common path behind the wait
         const c2 *smc = sm + (u >> 7) * HALF_ELEMS;
         c2 *out = reinterpret_cast<c2 *>(rows[u >> 7]) + H * Q;
         const int t = u & 127;
-        if (H == 0 && t == 0) {
-            c2 v1[16], v2[16];
+        const bool entry0 = H == 0 && t == 0;
+        const int c = t, cc = entry0 ? 128 : (H == 0 ? 256 - t : 255 - t);
+        c2 v1[16], v2[16];
+        {
+            const c2 *p1 = smc + (c & 15) * ROW + (c >> 4) * 16;
+            const c2 *p2 = smc + (cc & 15) * ROW + (cc >> 4) * 16;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                v1[j] = smc[j];
-                v2[j] = smc[16 * 8 + j];
+                v1[j] = p1[j];
+                v2[j] = p2[j];
             }
-            Bfly<16>::template run<-1>(v1);
-            Bfly<16>::template run<-1>(v2);
+        }
+        Bfly<16>::template run<-1>(v1);
+        Bfly<16>::template run<-1>(v2);
+        tm::ld_wait32(wr);
+        if (entry0) {
             {
                 const float2 z0 = c2_unpack(v1[reg16(0)]);
                 out[0] = c2_pack(z0.x + z0.y, z0.x - z0.y);  // DC, Nyquist
@@ -797,35 +811,22 @@ __device__ __forceinline__ void fwd_half_tm(c2 *sm, uint32_t tmem, const void *i
 #pragma unroll
             for (int k2 = 1; k2 <= 8; k2++) {
                 c2 xk, xp;
-                unpack_pair(v1[reg16(k2)], v1[reg16(16 - k2)], w[k2], xk, xp);
+                unpack_pair(v1[reg16(k2)], v1[reg16(16 - k2)], tm::pair_of(wr, k2), xk, xp);
                 out[256 * k2] = xk;
                 if (k2 != 8) out[256 * (16 - k2)] = xp;
             }
 #pragma unroll
             for (int k2 = 0; k2 < 8; k2++) {
                 c2 xk, xp;
-                unpack_pair(v2[reg16(k2)], v2[reg16(15 - k2)], k2 == 0 ? w[0] : w[8 + k2], xk, xp);
+                unpack_pair(v2[reg16(k2)], v2[reg16(15 - k2)], tm::pair_of(wr, k2 == 0 ? 0 : 8 + k2), xk, xp);
                 out[256 * k2 + 128] = xk;
                 out[256 * (15 - k2) + 128] = xp;
             }
         } else {
-            const int c = t, cc = H == 0 ? 256 - t : 255 - t;
-            c2 v1[16], v2[16];
-            {
-                const c2 *p1 = smc + (c & 15) * ROW + (c >> 4) * 16;
-                const c2 *p2 = smc + (cc & 15) * ROW + (cc >> 4) * 16;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    v1[j] = p1[j];
-                    v2[j] = p2[j];
-                }
-            }
-            Bfly<16>::template run<-1>(v1);
-            Bfly<16>::template run<-1>(v2);
 #pragma unroll
             for (int k2 = 0; k2 < 16; k2++) {
                 c2 xk, xp;
-                unpack_pair(v1[reg16(k2)], v2[reg16(15 - k2)], w[k2], xk, xp);
+                unpack_pair(v1[reg16(k2)], v2[reg16(15 - k2)], tm::pair_of(wr, k2), xk, xp);
                 out[256 * k2 + c] = xk;
                 out[256 * (15 - k2) + cc] = xp;
             }
