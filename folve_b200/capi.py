@@ -122,6 +122,8 @@ def lib() -> C.CDLL:
         "fcv_debug_set_fused": (None, [i]),
         "fcv_debug_fused_launches": (C.c_ulonglong, []),
         "fcv_debug_set_inv_pair": (None, [i]),
+        "fcv_debug_set_tmem": (None, [i]),
+        "fcv_debug_get_tmem": (i, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

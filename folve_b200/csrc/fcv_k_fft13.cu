@@ -442,6 +442,16 @@ void fcv::launch_filter_fft13(const fcv_filter *f, const float *dsrc, float2 *ds
     fwd13_raw_kernel<<<dim3(2, nrows), 128, f13::HALF_BYTES>>>(dsrc, dst, f->tb13);
 }
 
+// Tensor-memory variants (f13::tm): the inverse kernel of a batch uses it by default (FCV_INV_TMEM=0: off), the
+// forward kernel's stays an experiment (FCV_FWD_TMEM=1).  fcv_debug_set_tmem: bit 0 inverse, bit 1 forward (tests).
+static std::atomic<bool> g_inv_tmem{!(getenv("FCV_INV_TMEM") && atoi(getenv("FCV_INV_TMEM")) == 0)};
+static std::atomic<bool> g_fwd_tmem{getenv("FCV_FWD_TMEM") && atoi(getenv("FCV_FWD_TMEM")) != 0};
+extern "C" void fcv_debug_set_tmem(int mask) {
+    g_inv_tmem.store((mask & 1) != 0);
+    g_fwd_tmem.store((mask & 2) != 0);
+}
+extern "C" int fcv_debug_get_tmem(void) { return (g_inv_tmem.load() ? 1 : 0) | (g_fwd_tmem.load() ? 2 : 0); }
+
 // ---- launches -------------------------------------------------------------------------------
 // Stereo and mono blocks take the vector-load kernels (stereo: both channels per CTA), any other
 // channel count scalar loads: two channels per CTA when the count is even, else one.
@@ -460,7 +470,7 @@ static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
     }
     // batches of stereo blocks with several blocks per step: one CTA per (half, stream), twiddles in tensor memory
     // (experiment, off: slower)
-    static const bool fwd_tm = getenv("FCV_FWD_TMEM") && atoi(getenv("FCV_FWD_TMEM")) != 0;
+    const bool fwd_tm = g_fwd_tmem.load(std::memory_order_relaxed);
     if constexpr (!SEL::kSingle) {
         if (f->ninp == 2 && a.T > 1 && fwd_tm) {
             fwd13_tm_kernel<SEL, FMT><<<dim3(2, a.cnt), 256, 2 * f13::HALF_BYTES, q>>>(sel, f->tb13, a.R, a.T, rm);
@@ -516,7 +526,7 @@ static void launch_inv13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
         return;
     }
     // batches with several blocks per step: twiddles and overlap tail in tensor memory (FCV_INV_TMEM=0: off)
-    static const bool use_tm = !(getenv("FCV_INV_TMEM") && atoi(getenv("FCV_INV_TMEM")) == 0);
+    const bool use_tm = g_inv_tmem.load(std::memory_order_relaxed);
     if constexpr (!SEL::kSingle && F13_INV_NT == 256) {
         if (use_tm && a.T > 1) {
             if (pf) inv13_stream_kernel<SEL, FMT, true, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);

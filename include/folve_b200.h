@@ -305,6 +305,13 @@ unsigned long long fcv_debug_fused_launches(void);
  * go straight to the caller's pinned block (also FCV_INV_PAIR_SINGLE=1).  Results are identical; the
  * pair is not faster on either path. */
 void fcv_debug_set_inv_pair(int mask);
+/* Process-wide switch of the tensor-memory variants of the fragm 8192 transforms of a batch with several
+ * blocks per step (a thread's twiddles -- and the inverse transform's overlap tail -- kept in the SM's
+ * tensor memory across the blocks of a step instead of being re-read from global memory in every block).
+ * mask bit 0: inverse transform (on by default; FCV_INV_TMEM=0 turns it off), bit 1: forward transform of
+ * stereo blocks (off by default: measured slower; FCV_FWD_TMEM=1).  Results are bit-identical either way. */
+void fcv_debug_set_tmem(int mask);
+int fcv_debug_get_tmem(void);
 
 #ifdef __cplusplus
 }

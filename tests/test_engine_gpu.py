@@ -331,6 +331,51 @@ def test_stereo_pair_inverse_kernel_is_bit_identical(fmt):
     f.close()
 
 
+@pytest.mark.parametrize("fmt", ["f32", "s16", "s24"])
+def test_tensor_memory_transform_kernels_are_bit_identical(fmt):
+    """Batches with several blocks per step: the inverse transform that keeps each thread's twiddles and the
+    overlap tail in tensor memory (default) and the forward transform that does so with its twiddles (an
+    experiment that stays off) give the same bits as the kernels that re-read them from global memory
+    (fcv_debug_set_tmem): block contents, running maximum, per-block maxima; stereo and 3 -> 2 channels,
+    T = 2 and 8, short steps, silence, several steps (the tail is carried from step to step)."""
+    r = _rng(78)
+    L = capi.lib()
+    pcm = {"f32": capi.PCM_F32, "s16": capi.PCM_S16, "s24": capi.PCM_S24}[fmt]
+    before = L.fcv_debug_get_tmem()
+    for nin, nout in ((2, 2), (3, 2)):
+        spec = FilterSpec(nin, nout, 40000)
+        spec.add(0, 0, r.standard_normal(40000) * 0.004, 100).add(1, 1, r.standard_normal(30000) * 0.004, 0)
+        spec.add(nin - 1, 0, r.standard_normal(5000) * 0.004, 9000)
+        f = _engine(spec)
+        N, B = spec.fragm, 7
+        for T in (2, 8):
+            x = r.uniform(-0.3, 0.3, (3, B, T * N, nin))
+            xin = (x.astype(np.float32) if fmt == "f32" else
+                   np.rint(x * (20000 if fmt == "s16" else 5000000)).astype(np.int16 if fmt == "s16" else np.int32))
+            fv = np.array([T * N, 1, N - 1, N, T * N - 3, 0, 5000][:B], np.int32)
+            outs = []
+            for mask in (0, 1, 3):
+                L.fcv_debug_set_tmem(mask)
+                try:
+                    bt = capi.Batch(f, B, pcm, pcm, blocks_per_step=T)
+                    got = []
+                    for k in range(3):
+                        bt.host_in[:] = xin[k]
+                        bt.process(fv if k == 1 else None)
+                        got.append(bt.host_out.copy())
+                    got.append(bt.get_max().copy())
+                    got.append(bt.get_block_max().copy())
+                    bt.close()
+                    outs.append(got)
+                finally:
+                    L.fcv_debug_set_tmem(before)
+            for other in outs[1:]:
+                for a, c in zip(outs[0], other):
+                    assert np.array_equal(a, c)
+        f.close()
+    assert L.fcv_debug_get_tmem() == before
+
+
 @pytest.mark.parametrize("nin,nout,T,size", [(1, 1, 4, 30000), (3, 2, 4, 30000), (1, 2, 8, 30000), (6, 6, 2, 30000),
                                              (3, 2, 8, 30000), (6, 6, 8, 30000), (2, 2, 8, 110000), (2, 3, 4, 110000)])
 def test_time_tiled_other_channel_counts_and_s24(nin, nout, T, size):
