@@ -425,6 +425,16 @@ __device__ __forceinline__ void inv_pass_c(c2 *sm, const Tables &tb, const float
     }
 }
 
+// pcm_store at a byte address.  The epilogues below address a thread's samples as
+// base + (512 n2) * frame_bytes (+ frame_bytes) with compile-time n2: one IMAD.WIDE per pair instead of the
+// 64-bit (2n * nout + o) * width chain per sample (14 -> 3 address instructions per pair of samples).
+template <int FMT>
+__device__ __forceinline__ void pcm_store_b(char *p, float v) {
+    if (FMT == PCM_F32) *reinterpret_cast<float *>(p) = v;
+    else if (FMT == PCM_S16) *reinterpret_cast<short *>(p) = (short)__float2int_rn(v * 32767.0f);
+    else *reinterpret_cast<int *>(p) = __float2int_rn(v * 8388607.0f);
+}
+
 // Pass A^-1 of both halves + overlap-add, tail save, re-interleave, float -> PCM and the
 // signed maximum of the valid frames (sound-processor.cc:115-125), all from registers.
 // sm: [2][HALF_ELEMS] (half 0, half 1).  Returns this thread's maximum.
@@ -432,8 +442,10 @@ template <int FMT, int NT>
 __device__ __forceinline__ float inv_pass_a(const c2 *sm, const Tables &tb, float2 *__restrict__ tail, void *dout,
                                             int nout, int o, int frames) {
     float lmax = 0.0f;
+    const uint32_t fbytes = (uint32_t)nout * (FMT == PCM_S16 ? 2u : 4u);   // bytes per frame
 #pragma unroll 1
     for (int u = threadIdx.x; u < 256; u += NT) {
+        char *const pbase = reinterpret_cast<char *>(dout) + (size_t)(2 * u) * fbytes + (size_t)o * (FMT == PCM_S16 ? 2 : 4);
         c2 va[16], vb[16];
 #pragma unroll
         for (int k0 = 0; k0 < 16; k0++) {
@@ -458,8 +470,9 @@ __device__ __forceinline__ float inv_pass_a(const c2 *sm, const Tables &tb, floa
             const float y0 = s.x + tl[r].x, y1 = s.y + tl[r].y;
             tail[n] = d;
             const int f0 = 2 * n;
-            pcm_store<FMT>(dout, (size_t)f0 * nout + o, y0);
-            pcm_store<FMT>(dout, (size_t)(f0 + 1) * nout + o, y1);
+            char *p = pbase + (size_t)((uint32_t)(512 * n2) * fbytes);
+            pcm_store_b<FMT>(p, y0);
+            pcm_store_b<FMT>(p + fbytes, y1);
             if (f0 < frames) lmax = fmaxf(lmax, y0);
             if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
         }
@@ -624,6 +637,8 @@ template <int FMT>
 __device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void *dout, int nout, int o, int frames) {
     float lmax = 0.0f;
     const int u = threadIdx.x;
+    const uint32_t fbytes = (uint32_t)nout * (FMT == PCM_S16 ? 2u : 4u);   // bytes per frame
+    char *const pbase = reinterpret_cast<char *>(dout) + (size_t)(2 * u) * fbytes + (size_t)o * (FMT == PCM_S16 ? 2 : 4);
     uint32_t wr[32];
     tm::ld_issue32(tmem + tm::TWA, wr);
     c2 va[16], vb[16];
@@ -654,8 +669,9 @@ __device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void
         const float y0 = s.x + t.x, y1 = s.y + t.y;
         tl[r] = c2_sub(va[r], b);
         const int f0 = 2 * n;
-        pcm_store<FMT>(dout, (size_t)f0 * nout + o, y0);
-        pcm_store<FMT>(dout, (size_t)(f0 + 1) * nout + o, y1);
+        char *p = pbase + (size_t)((uint32_t)(512 * n2) * fbytes);
+        pcm_store_b<FMT>(p, y0);
+        pcm_store_b<FMT>(p + fbytes, y1);
         if (f0 < frames) lmax = fmaxf(lmax, y0);
         if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
     }
