@@ -33,6 +33,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fcv_c2.cuh"
 #include "fcv_fft.cuh"
 
@@ -119,7 +121,8 @@ __device__ __forceinline__ void raw_to_pairs(uint4 r, float2 &left, float2 &righ
 // z[n] = (x[2n], x[2n+1]) of C consecutive channels starting at ch0, frames >= fv read as 0.
 // NCH = 2: stereo block and both channels wanted (one vector load); NCH = 1: mono block;
 // NCH = 0: any layout, scalar loads.
-template <int FMT, int NCH, int C>
+// FULL: every frame of the block is valid (fv == N): no zeroing.
+template <int FMT, int NCH, int C, bool FULL = false>
 __device__ __forceinline__ void load_z(const void *in, int nchan, int ch0, int n, int fv, c2 (&z)[C]) {
     float2 v[C];
     if (NCH == 2 && C == 2) {
@@ -139,15 +142,17 @@ __device__ __forceinline__ void load_z(const void *in, int nchan, int ch0, int n
     }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        if (2 * n >= fv) v[c].x = 0.0f;
-        if (2 * n + 1 >= fv) v[c].y = 0.0f;
+        if (!FULL) {
+            if (2 * n >= fv) v[c].x = 0.0f;
+            if (2 * n + 1 >= fv) v[c].y = 0.0f;
+        }
         z[c] = c2_pack(v[c].x, v[c].y);
     }
 }
 
 // ---- forward ---------------------------------------------------------------------------
 // Pass A of half H for C channels: global PCM -> registers -> shared row k0.
-template <int H, int FMT, int NCH, int C, int NT>
+template <int H, int FMT, int NCH, int C, int NT, bool FULL = false>
 __device__ __forceinline__ void fwd_pass_a(c2 *sm, const Tables &tb, const void *in, int nchan, int ch0, int fv) {
 #pragma unroll 1
     for (int u = threadIdx.x; u < 256; u += NT) {
@@ -155,7 +160,7 @@ __device__ __forceinline__ void fwd_pass_a(c2 *sm, const Tables &tb, const void 
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             c2 z[C];
-            load_z<FMT, NCH, C>(in, nchan, ch0, u + 256 * j, fv, z);
+            load_z<FMT, NCH, C, FULL>(in, nchan, ch0, u + 256 * j, fv, z);
 #pragma unroll
             for (int c = 0; c < C; c++) v[c][j] = z[c];
         }
@@ -327,8 +332,10 @@ __device__ __forceinline__ void fwd_pass_c(const c2 *sm, const Tables &tb, float
 // NT = 128 * C threads: pass A one u per thread (C = 2) or two (C = 1), pass C one job per thread.
 template <int H, int FMT, int NCH, int C, int NT>
 __device__ __forceinline__ void fwd_half(c2 *sm, const Tables &tb, const void *in, int nchan, int ch0, int fv,
-                                         float2 *const (&rows)[C]) {
-    fwd_pass_a<H, FMT, NCH, C, NT>(sm, tb, in, nchan, ch0, fv);
+                                         float2 *const (&rows)[C], bool full_path = false) {
+    // a whole block (the usual case) takes pass A without the per-sample zeroing (32 ISETP + 64 FSEL per thread)
+    if (full_path && fv >= N) fwd_pass_a<H, FMT, NCH, C, NT, true>(sm, tb, in, nchan, ch0, fv);
+    else fwd_pass_a<H, FMT, NCH, C, NT>(sm, tb, in, nchan, ch0, fv);
     __syncthreads();
     pass_b<-1, C, NT>(sm, tb);
     __syncthreads();
@@ -634,7 +641,8 @@ __device__ __forceinline__ void inv_fill_twc(const Tables &tb, int j, c2 (&w)[16
 // phase ahead of their use (the first twiddles while shared memory is read, the tail in front of the
 // butterflies); the tail store stays in flight until the next block's tail load (wait_st in front of it).
 template <int FMT>
-__device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void *dout, int nout, int o, int frames) {
+__device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void *dout, int nout, int o, int frames,
+                                               bool full_path = false) {
     float lmax = 0.0f;
     const int u = threadIdx.x;
     const uint32_t fbytes = (uint32_t)nout * (FMT == PCM_S16 ? 2u : 4u);   // bytes per frame
@@ -660,21 +668,27 @@ __device__ __forceinline__ float inv_pass_a_tm(const c2 *sm, uint32_t tmem, void
     Bfly<16>::template run<+1>(vb);
     tm::ld_wait32(wr);
     c2 tl[16];
+    // FULL: every frame of the block counts for the maximum (a whole block, the usual case): no per-sample test
+    auto epilogue = [&](auto full) {
+        constexpr bool FULL = decltype(full)::value;
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int n2 = out16(r), n = u + 256 * n2;
-        const c2 b = n2 == 0 ? vb[r] : c2_cmulconj(vb[r], c2_pack(w32(n2)));
-        const float2 s = c2_unpack(c2_add(va[r], b));
-        const float2 t = c2_unpack(tm::pair_of(wr, r));
-        const float y0 = s.x + t.x, y1 = s.y + t.y;
-        tl[r] = c2_sub(va[r], b);
-        const int f0 = 2 * n;
-        char *p = pbase + (size_t)((uint32_t)(512 * n2) * fbytes);
-        pcm_store_b<FMT>(p, y0);
-        pcm_store_b<FMT>(p + fbytes, y1);
-        if (f0 < frames) lmax = fmaxf(lmax, y0);
-        if (f0 + 1 < frames) lmax = fmaxf(lmax, y1);
-    }
+        for (int r = 0; r < 16; r++) {
+            const int n2 = out16(r), n = u + 256 * n2;
+            const c2 b = n2 == 0 ? vb[r] : c2_cmulconj(vb[r], c2_pack(w32(n2)));
+            const float2 s = c2_unpack(c2_add(va[r], b));
+            const float2 t = c2_unpack(tm::pair_of(wr, r));
+            const float y0 = s.x + t.x, y1 = s.y + t.y;
+            tl[r] = c2_sub(va[r], b);
+            const int f0 = 2 * n;
+            char *p = pbase + (size_t)((uint32_t)(512 * n2) * fbytes);
+            pcm_store_b<FMT>(p, y0);
+            pcm_store_b<FMT>(p + fbytes, y1);
+            if (FULL || f0 < frames) lmax = fmaxf(lmax, y0);
+            if (FULL || f0 + 1 < frames) lmax = fmaxf(lmax, y1);
+        }
+    };
+    if (full_path && frames >= N) epilogue(std::true_type{});
+    else epilogue(std::false_type{});
     tm::tm_st<16>(tmem + tm::TAIL, tl);
     return lmax;
 }

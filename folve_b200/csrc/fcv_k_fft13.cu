@@ -47,7 +47,7 @@ fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, i
     if (blockIdx.x == 0 && threadIdx.x == 0) {   // the only thread that needs the stream's descriptor
         const StreamDev s = sel.stream(b);
         // per-block maximum mode: the inverse kernel of this block starts from zero
-        if (reset_max && bt == 0) *s.maxv = 0.0f;
+        if ((reset_max & 1) && bt == 0) *s.maxv = 0.0f;
         s.bmax[bt] = 0.0f;  // this block's maximum starts from zero
     }
     if (frames == 0) {  // silence: its spectrum is zero
@@ -58,8 +58,9 @@ fwd13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int ninp, i
     }
     const size_t wire = FMT == PCM_S16 ? 2 : 4;
     const void *in = reinterpret_cast<const char *>(sel.din(b)) + (size_t)bt * N * ninp * wire;
-    if (h == 0) f13::fwd_half<0, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
-    else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows);
+    const bool fp = NCH == 2 && C == 2 && (reset_max & 2);   // stereo: FCV_FWD_FULL (launch_fwd13_fmt)
+    if (h == 0) f13::fwd_half<0, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows, fp);
+    else f13::fwd_half<1, FMT, NCH, C, 128 * C>(sm, tb, in, ninp, ch0, frames, rows, fp);
 }
 
 // Stereo blocks of a batch with several blocks per step: one CTA = one half of both channels' spectra of one
@@ -181,7 +182,9 @@ __device__ __forceinline__ void block_max_update13(float *dst, float m) {
 // the T blocks (f13::tm, fcv_fft13.cuh); FCV_INV_TMEM=0 selects the kernel without it.
 template <class SEL, int FMT, bool PF, bool TM = false>
 __global__ void __launch_bounds__(F13_INV_NT, f13_min_ctas(F13_INV_NT))
-inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, int T) {
+inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout_flags, int T) {
+    const int nout = nout_flags & 0xffff;          // bit 16: whole blocks skip the per-sample test of the maximum (TM)
+    const bool full_path = (nout_flags >> 16) != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c2 *sm = reinterpret_cast<c2 *>(smem_raw);
     constexpr int NT = F13_INV_NT;
@@ -257,7 +260,7 @@ inv13_stream_kernel(const __grid_constant__ SEL sel, f13::Tables tb, int nout, i
         __syncthreads();
 #endif
         void *dout = reinterpret_cast<char *>(s.dout) + (size_t)bt * N * nout * wire;
-        const float m = TM ? f13::inv_pass_a_tm<FMT>(sm, tmem, dout, nout, o, frames)
+        const float m = TM ? f13::inv_pass_a_tm<FMT>(sm, tmem, dout, nout, o, frames, full_path)
                            : f13::inv_pass_a<FMT, NT>(sm, tb, tail, dout, nout, o, frames);
         lmax = fmaxf(lmax, m);
         block_max_update13(s.bmax + bt, m);
@@ -477,9 +480,11 @@ static void launch_fwd13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
             return;
         }
     }
+    // bit 1 of the last argument: whole blocks take pass A without the per-sample zeroing (FCV_FWD_FULL=0: off)
+    static const int fwd_full = getenv("FCV_FWD_FULL") ? atoi(getenv("FCV_FWD_FULL")) : 1;
     if (f->ninp == 2)
         launch_k(fwd13_stream_kernel<SEL, FMT, 2, 2>, dim3(2, a.cnt, a.T), dim3(256), 2 * f13::HALF_BYTES, q, a.pdl, sel,
-                 f->tb13, f->ninp, a.R, a.T, rm);
+                 f->tb13, f->ninp, a.R, a.T, rm | (fwd_full ? 2 : 0));
     else if (f->ninp == 1)
         launch_k(fwd13_stream_kernel<SEL, FMT, 1, 1>, dim3(2, a.cnt, a.T), dim3(128), f13::HALF_BYTES, q, a.pdl, sel,
                  f->tb13, f->ninp, a.R, a.T, rm);
@@ -529,8 +534,12 @@ static void launch_inv13_fmt(const StepArgs &a, const SEL &sel, cudaStream_t q) 
     const bool use_tm = g_inv_tmem.load(std::memory_order_relaxed);
     if constexpr (!SEL::kSingle && F13_INV_NT == 256) {
         if (use_tm && a.T > 1) {
-            if (pf) inv13_stream_kernel<SEL, FMT, true, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
-            else inv13_stream_kernel<SEL, FMT, false, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, a.f->nout, a.T);
+            // bit 16 of the channel-count argument: whole blocks take the epilogue without the per-sample test of the
+            // maximum (FCV_INV_FULL=0: off)
+            static const int inv_full = getenv("FCV_INV_FULL") ? atoi(getenv("FCV_INV_FULL")) : 1;
+            const int nout_arg = a.f->nout | (inv_full ? 1 << 16 : 0);
+            if (pf) inv13_stream_kernel<SEL, FMT, true, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, nout_arg, a.T);
+            else inv13_stream_kernel<SEL, FMT, false, true><<<grid, 256, smem, q>>>(sel, a.f->tb13, nout_arg, a.T);
             return;
         }
     }
