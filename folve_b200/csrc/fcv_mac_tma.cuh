@@ -6,11 +6,13 @@
 // row feeds all T accumulators, the filter rows slide through a register window.  What
 // changes is who moves the data: one producer warp issues 2 KB bulk copies (one per
 // stream row tile and one for the filter row tile) into a ring of NS shared-memory stages
-// (NS lanes, one ring revolution at a time, a row each), completion is signalled on an
+// (G lanes per pass, a row each: template parameter G below), completion is signalled on an
 // mbarrier per stage, and the four consumer warps only execute
-// try_wait / LDS.128 / FFMA2 / elected arrive.  Loads in flight no longer occupy
-// registers or issue slots (no LDG, no L2 prefetch, no address arithmetic in the math
-// warps), so the pipeline can run NS rows ahead of the arithmetic.
+// try_wait / LDS.128 / FFMA2 / elected arrive -- straight-line code without per-output
+// predicates, 81 instructions per warp and row of which 64 are FFMA2 (see the consumer
+// section).  Loads in flight no longer occupy registers or issue slots (no LDG, no L2
+// prefetch, no address arithmetic in the math warps), so the pipeline runs NS - G rows
+// ahead of the arithmetic.
 //
 //   work item = (spectrum tile of 128 float4 = 2 KB, group of S streams, output), OUTPUT fastest:
 //          the CTAs that run side by side are the outputs of one (tile, stream group).  Where
@@ -148,14 +150,15 @@ mac_tma_kernel(const float2 *__restrict__ xring0, size_t xring_stride, int nstre
     const size_t rowb = (size_t)M4 * 16;
 
     if (warp == CONSUMER_WARPS) {
-        // ---- producer: NS lanes of the warp take the NS rows of one ring revolution, one row
-        // each -- every lane waits for its own stage to be released and issues that row's copies.
-        // The address arithmetic and the barrier hand-shake are executed once per NS rows
-        // instead of once per row: the producer shares its scheduler with consumer warp 0, and
-        // as a single lane walking the rows (~90 instructions each) it, not HBM, paced the kernel.
-        // Row d of every (input, output) pair lives in stage d % NS, so a lane always serves the
-        // same stage and keeps that stage's phase bit; the consumers index the stages of a
-        // T-row chunk with compile-time constants when NS divides T.
+        // ---- producer: GL lanes of the warp take the GL rows of one pass, one row each -- every
+        // lane waits for its own stage to be released and issues that row's copies (the lanes of a
+        // pass leave their waits together, see G above).  The address arithmetic and the barrier
+        // hand-shake are executed once per GL rows instead of once per row: the producer shares its
+        // scheduler with consumer warp 0, and as a single lane walking the rows (~90 instructions
+        // each) it, not HBM, paced the kernel.  Row d of every (input, output) pair lives in stage
+        // d % NS and is issued by lane d % GL, so a stage is always served by the same lane, which
+        // keeps that stage's phase bit; the consumers index the stages of a T-row chunk with
+        // compile-time constants when NS divides T.
         static_assert(NS <= 32, "one lane per stage");
         static_assert(G >= 0 && G <= NS && (G == 0 || NS % G == 0), "lanes per pass: a stage is always served by the same lane");
         constexpr int GL = G > 0 ? G : NS;   // rows whose addresses one pass computes
