@@ -16,9 +16,13 @@ static bool launch_tma(const StepArgs &a, int newest, cudaStream_t q) {
     if (cudaFuncSetAttribute(tma::mac_tma_kernel<T, S, NS, MC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return false;
-    // one CTA per work item; FCV_MAC_PERSIST=n runs a persistent grid of n CTAs per SM instead
-    // (measured 5 % slower on SantaLucia x 1024 streams: 1.05 vs 1.00 ms, profiles/r01_experiments.md)
-    static const int persist = getenv("FCV_MAC_PERSIST") ? atoi(getenv("FCV_MAC_PERSIST")) : 0;
+    // Grid: persistent, MC CTAs per SM walking the items, for filters with one or two outputs; one CTA per work
+    // item otherwise.  Measured with the final kernels (profiles/r02_experiments.md): SantaLucia 0.822 -> 0.811 ms,
+    // crossfeed (ring depth 1: a work item is only 8 rows, the pipeline's cold start per CTA is what the persistent
+    // grid saves) 0.476 -> 0.414 ms, dense 6 x 6 1.40 -> 1.53 ms (the CTAs drift apart and the outputs of a tile no
+    // longer read their shared X rows together).  FCV_MAC_PERSIST=n forces n CTAs per SM (0: never persistent).
+    static const int persist_env = getenv("FCV_MAC_PERSIST") ? atoi(getenv("FCV_MAC_PERSIST")) : -1;
+    const int persist = persist_env >= 0 ? persist_env : (T == 8 && f->nout <= 2 ? MC : 0);
     const int ntiles = M4 / tma::TPB, ngroups = (a.cnt + S - 1) / S, nitems = ntiles * ngroups * f->nout;
     int grid = nitems;
     if (persist > 0 && a.num_sms * persist < nitems) grid = a.num_sms * persist;

@@ -331,6 +331,37 @@ def test_stereo_pair_inverse_kernel_is_bit_identical(fmt):
     f.close()
 
 
+def test_persistent_mac_grid_equals_small_batches():
+    """Stereo filters at 8 blocks per step run the time-tiled MAC as a persistent grid (3 CTAs per SM walking the
+    work items) once a batch has more items than CTA slots (here: 24 streams = 768 items); a batch of two streams
+    (64 items) gets one CTA per item.  Streams are independent, so the big batch must give the bits of the small
+    ones: two steps, int16 wire, a filter whose window does not end on a chunk boundary."""
+    r = _rng(79)
+    spec = FilterSpec(2, 2, 9 * 8192 - 100)
+    spec.add(0, 0, r.standard_normal(9 * 8192 - 100) * 0.003, 0).add(1, 1, r.standard_normal(50000) * 0.003, 300)
+    spec.add(1, 0, r.standard_normal(4000) * 0.003, 8192)
+    f = _engine(spec)
+    N, B, T = spec.fragm, 24, 8
+    x = np.rint(r.uniform(-0.3, 0.3, (2, B, T * N, 2)) * 20000).astype(np.int16)
+    big = capi.Batch(f, B, capi.PCM_S16, capi.PCM_S16, blocks_per_step=T)
+    want = []
+    for k in range(2):
+        big.host_in[:] = x[k]
+        big.process()
+        want.append(big.host_out.copy())
+    wmax = big.get_max().copy()
+    big.close()
+    for s0 in range(0, B, 2):
+        small = capi.Batch(f, 2, capi.PCM_S16, capi.PCM_S16, blocks_per_step=T)
+        for k in range(2):
+            small.host_in[:] = x[k][s0:s0 + 2]
+            small.process()
+            assert np.array_equal(small.host_out, want[k][s0:s0 + 2])
+        assert np.array_equal(small.get_max(), wmax[s0:s0 + 2])
+        small.close()
+    f.close()
+
+
 @pytest.mark.parametrize("fmt", ["f32", "s16", "s24"])
 def test_tensor_memory_transform_kernels_are_bit_identical(fmt):
     """Batches with several blocks per step: the inverse transform that keeps each thread's twiddles and the
