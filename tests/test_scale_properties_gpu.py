@@ -15,12 +15,14 @@ def _load(name):
     return wl, wl.load(capi.Filter(wl.ninp, wl.nout, wl.size, wl.fragm)).commit(0)
 
 
-def test_santalucia_1024_streams_linearity_and_independence():
+@pytest.mark.parametrize("T", [4, 8])
+def test_santalucia_1024_streams_linearity_and_independence(T):
+    """T = 8 is the bench configuration: the time-tiled MAC runs as a persistent grid there (32768 work items)."""
     wl, f = _load("santalucia")
-    N, B, T = wl.fragm, 1024, 4
+    N, B = wl.fragm, 1024
     assert f.partitions == 25 and f.ring_depth == 22 and f.active_rows == 44
     r = np.random.default_rng(1)
-    nsteps = 8                                   # 32 blocks > 22 partitions: the whole ring is exercised
+    nsteps = 32 // T                             # 32 blocks > 22 partitions: the whole ring is exercised
     xa = r.uniform(-0.02, 0.02, (nsteps, 16, T * N, 2)).astype(np.float32)
     xb = r.uniform(-0.02, 0.02, (nsteps, 16, T * N, 2)).astype(np.float32)
     bt = capi.Batch(f, B, blocks_per_step=T)
