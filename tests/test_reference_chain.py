@@ -156,3 +156,62 @@ def test_pooled_processor_reuse_quirk(dirs):
     finally:
         R.drop_pool()
         R.set_reset_is_fresh(False)
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chains.npz")
+
+
+def test_golden_fixture_is_what_the_reference_build_gives(dirs):
+    """tests/golden/chains.npz against the reference build of this checkout, through the committed
+    generator's own cases and inputs: every stored head, tail, maximum and flag bit for bit.  (The GPU
+    suite checks the CUDA engine against the same file; this pins the file to its generator.)"""
+    from golden.make_golden import CASES, case_inputs, summarize
+    g = np.load(GOLDEN)
+    R = H.reference()
+    for name, fdir, lens, gapless, seed in CASES:
+        d, rate, ch, bits = dirs[fdir]
+        conf = [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".conf")][0]
+        fragm = R.load_config(conf, rate, ch)["fragm"]
+        files = case_inputs(fragm, ch, lens, seed)
+        R.drop_pool()
+        outs, mx, flags = R.run_chain(d, rate, ch, bits, files, gapless=gapless)
+        assert list(g[f"{name}/flags"]) == flags, name
+        assert np.array_equal(g[f"{name}/max"], np.array(mx, np.float32)), name
+        for k, y in enumerate(outs):
+            assert y.shape[0] == int(g[f"{name}/{k}/frames"][0]), (name, k)
+            head, tail, s, sa = summarize(y)
+            assert np.array_equal(head, g[f"{name}/{k}/head"]), (name, k)
+            assert np.array_equal(tail, g[f"{name}/{k}/tail"]), (name, k)
+            assert np.array_equal(s, g[f"{name}/{k}/sum"]) and np.array_equal(sa, g[f"{name}/{k}/abssum"]), (name, k)
+
+
+def test_golden_fixture_agrees_with_float64_truth(dirs):
+    """The stored outputs against direct float64 convolution of the regenerated inputs: a gapless chain is
+    one long signal as far as the stored hand-off flags say, a chain without -g starts every file from silence."""
+    from golden.make_golden import CASES, case_inputs
+    g = np.load(GOLDEN)
+    for name, fdir, lens, gapless, seed in CASES:
+        c, h = _impulses(fdir, dirs)
+        ch = dirs[fdir][2]
+        files = case_inputs(c["fragm"], ch, lens, seed)
+        # a file whose flags carry "in" (bit 0) continues its predecessor's signal, any other starts from silence
+        # (tiny_chain: file 1 disappears in file 0's top-up -- quirk 4 -- and file 2 then opens fresh)
+        flags = [int(v) for v in g[f"{name}/flags"]]
+        assert gapless or not any(flags)
+        truths, k = [], 0
+        while k < len(files):
+            e = k + 1
+            while e < len(files) and flags[e] & 1:
+                e += 1
+            t = truth_f64(np.concatenate(files[k:e]), h, c["nout"])
+            truths += np.split(t, np.cumsum([f.shape[0] for f in files[k:e]])[:-1])
+            k = e
+        for k, t in enumerate(truths):
+            n = int(g[f"{name}/{k}/frames"][0])
+            if n == 0:
+                continue                                           # quirk 4: consumed by the predecessor's top-up
+            assert n == t.shape[0], (name, k)
+            fs = max(1.0, np.abs(t).max())
+            assert np.abs(g[f"{name}/{k}/head"] - t[:1024]).max() < 2e-6 * fs, (name, k)
+            assert np.abs(g[f"{name}/{k}/tail"] - t[-1024:]).max() < 2e-6 * fs, (name, k)
+            assert np.allclose(g[f"{name}/{k}/sum"], t.sum(axis=0), atol=1e-5 * n ** 0.5 + 1e-4), (name, k)
