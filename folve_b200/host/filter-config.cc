@@ -77,8 +77,16 @@ int CmdConvolverNew(Parser &ps, const char *args) {
     cfg->fragm = FragmForSize(size);
     if (cfg->filter) {
         // A second /convolver/new: Convproc::configure refuses (not idle) and the
-        // reference reports "Can't initialise convolution engine" as ERR_OTHER.
+        // reference reports "Can't initialise convolution engine" as ERR_OTHER, which
+        // ends the parse "successfully" with the SECOND line's ninp / nout / size / fragm
+        // in the config and the FIRST line's engine behind it.  SoundProcessor::Create
+        // (sound-processor.cc:44-46) then returns NULL if the second line names more
+        // inputs or outputs than the first, and otherwise builds a processor whose
+        // block size and channel counts disagree with its Convproc.  Here such a file
+        // never yields a processor: the filter is dropped.
         syslog(LOG_ERR, "Can't initialise convolution engine\n");
+        fcv_filter_unref(cfg->filter);
+        cfg->filter = nullptr;
         return CFG_ERR_OTHER;
     }
     cfg->filter = fcv_filter_begin(cfg->ninp, cfg->nout, size, (unsigned)cfg->fragm);

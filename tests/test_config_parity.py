@@ -108,3 +108,117 @@ def test_loader_semantics_spot_checks(tmp_path):
     assert h[2000] == 0 and h[2001] == pytest.approx(-0.5 * 2 / np.pi * (0.43 + 0.57 * np.cos(np.pi / 2000)), rel=1e-6)
     assert h[1999] == -h[2001]
     assert (0, 1) in c["pairs"]                 # delay 1000 >= length / 2 = 999: kept
+
+
+def _random_config(r, wavs):
+    """One random jconvolver-style config: mostly well-formed commands with random parameters, sometimes a
+    token damaged, dropped or added, sometimes a command out of order."""
+    ninp, nout = int(r.integers(1, 5)), int(r.integers(1, 5))
+    size = int(r.choice([0, 1, 100, 256, 1000, 5000, 5000, 8192, 20000, 20000]))
+    part = int(r.choice([0, 64, 256, 1000, 1024, 8192]))
+    lines = []
+    if r.random() < 0.9:
+        dens = ["", " 0.5", " 1", " x"][int(r.choice(4, p=[0.6, 0.2, 0.15, 0.05]))]
+        lines.append(f"/convolver/new {ninp} {nout} {part} {size}{dens}")
+
+    def io(n):
+        return int(r.integers(1, n + 1)) if r.random() < 0.975 else int(r.choice([0, n + 1, -1, 65]))
+
+    def num(kind):
+        if r.random() < 0.012:
+            return str(r.choice(["abc", "", "1e", "0x10", "-", "3.5.1", "1,5"]))
+        if kind == "gain":
+            return str(r.choice(["1", "0.5", "-0.25", "1e-1", "2.", ".75", "+1", "-1.0e0"]))
+        return str(int(r.choice([0, 0, 0, 1, 7, 50, 63, 64, 255, 256, 300, 999, 4000, 30000, -1])))
+
+    for _ in range(int(r.integers(0, 12))):
+        c = r.random()
+        if c < 0.35:
+            w = wavs[int(r.integers(len(wavs)))] if r.random() < 0.9 else ("nonexistent.wav", 1, 0)
+            name = w[0] if r.random() < 0.7 else '"' + w[0] + '"'
+            chan = int(r.integers(1, w[1] + 1)) if r.random() < 0.9 else w[1] + 1
+            # offset + length stay inside the file: past its end the reference's read loop (zita-config.cc:146-171)
+            # gets 0 frames for ever and Create never returns (DESIGN section 4)
+            off = int(r.choice([0, 0, 1, 7, w[2] // 2, w[2], w[2] + 1]))
+            length = 0 if r.random() < 0.5 or off >= w[2] else int(r.integers(1, w[2] - off + 1))
+            ln = f"/impulse/read {io(ninp)} {io(nout)} {num('gain')} {num('d')} {off} {length} {chan} {name}"
+        elif c < 0.55:
+            ln = f"/impulse/dirac {io(ninp)} {io(nout)} {num('gain')} {num('d')}"
+        elif c < 0.70:
+            ln = f"/impulse/hilbert {io(ninp)} {io(nout)} {num('gain')} {num('d')} {int(r.choice([0, 63, 64, 100, 999, 4096, 4097]))}"
+        elif c < 0.82:
+            ln = f"/impulse/copy {io(ninp)} {io(nout)} {io(ninp)} {io(nout)}"
+        elif c < 0.88:
+            ln = str(r.choice(["/cd sub", "/cd .", "/cd", '/cd "sub"', "/cd nowhere"]))
+        elif c < 0.93:
+            ln = str(r.choice(["/input/name 1 left", "/output/name 2 right", "/input/name", "/output/name 9 x y z"]))
+        elif c < 0.97:
+            ln = str(r.choice(["# a comment", "", "   ", "\t", "#/impulse/dirac 1 1 1 0", "  # indented comment"]))
+        else:
+            ln = str(r.choice(["/unknown/cmd 1 2", "garbage", " /impulse/dirac 1 1 1 0", "/impulse/dirac", "/convolver/new 2 2 64 100"]))
+        m = r.random()
+        toks = ln.split(" ")
+        if m < 0.02 and len(toks) > 1:
+            toks.pop(int(r.integers(1, len(toks))))
+        elif m < 0.04:
+            toks.append(str(r.choice(["extra", "7", "#c"])))
+        elif m < 0.08:
+            ln = ln.replace(" ", str(r.choice(["  ", "\t", " \t "])))
+            toks = None
+        lines.append(" ".join(toks) if toks is not None else ln)
+    if r.random() < 0.08:
+        lines.insert(0, lines.pop()) if lines else None        # a command in front of /convolver/new
+    end = "\n" if r.random() < 0.9 else ""
+    return ("\r\n" if r.random() < 0.05 else "\n").join(lines) + end
+
+
+def _fuzz_main(root, count=600):
+    from harness_py import write_wav
+    r = np.random.default_rng(2024)
+    d = os.path.join(root, "fuzz")
+    os.makedirs(os.path.join(d, "sub"))
+    wavs = [("mono16.wav", 1, 3000), ("stereo24.wav", 2, 700), ("quad_float.wav", 4, 9000), ("sub/short.wav", 1, 10),
+            ("with space.wav", 2, 257)]
+    for k, (fn, ch, n) in enumerate(wavs):
+        data = np.random.default_rng(50 + k).uniform(-0.5, 0.5, (n, ch)) * np.exp(-np.arange(n) / (n / 4))[:, None]
+        write_wav(os.path.join(d, fn), data, [44100, 48000, 44100, 44100, 96000][k],
+                  ["pcm16", "pcm24", "float", "pcm16", "pcm32"][k])
+    seen = {"created": 0, "failed": 0, "pairs": 0, "second_new": 0}
+    for k in range(count):
+        text = _random_config(r, wavs)
+        conf = os.path.join(d, f"filter-{k}.conf")
+        with open(conf, "w") as f:
+            f.write(text)
+        print(f"config {k}: {text!r}", flush=True)
+        if sum(ln.startswith("/convolver/new") for ln in text.splitlines()) > 1:
+            # a second /convolver/new that is reached: the reference keeps the first line's engine under the second
+            # line's ninp / nout / size / fragm (Create then gives NULL or a mismatched processor); here such a
+            # file never yields a processor (filter-config.cc, DESIGN section 4).  Same verdict from the parser.
+            a, b = H.reference().load_config(conf, 44100, 2), H.product().load_config(conf, 44100, 2)
+            assert a["rc"] == b["rc"] and (b["created"] == 0 or a["created"] == 1)
+            if a["created"] != b["created"]:
+                seen["second_new"] += 1
+                continue
+        a, b = _compare(conf, 44100, 2)
+        seen["created" if a["created"] else "failed"] += 1
+        seen["pairs"] += len(a["pairs"])
+    print("SEEN", seen["created"], seen["failed"], seen["pairs"], flush=True)
+
+
+def test_random_configs_load_identically(tmp_path):
+    """Differential test of the loader against the reference's parser: 600 seeded random configs (well-formed and
+    damaged) must give the same verdict (created or not, error code) and bit-identical impulses for every pair.
+    Runs in a child process with a time limit: a parser that never returns is a failure, not a hung suite."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = f"import sys; sys.path.insert(0, {here!r}); import test_config_parity as T; T._fuzz_main({str(tmp_path)!r})"
+    try:
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240, cwd=here)
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        raise AssertionError("loader did not return on:\n" + "\n".join(out.splitlines()[-1:]))
+    tail = "\n".join(p.stdout.splitlines()[-2:])
+    assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
+    created, failed, pairs = (int(v) for v in p.stdout.splitlines()[-1].split()[1:])
+    assert created > 200 and failed > 200 and pairs > 150, (created, failed, pairs)
