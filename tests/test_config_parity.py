@@ -222,3 +222,31 @@ def test_random_configs_load_identically(tmp_path):
     assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
     created, failed, pairs = (int(v) for v in p.stdout.splitlines()[-1].split()[1:])
     assert created > 200 and failed > 200 and pairs > 150, (created, failed, pairs)
+
+
+def test_quoted_string_scanner_equals_the_reference():
+    """ScanString against the reference's sstring (zita-sstring.cc, compiled unmodified into oracle/_ref) on
+    20 000 random byte strings over the characters that matter to it (quotes, backslashes, blanks, control
+    characters) and on several destination sizes: same return value, same destination bytes."""
+    import ctypes as C
+    ref = C.CDLL(H.REFERENCE_SO)._Z7sstringPKcPci
+    own = C.CDLL(H.PRODUCT_SO)._ZN10folve_b20010ScanStringEPKcPci
+    for f in (ref, own):
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    r = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"\"\"\"'''\\\\\\   \t\nab/.x#", np.uint8)
+    checked = nonzero = 0
+    for k in range(20000):
+        n = int(r.integers(0, 24))
+        src = bytes(r.choice(alphabet, n)) if r.random() < 0.95 else bytes(r.integers(1, 256, n, dtype=np.uint8))
+        size = int(r.choice([1, 2, 3, 5, 8, 64, 1024]))
+        da, db = C.create_string_buffer(b"\xee" * 1100, 1100), C.create_string_buffer(b"\xee" * 1100, 1100)
+        ra, rb = ref(src, da, size), own(src, db, size)
+        assert ra == rb, (src, size, ra, rb)
+        if ra:
+            assert da.raw[:size] == db.raw[:size], (src, size, da.raw[:size], db.raw[:size])
+            nonzero += 1
+        assert da.raw[size:] == db.raw[size:] == b"\xee" * (1100 - size), (src, size)   # nothing written past `size`
+        checked += 1
+    assert nonzero > 5000
