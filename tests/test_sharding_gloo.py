@@ -61,3 +61,29 @@ def test_album_sharding_world2():
     got = dict(q.get() for _ in range(2))
     assert got[0] + got[1] == 37 * 8
     assert min(got.values()) > 0
+
+
+def test_cxx_placement_equals_the_python_rule():
+    """SoundProcessor::DeviceForKey (the in-process placement of the C++ host layer) and sharding.device_for_path
+    (what the ranks of bench.py agree on) are the same function of the album directory: 3000 random keys, non-ASCII
+    names included, 1 to 8 devices.  CRC32 only -- no GPU involved."""
+    import ctypes as C
+
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from folve_b200 import sharding
+    so = os.path.join(ROOT, "folve_b200", "libfolve_host.so")
+    if not os.path.exists(so):
+        pytest.skip("needs folve_b200/libfolve_host.so")
+    f = C.CDLL(so).fh_device_for_key
+    f.restype, f.argtypes = C.c_int, [C.c_char_p, C.c_int]
+    r = np.random.default_rng(5)
+    words = ["music", "Ünïcode", "a b", "日本語", "x" * 200, "1999 - Live", "cd.2", "flac"]
+    used = set()
+    for _ in range(3000):
+        album = "/" + "/".join(words[int(k)] for k in r.integers(0, len(words), int(r.integers(1, 6))))
+        n = int(r.integers(1, 9))
+        want = sharding.device_for_path(album + "/01 - track.flac", n)
+        assert f(album.encode(), n) == want, (album, n)
+        used.add((n, want))
+    assert len(used) == sum(range(1, 9))            # every device of every box size is hit
