@@ -140,3 +140,28 @@ def test_deterministic_signals(signal):
     else:
         x = np.stack([np.where((n // 50) % 2 == 0, 1.0, -1.0), np.where((n // 3) % 2 == 0, -1.0, 1.0)], 1)
     _check(spec, x.astype(np.float32))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_filter_structures(seed):
+    """Random channel counts, sizes (every block size of the fragm rule), overlapping additions at random
+    offsets, links made before and after their source gets data, unused pairs, ragged last block: the oracle
+    against direct float64 convolution."""
+    r = _rng(1000 + seed)
+    ninp, nout = int(r.integers(1, 5)), int(r.integers(1, 5))
+    size = int(r.choice([40, 64, 100, 129, 300, 700, 1500, 3000, 6000, 9000]))
+    spec = FilterSpec(ninp, nout, size)
+    pairs = [(i, o) for i in range(ninp) for o in range(nout)]
+    for _ in range(int(r.integers(1, 9))):
+        i, o = pairs[int(r.integers(len(pairs)))]
+        if r.random() < 0.25:
+            i2, o2 = pairs[int(r.integers(len(pairs)))]
+            if (i2, o2) != (i, o):
+                spec.link(i, o, i2, o2)
+            continue
+        taps = int(r.integers(1, size + 1))
+        i0 = int(r.integers(0, size))
+        spec.add(i, o, r.standard_normal(taps) * 0.3 / np.sqrt(taps), i0)
+    frames = int(r.integers(1, 4)) * spec.fragm + int(r.integers(0, spec.fragm))
+    x = r.uniform(-0.5, 0.5, (frames, ninp)).astype(np.float32)
+    _check(spec, x)
