@@ -250,3 +250,23 @@ def test_quoted_string_scanner_equals_the_reference():
         assert da.raw[size:] == db.raw[size:] == b"\xee" * (1100 - size), (src, size)   # nothing written past `size`
         checked += 1
     assert nonzero > 5000
+
+
+def test_block_size_and_partition_count_for_every_size_class(tmp_path):
+    """/convolver/new over the sizes around every power of two up to MAXSIZE and beyond it: same verdict, block size
+    (zita-fconfig.cc:74-77) and partition count on both sides; the dirac at the last valid position lands in the last
+    partition on both.  (From 2^31 on the reference reads the size into a signed int and its range check no longer
+    sees it; this loader refuses everything above MAXSIZE.)"""
+    sizes = [0, 1, 2, 3]
+    for k in range(5, 21):
+        sizes += [2 ** k - 1, 2 ** k, 2 ** k + 1]
+    sizes += [0x100000 + 2, 2 ** 30, 2 ** 31 - 1]
+    seen = set()
+    for size in sizes:
+        conf = tmp_path / f"filter-{size}.conf"
+        conf.write_text(f"/convolver/new 1 1 0 {size}\n/impulse/dirac 1 1 0.5 {max(size - 1, 0)}\n")
+        a, b = _compare(str(conf), 44100, 1)
+        if a["created"]:
+            seen.add(a["fragm"])
+            assert a["fragm"] == b["fragm"] and a["npar"] == b["npar"]
+    assert seen == {64, 128, 256, 512, 1024, 2048, 4096, 8192}
