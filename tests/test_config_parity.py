@@ -189,17 +189,18 @@ def _fuzz_main(root, count=600):
         conf = os.path.join(d, f"filter-{k}.conf")
         with open(conf, "w") as f:
             f.write(text)
-        print(f"config {k}: {text!r}", flush=True)
+        rate, ch = (44100, 96000)[k % 2], (2, 1, 6)[k % 3]       # what Create() is called with
+        print(f"config {k} ({rate} Hz, {ch} channels): {text!r}", flush=True)
         if sum(ln.startswith("/convolver/new") for ln in text.splitlines()) > 1:
             # a second /convolver/new that is reached: the reference keeps the first line's engine under the second
             # line's ninp / nout / size / fragm (Create then gives NULL or a mismatched processor); here such a
             # file never yields a processor (filter-config.cc).  Same verdict from the parser.
-            a, b = H.reference().load_config(conf, 44100, 2), H.product().load_config(conf, 44100, 2)
+            a, b = H.reference().load_config(conf, rate, ch), H.product().load_config(conf, rate, ch)
             assert a["rc"] == b["rc"] and (b["created"] == 0 or a["created"] == 1)
             if a["created"] != b["created"]:
                 seen["second_new"] += 1
                 continue
-        a, b = _compare(conf, 44100, 2)
+        a, b = _compare(conf, rate, ch)
         seen["created" if a["created"] else "failed"] += 1
         seen["pairs"] += len(a["pairs"])
     print("SEEN", seen["created"], seen["failed"], seen["pairs"], flush=True)
