@@ -104,3 +104,46 @@ def test_reference_callers_on_the_b200_engine(library, gapless, pre_buffer):
             assert mx == pytest.approx(mxr, abs=2e-6), p
     assert worst <= 4, worst
     assert n_off <= 0.03 * n_all
+
+
+@pytest.mark.skipif(not (D.have_refstack() and H.have_reference()), reason="needs oracle/_ref (make -C oracle ref refstack)")
+def test_random_albums_reference_filesystem_equals_the_restated_caller(tmp_path):
+    """The same comparison over 12 random albums of a mono 22.05 kHz library with the block size of 256 frames:
+    track lengths drawn from the classes the hand-off logic distinguishes (whole blocks, a few frames more,
+    one frame short of a block, shorter than a block, a single frame), gapless."""
+    filters = tmp_path / "filters"
+    dirs = make_filter_dirs(filters)
+    d, rate, ch, bits = dirs["tiny"]
+    N = 256
+    r = np.random.default_rng(31)
+    music = tmp_path / "music"
+    albums = {}
+    for a in range(12):
+        lengths = []
+        for _ in range(int(r.integers(2, 7))):
+            k = int(r.integers(0, 4))
+            lengths.append(max(1, [k * N, k * N + int(r.integers(1, 40)), (k + 1) * N - 1, int(r.integers(2, N)), 1]
+                                  [int(r.integers(0, 5))]))
+        name = f"album{a:02d}"
+        os.makedirs(music / name)
+        albums[name] = []
+        for k, n in enumerate(lengths):
+            x = _noise(n, ch, 0.25, 1000 * a + k)
+            write_wav(str(music / name / f"{k + 1:02d}.wav"), x, rate, "pcm16")
+            albums[name].append((f"/{name}/{k + 1:02d}.wav", x))
+    R = H.reference()
+    R.drop_pool()
+    R.set_reset_is_fresh(True)
+    m = D.Mount(D.REFSTACK_SO, str(music), str(filters), "tiny", gapless=True)
+    handed = 0
+    for name, tracks in albums.items():
+        got = [(p,) + m.read(p, ch)[:3] for (p, _) in tracks]
+        ys, mx, flags = R.run_chain(d, rate, ch, bits, [x for (_, x) in tracks], gapless=True,
+                                    out_format=H.SF_FORMAT_PCM_24)
+        for (p, y, fl, m_out), yr, fr in zip(got, ys, flags):
+            assert fl & 4, p
+            assert y.shape == yr.shape, (p, [x.shape[0] for (_, x) in tracks])
+            assert np.array_equal(y, yr), p
+            assert (fl & 3) == fr, (p, fl, fr, [x.shape[0] for (_, x) in tracks])
+            handed += fr & 1
+    assert handed >= 10
