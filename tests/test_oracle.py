@@ -165,3 +165,47 @@ def test_random_filter_structures(seed):
     frames = int(r.integers(1, 4)) * spec.fragm + int(r.integers(0, spec.fragm))
     x = r.uniform(-0.5, 0.5, (frames, ninp)).astype(np.float32)
     _check(spec, x)
+
+
+@pytest.mark.parametrize("nreal", [8, 16, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 65536])
+def test_fft_stand_in_against_float64(nreal):
+    """oracle/fft_oracle.c stands in for FFTW's r2c / c2r (unnormalised, forward sign -1): against numpy's float64
+    transforms at float32 accuracy, round trip == nreal * x, DC / Nyquist imaginary parts ignored by c2r, inputs left
+    untouched.  Sizes: 2 * fragm for every block size of the fragm rule, and the ends of the plan's range."""
+    import ctypes as C
+    from oracle_py import lib
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    L.offt_plan_create.restype, L.offt_plan_create.argtypes = C.c_void_p, [C.c_int]
+    L.offt_plan_destroy.restype, L.offt_plan_destroy.argtypes = None, [C.c_void_p]
+    for f in (L.offt_r2c, L.offt_c2r):
+        f.restype, f.argtypes = None, [C.c_void_p, fp, fp]
+    p = L.offt_plan_create(nreal)
+    assert p
+    r = _rng(nreal)
+    x = r.uniform(-1, 1, nreal).astype(np.float32)
+    x0 = x.copy()
+    X = np.zeros(nreal + 2, np.float32)
+    L.offt_r2c(p, x.ctypes.data_as(fp), X.ctypes.data_as(fp))
+    assert np.array_equal(x, x0)
+    want = np.fft.rfft(x.astype(np.float64))
+    got = X[0::2].astype(np.float64) + 1j * X[1::2].astype(np.float64)
+    rms = np.sqrt(np.mean(np.abs(want) ** 2))
+    assert np.abs(got - want).max() < 4e-6 * rms * np.log2(nreal)
+    assert X[1] == 0 and X[nreal + 1] == 0
+    Xd = X.copy()
+    Xd[1], Xd[nreal + 1] = 123.0, -7.0                   # must be ignored
+    Xd0 = Xd.copy()
+    y = np.zeros(nreal, np.float32)
+    L.offt_c2r(p, Xd.ctypes.data_as(fp), y.ctypes.data_as(fp))
+    assert np.array_equal(Xd, Xd0)
+    assert np.abs(y / nreal - x).max() < 2e-6 * np.log2(nreal)
+    # a spectrum of its own: c2r against irfft
+    Z = (r.standard_normal(nreal // 2 + 1) + 1j * r.standard_normal(nreal // 2 + 1))
+    Z[0], Z[-1] = Z[0].real, Z[-1].real
+    Zi = np.zeros(nreal + 2, np.float32)
+    Zi[0::2], Zi[1::2] = Z.real, Z.imag
+    L.offt_c2r(p, Zi.ctypes.data_as(fp), y.ctypes.data_as(fp))
+    zt = np.fft.irfft(Zi[0::2].astype(np.float64) + 1j * Zi[1::2].astype(np.float64), nreal) * nreal
+    assert np.abs(y - zt).max() < 4e-6 * np.sqrt(np.mean(zt ** 2)) * np.log2(nreal)
+    L.offt_plan_destroy(p)
