@@ -713,6 +713,20 @@ int fh_config_impulse(fh_config *c, int inp, int out, float *dst, int capacity) 
 #endif
 }
 
+// The files LoadFilterConfig stamped for the staleness check (every /impulse/read file that was reached):
+// returns their number, *current = 1 while none of them changed (mtime in nanoseconds, size, existence).
+// The reference has no such record (sound-processor.cc:129-133, TODO): -1 there.
+int fh_config_impulse_stamps(const fh_config *c, int *current) {
+#if FOLVE_HARNESS_REFERENCE
+    (void)c;
+    *current = 1;
+    return -1;
+#else
+    *current = folve_b200::StampsCurrent(c->cfg.impulse_files) ? 1 : 0;
+    return (int)c->cfg.impulse_files.size();
+#endif
+}
+
 void fh_config_close(fh_config *c) {
 #if !FOLVE_HARNESS_REFERENCE
     if (c && c->cfg.filter) fcv_filter_unref(c->cfg.filter);

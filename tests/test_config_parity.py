@@ -271,3 +271,61 @@ def test_block_size_and_partition_count_for_every_size_class(tmp_path):
             seen.add(a["fragm"])
             assert a["fragm"] == b["fragm"] and a["npar"] == b["npar"]
     assert seen == {64, 128, 256, 512, 1024, 2048, 4096, 8192}
+
+
+def test_impulse_files_are_stamped_for_the_staleness_check(tmp_path):
+    """SURVEY 8(f)4 / the reference's TODO at sound-processor.cc:129-133, host side without a GPU: the loader records
+    every file an /impulse/read line reached -- the missing one included, not the one behind the line parsing stopped
+    at -- and the record goes stale when one of them is rewritten with the same size within the same second, changes
+    size, disappears, or when the missing one appears."""
+    import ctypes as C
+    import time
+    from harness_py import write_wav
+    d = tmp_path / "stale"
+    (d / "sub").mkdir(parents=True)
+    ir = np.random.default_rng(1).uniform(-0.5, 0.5, (300, 1))
+    write_wav(str(d / "a.wav"), ir, 44100, "pcm16")
+    write_wav(str(d / "sub" / "b.wav"), ir[::-1], 44100, "pcm16")
+    conf = d / "filter-44100.conf"
+    conf.write_text("/convolver/new 2 2 64 1000\n/impulse/read 1 1 1 0 0 0 1 a.wav\n/cd sub\n/impulse/read 2 2 1 0 0 0 1 b.wav\n"
+                    "/impulse/dirac 1 2 0.1 5\n/impulse/read 2 1 1 0 0 0 1 later.wav\n/impulse/read 1 2 1 0 0 0 1 never-reached.wav\n")
+    L = H.product().L
+    L.fh_config_impulse_stamps.restype = C.c_int
+    L.fh_config_impulse_stamps.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.fh_config_open.restype = C.c_void_p
+
+    def load():
+        return C.c_void_p(L.fh_config_open(str(conf).encode(), 44100, 2))
+
+    def state(h):
+        cur = C.c_int(-1)
+        return L.fh_config_impulse_stamps(h, C.byref(cur)), cur.value
+
+    h = load()
+    assert state(h) == (3, 1)                       # a.wav, sub/b.wav, sub/later.wav (missing: parsing stops there)
+    time.sleep(0.01)
+    write_wav(str(d / "a.wav"), ir * 0.5, 44100, "pcm16")          # same size, same second, new content
+    assert state(h) == (3, 0)
+    L.fh_config_close(h)
+    h = load()
+    assert state(h) == (3, 1)
+    write_wav(str(d / "sub" / "later.wav"), ir, 44100, "pcm16")     # the missing file appears
+    assert state(h) == (3, 0)
+    L.fh_config_close(h)
+    h = load()
+    assert state(h) == (4, 1)                       # now the line after it is reached as well
+    write_wav(str(d / "sub" / "b.wav"), ir[:100], 44100, "pcm16")   # size change
+    assert state(h) == (4, 0)
+    L.fh_config_close(h)
+    h = load()
+    os.remove(d / "a.wav")
+    assert state(h) == (4, 0)
+    L.fh_config_close(h)
+    R = H.reference().L
+    R.fh_config_impulse_stamps.restype = C.c_int
+    R.fh_config_impulse_stamps.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    R.fh_config_open.restype = C.c_void_p
+    hr = C.c_void_p(R.fh_config_open(str(conf).encode(), 44100, 2))
+    cur = C.c_int(0)
+    assert R.fh_config_impulse_stamps(hr, C.byref(cur)) == -1       # the reference keeps no such record
+    R.fh_config_close(hr)
